@@ -1,0 +1,166 @@
+/* wildfire.h -- C ABI of libwildfire_b200.so
+ *
+ * B200-native (sm_100a) batched replacement for the reference's environment
+ * step: Simulation/forest_fire.py + Simulation/environment.py of
+ * dashdeckers/Wildfire-Control-Python.  One handle owns N independent
+ * environments on one GPU; every call steps / resets all of them in one launch.
+ *
+ * FFI precedent in the reference: pyastar/pyastar.py:9-22 binds one extern "C"
+ * symbol of pyastar/astar.cpp:41-44 through ctypes with caller-allocated output
+ * arrays.  This header keeps that style: plain pointers and sizes, int status
+ * codes, no C++ or torch types.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - "dev" pointers are device pointers on the handle's GPU, owned by the caller
+ *     (torch tensors); the library owns only the environments' internal planes.
+ *   - All *_dev calls are asynchronous on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the legacy default stream).  A handle is not thread-safe.
+ *   - Grid indexing follows the reference: cell (x, y) of env n lives at
+ *     [n][x][y], x is the SLOW axis (environment.py: env[x, y, layer]).
+ *   - Return value: WF_OK (0) or a negative error code; wf_last_error() gives text.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA
+ *     device wf_create fails with WF_ERR_CUDA.
+ */
+#ifndef WILDFIRE_H
+#define WILDFIRE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_ABI_VERSION 1
+
+enum {
+    WF_OK = 0,
+    WF_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+    WF_ERR_CUDA = -2,    /* CUDA runtime error (text in wf_last_error) */
+    WF_ERR_STATE = -3    /* call not valid in the handle's current state */
+};
+
+/* Observation element type written by wf_step / wf_rollout. */
+enum { WF_OBS_U8 = 0, WF_OBS_F32 = 1 };
+
+/* Cell types -- Simulation/utility.py:128-140. */
+enum { WF_GRASS = 0, WF_FIRE = 1, WF_BURNT = 2, WF_DIRT = 3, WF_WATER = 4 };
+
+/* Replaces the module-global METADATA dict (Simulation/constants.py:30-47) and the
+ * `grass` cell parameters (Simulation/utility.py:94-102).  Same names, same meaning. */
+typedef struct wf_config {
+    int32_t width, height;     /* METADATA['width'/'height']; 10 <= W, H (utility.py:68), W >= H */
+    int32_t n_actions;         /* actions 0..3 = N,S,E,W; 4 = dig toggle iff allow_dig_toggle; else no-op */
+    int32_t a_speed;           /* fire ticks once every a_speed steps (forest_fire.py:40-43) */
+    int32_t allow_dig_toggle;
+    int32_t make_rivers;       /* reset_map river (environment.py:69-95), drawn from the RESET stream */
+    int32_t containment_wins;  /* kept for parity: a no-op in the reference (environment.py:365-366) */
+    int32_t wind_random;       /* METADATA['wind'] == "random" (environment.py:188-190) */
+    int32_t wind_x, wind_y;    /* else METADATA['wind'] = [wind_speed, (wind_x, wind_y)] */
+    int32_t fuel;              /* grass['fuel'], 1..255 */
+    int32_t radius;            /* grass['radius']; only 1 (the 4-neighbour stencil) is implemented */
+    int32_t extra_ignitions;   /* World.set_fire_to() calls right after reset(), IGNITE stream */
+    int32_t auto_reset;        /* 1: an env that returns done is reset inside the same step */
+    double wind_speed;
+    double death_penalty, contained_bonus, default_reward;
+    double heat, threshold;    /* grass['heat'], grass['threshold'] */
+    uint64_t seed;             /* key of the shared Philox4x32-10 stream */
+    int64_t env_id_base;       /* global id of env 0 (multi-GPU sharding: counter = env_id_base + n) */
+} wf_config;
+
+/* Optional per-env overrides for wf_reset (parity injection / scripted starts). */
+typedef struct wf_init {
+    int32_t ax, ay;            /* agent start cell; ax < 0 = draw from the RESET stream */
+} wf_init;
+
+/* Per-env scalars exposed by wf_get_scalars (int32 x WF_NSCALARS per env). */
+enum {
+    WF_S_ALIVE = 0,    /* len(World.agents) == 1 */
+    WF_S_AX, WF_S_AY,  /* agents[0].x / .y (last position once dead) */
+    WF_S_DEAD,         /* Agent.dead */
+    WF_S_DIGGING,      /* Agent.digging */
+    WF_S_VISIBLE,      /* agent_pos layer holds a 1 at (ax, ay) -- quirk Q1 */
+    WF_S_RUNNING,      /* World.RUNNING */
+    WF_S_FIRE_AT_BORDER,
+    WF_S_LATCHED,      /* containment bonus already paid (border_points empty, quirk Q4) */
+    WF_S_EPISODE, WF_S_T,
+    WF_S_WIND_ID,      /* index into the handle's wind table */
+    WF_S_WIND_X, WF_S_WIND_Y,
+    WF_S_N_BURNING,    /* len(World.burning_cells) after the last step */
+    WF_S_RESERVED,
+    WF_NSCALARS = 16
+};
+
+typedef struct wf_env wf_env; /* opaque handle */
+
+/* ---- lifetime ------------------------------------------------------------------ */
+void wf_default_config(wf_config* cfg, int32_t size);
+int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out);
+void wf_destroy(wf_env* env);
+const char* wf_last_error(void);
+int wf_abi_version(void);
+/* Name of the kernel family chosen for this geometry: "warp" (W,H <= 32) or "tile". */
+const char* wf_kernel_family(const wf_env* env);
+
+/* ---- ForestFire.reset() -- forest_fire.py:52-54 -> World.reset environment.py:186-212 ----
+ * mask_dev: N bytes, reset env n iff mask[n] != 0 (NULL = all).  init_dev: N wf_init or NULL.
+ * obs_dev (may be NULL): receives World.get_state() of every env, [N][W][H][3]. */
+int wf_reset(wf_env* env, const uint8_t* mask_dev, const wf_init* init_dev,
+             void* obs_dev, int32_t obs_dtype, void* stream);
+
+/* ---- ForestFire.step(action) -- forest_fire.py:30-49 -----------------------------
+ * actions_dev: N int32.  obs_dev: [N][W][H][3] (NULL = skip).  reward_dev: N float64
+ * (World.get_reward, environment.py:342-390).  done_dev: N bytes (not World.RUNNING). */
+int wf_step(wf_env* env, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype,
+            double* reward_dev, uint8_t* done_dev, void* stream);
+
+/* K consecutive steps in ONE launch, state resident on chip between steps (warp family).
+ * actions_dev: [K][N] int32, or NULL = draw action t from the ACTION stream (what the
+ * oracle's wfo_stream_action does).  obs_dev [K][N][W][H][3], reward_dev [K][N],
+ * done_dev [K][N]; any of the three may be NULL.  Requires auto_reset or tolerates
+ * finished envs by freezing them (reward 0, done 1). */
+int wf_rollout(wf_env* env, int32_t k_steps, const int32_t* actions_dev, void* obs_dev,
+               int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream);
+
+/* Host-buffer variant of wf_step (what a CPU-side caller of the reference would bind):
+ * copies actions H2D, steps, copies obs/reward/done D2H and synchronises.  Buffers should
+ * be page-locked for full PCIe rate; pageable memory works but is slower. */
+int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32_t obs_dtype,
+                 double* reward_host, uint8_t* done_host);
+
+/* ---- state access (parity injection, checkpointing) --------------------------------
+ * Canonical planes, device pointers, any may be NULL:
+ *   type/burning/fm_inf/fuel/apos: [N][W][H] uint8;  hits: [N][W][H][4] uint8 = number of
+ *   heat quanta received from direction d (0 N,1 S,2 E,3 W as seen from the source), so
+ *   that temp = sum_d hits[d] * coef[wind_id][d]  (environment.py:286-290);
+ *   scalars: [N][WF_NSCALARS] int32. */
+int wf_get_state(wf_env* env, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, uint8_t* fuel,
+                 uint8_t* hits, uint8_t* apos, int32_t* scalars, void* stream);
+int wf_set_state(wf_env* env, const uint8_t* type, const uint8_t* burning, const uint8_t* fm_inf,
+                 const uint8_t* fuel, const uint8_t* hits, const int32_t* scalars, void* stream);
+/* World.set_fire_to(cell) on selected envs: cells_dev [N][2] int32 (x, y), x < 0 = skip. */
+int wf_set_fire_to(wf_env* env, const int32_t* cells_dev, void* stream);
+/* World.get_state() without stepping. */
+int wf_get_obs(wf_env* env, void* obs_dev, int32_t obs_dtype, void* stream);
+
+/* Heat quanta table: coef[wind_id][4] float64 (host pointer), n_wind entries (1 or 27). */
+int wf_get_wind_table(const wf_env* env, double* coef_host, double* speed_host,
+                      int32_t* vec_host, int32_t* n_wind);
+
+/* Episode statistics accumulated on device since creation / last wf_stats_reset:
+ * out_host[0]=env-steps [1]=episodes ended [2]=agent deaths [3]=containments [4]=burn-outs
+ * [5]=fire ticks.  Synchronises `stream`. */
+int wf_stats(wf_env* env, int64_t out_host[8], void* stream);
+int wf_stats_reset(wf_env* env, void* stream);
+
+/* Self-test hook: one Philox4x32-10 block computed ON THE DEVICE (ctr[4] then key[2] in, 4 words out),
+ * so the device generator can be pinned to the Random123 known-answer vectors. */
+int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_host[4]);
+
+/* How many kernels of this library the handle has launched (bench.py's gpu_launches). */
+int64_t wf_launch_count(const wf_env* env);
+/* Introspection for DESIGN.md / bench roofline: bytes of internal state per env. */
+int64_t wf_state_bytes_per_env(const wf_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WILDFIRE_H */

@@ -1,0 +1,215 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures recorded from the
+Python reference and against the C oracle on the same seeded inputs.  Bit-exact on type /
+burning / fm_inf / fuel / agent / fire_at_border / obs / reward / done; temp within 1e-9 on grass.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wf_oracle as wo
+from tests.golden_util import env_cfg, expected_obs, golden_names, load_golden
+from tests.gpu_util import TEMP_TOL, compare_states, make_pair, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from wildfire_control_python_b200 import _lib as L
+    return L
+
+
+KATS = [
+    ((0, 0, 0, 0, 0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+    ((0xFFFFFFFF,) * 6, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0),
+     (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+]
+
+
+@pytest.mark.parametrize("ctr_key,want", KATS)
+def test_device_philox_kat(ctr_key, want):
+    L = _lib()
+    inp = (C.c_uint32 * 6)(*ctr_key)
+    out = (C.c_uint32 * 4)()
+    L.check(L.lib().wf_philox_kat(0, inp, out))
+    assert tuple(out) == want
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_reproduces_reference_golden(name):
+    """Env 0 of a 3-env batch must follow the trajectory the Python reference produced."""
+    g = load_golden(name)
+    cfg = env_cfg(g)
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    L = _lib()
+    gpu = BatchedForestFire(3, **cfg)
+    F = len(g["kind"])
+    mask = torch.tensor([1, 0, 0], dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        tag = f"{name} frame {f}"
+        if g["kind"][f] == 0:
+            obs = gpu.reset() if f == 0 else gpu.reset(mask=mask)
+        else:
+            a = int(g["action"][f])
+            obs, rew, done, _ = gpu.step(torch.tensor([a, a, a], dtype=torch.int32, device="cuda"))
+            assert float(rew[0]) == float(g["reward"][f]), f"{tag}: reward {float(rew[0])} != {g['reward'][f]}"
+            assert bool(done[0]) == bool(g["done"][f]), f"{tag}: done"
+        st = {k: to_np(v)[0] for k, v in gpu.get_state().items()}
+        for k in ("type", "burning", "fm_inf", "fuel", "apos"):
+            assert np.array_equal(st[k], g[k][f]), f"{tag}: plane {k}\ngpu=\n{st[k].T}\nref=\n{g[k][f].T}"
+        sc = st["scalars"]
+        assert sc[L.S_ALIVE] == g["alive"][f], tag
+        if g["alive"][f]:
+            assert (sc[L.S_AX], sc[L.S_AY]) == (g["ax"][f], g["ay"][f]), tag
+        assert sc[L.S_FIRE_AT_BORDER] == g["fire_at_border"][f], tag
+        assert sc[L.S_RUNNING] == g["running"][f], tag
+        assert (sc[L.S_WIND_X], sc[L.S_WIND_Y]) == (g["wind_x"][f], g["wind_y"][f]), tag
+        assert gpu.wind_speed_table[sc[L.S_WIND_ID]] == g["wind_speed"][f], tag
+        grass = g["type"][f] == 0
+        assert np.abs(st["temp"] - g["temp"][f])[grass].max(initial=0.0) <= TEMP_TOL, f"{tag}: temp"
+        assert np.array_equal(to_np(obs)[0], expected_obs(g, f)), f"{tag}: obs"
+
+
+SCENARIOS = [
+    dict(width=14, height=14, seed=101),
+    dict(width=10, height=10, seed=102, allow_dig_toggle=True, n_actions=6),
+    dict(width=20, height=20, seed=103, wind="random", make_rivers=True),
+    dict(width=16, height=16, seed=104, a_speed=2, wind=[0.85, (1, 0)], extra_ignitions=2),
+    dict(width=32, height=32, seed=105, wind=[0.85, (-1, 1)], extra_ignitions=5),
+    dict(width=17, height=13, seed=106, wind=[0.7, (0, 1)]),
+    dict(width=11, height=11, seed=107, fuel=40, threshold=5.0, heat=0.35),
+]
+
+
+@pytest.mark.parametrize("cfg", SCENARIOS, ids=lambda c: f"{c['width']}x{c['height']}_s{c['seed']}")
+def test_step_matches_oracle_batch(cfg):
+    """37 envs (ragged vs the 2-or-1 envs-per-warp packing), stream actions, explicit masked resets."""
+    N, STEPS = 37, 220
+    gpu, orc = make_pair(N, cfg)
+    obs = gpu.reset()
+    for e in orc:
+        e.reset()
+    compare_states("reset", gpu, orc, obs=obs)
+    for s in range(STEPS):
+        acts = [e.random_action() for e in orc]
+        frozen = [not e.planes()["running"] for e in orc]
+        obs, rew, done, _ = gpu.step(torch.tensor(acts, dtype=torch.int32, device="cuda"))
+        rew, done = to_np(rew), to_np(done)
+        for i, e in enumerate(orc):
+            if frozen[i]:
+                assert rew[i] == 0.0 and done[i]
+                continue
+            _, r, d, _ = e.step(acts[i])
+            assert rew[i] == r, f"step {s} env {i}: reward {rew[i]} != {r}"
+            assert bool(done[i]) == d, f"step {s} env {i}: done"
+        if s % 7 == 0 or s == STEPS - 1:
+            compare_states(f"step {s}", gpu, orc, obs=obs)
+        if s % 25 == 24:  # reset the finished envs, like a caller of the reference would
+            m = np.array([not e.planes()["running"] for e in orc], np.uint8)
+            if m.any():
+                obs = gpu.reset(mask=torch.from_numpy(m).cuda())
+                for i in np.nonzero(m)[0]:
+                    orc[i].reset()
+                compare_states(f"masked reset after step {s}", gpu, orc, obs=obs)
+
+
+@pytest.mark.parametrize("cfg", [dict(width=14, height=14, seed=201),
+                                 dict(width=12, height=12, seed=202, wind="random", make_rivers=True, a_speed=2)],
+                         ids=["c2", "rivers_wind_aspeed2"])
+def test_fused_rollout_matches_oracle(cfg):
+    """wf_rollout: K steps in one launch, actions from the ACTION stream, auto-reset on done."""
+    N, K = 67, 300
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    obs, rew, done = gpu.rollout(K)
+    obs, rew, done = to_np(obs), to_np(rew), to_np(done)
+    n_done = 0
+    for i, e in enumerate(orc):
+        for k in range(K):
+            o, r, d, _ = e.step(e.random_action())
+            assert rew[k, i] == r, f"env {i} step {k}: reward {rew[k, i]} != {r}"
+            assert bool(done[k, i]) == d, f"env {i} step {k}: done"
+            if d:
+                o = e.reset()
+                n_done += 1
+            assert np.array_equal(obs[k, i], o), f"env {i} step {k}: obs"
+    assert n_done > N  # several episodes per env on average
+    compare_states("after rollout", gpu, orc)
+    st = gpu.stats()
+    assert st["episodes"] == n_done and st["env_steps"] == N * K
+
+
+def test_rollout_equals_repeated_step():
+    cfg = dict(width=14, height=14, seed=301)
+    N, K = 33, 64
+    a, _ = make_pair(N, cfg, auto_reset=True)
+    b, _ = make_pair(N, cfg, auto_reset=True)
+    a.reset(); b.reset()
+    acts = torch.randint(0, 4, (K, N), dtype=torch.int32, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    obs_a, rew_a, done_a = a.rollout(K, actions=acts)
+    for k in range(K):
+        o, r, d, _ = b.step(acts[k])
+        assert torch.equal(o, obs_a[k]) and torch.equal(r, rew_a[k]) and torch.equal(d, done_a[k]), k
+
+
+def test_f32_observation_equals_u8():
+    cfg = dict(width=14, height=14, seed=401)
+    a, _ = make_pair(9, cfg, auto_reset=True)
+    b, _ = make_pair(9, cfg, auto_reset=True, obs_dtype=torch.float32)
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa.float(), ob)
+    for _ in range(50):
+        acts = torch.randint(0, 4, (9,), dtype=torch.int32, device="cuda")
+        oa, ra, da, _ = a.step(acts)
+        ob, rb, db, _ = b.step(acts)
+        assert ob.dtype == torch.float32 and torch.equal(oa.float(), ob) and torch.equal(ra, rb) and torch.equal(da, db)
+
+
+def test_step_host_roundtrip():
+    cfg = dict(width=14, height=14, seed=501)
+    gpu, orc = make_pair(16, cfg)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    for s in range(30):
+        acts = np.array([e.random_action() for e in orc], np.int32)
+        obs, rew, done, _ = gpu.step_host(acts)
+        for i, e in enumerate(orc):
+            if not e.planes()["running"]:
+                continue
+            o, r, d, _ = e.step(int(acts[i]))
+            assert rew[i] == r and bool(done[i]) == d and np.array_equal(obs[i], o)
+
+
+def test_set_state_free_burn_known_answer():
+    """14x14 free burn, agent parked at (7, 10): done at tick 185, nothing left."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    gpu = BatchedForestFire(2, width=14, height=14, seed=0)
+    gpu.reset(starts=torch.tensor([[7, 10], [7, 10]], dtype=torch.int32))
+    noop = torch.full((2,), 5, dtype=torch.int32, device="cuda")
+    t = 0
+    while True:
+        _, rew, done, _ = gpu.step(noop)
+        t += 1
+        if bool(done[0]):
+            break
+        assert float(rew[0]) == -1.0
+    assert t == 185
+    st = gpu.get_state()
+    assert int((st["type"][0] == 0).sum()) == 0
+    assert float(rew[0]) == 0.0
+
+
+def test_errors_are_reported_not_thrown():
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    L = _lib()
+    with pytest.raises(L.WildfireError, match="radius"):
+        BatchedForestFire(1, width=10, height=10, radius=2)
+    with pytest.raises(L.WildfireError, match=">= 10"):
+        BatchedForestFire(1, width=8, height=8)
+    with pytest.raises(L.WildfireError, match="HEIGHT-1"):
+        BatchedForestFire(1, width=10, height=12)

@@ -1,0 +1,280 @@
+"""BatchedForestFire -- N independent forest-fire environments stepped by one CUDA launch.
+
+Host-side mirror of the reference's ``ForestFire`` facade (Simulation/forest_fire.py:18-106):
+same ``reset()`` / ``step(action)`` contract, same METADATA key names, same action set, reward and
+done logic -- but every call acts on a whole batch and every array is a torch CUDA tensor.
+PyTorch only provides device memory and the current stream; all arithmetic happens in
+libwildfire_b200.so (hand-written sm_100a kernels) behind the C ABI of include/wildfire.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import make_metadata
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def config_from_metadata(m: dict) -> "_lib.WfConfig":
+    """METADATA-style dict (constants.make_metadata) -> the C ABI's wf_config."""
+    cfg = _lib.WfConfig()
+    cfg.width, cfg.height = int(m["width"]), int(m["height"])
+    cfg.n_actions, cfg.a_speed = int(m["n_actions"]), int(m["a_speed"])
+    cfg.allow_dig_toggle = int(bool(m["allow_dig_toggle"]))
+    cfg.make_rivers = int(bool(m["make_rivers"]))
+    cfg.containment_wins = int(bool(m["containment_wins"]))
+    if m["wind"] == "random":
+        cfg.wind_random = 1
+        cfg.wind_speed, cfg.wind_x, cfg.wind_y = 0.0, 0, 0
+    else:
+        cfg.wind_random = 0
+        cfg.wind_speed = float(m["wind"][0])
+        cfg.wind_x, cfg.wind_y = int(m["wind"][1][0]), int(m["wind"][1][1])
+    cfg.fuel, cfg.radius = int(m["fuel"]), int(m["radius"])
+    cfg.extra_ignitions = int(m["extra_ignitions"])
+    cfg.auto_reset = int(bool(m["auto_reset"]))
+    cfg.death_penalty = float(m["death_penalty"])
+    cfg.contained_bonus = float(m["contained_bonus"])
+    cfg.default_reward = float(m["default_reward"])
+    cfg.heat, cfg.threshold = float(m["heat"]), float(m["threshold"])
+    cfg.seed = int(m["seed"])
+    cfg.env_id_base = int(m["env_id_base"])
+    return cfg
+
+
+class BatchedForestFire:
+    """``n_envs`` reference environments on one GPU.
+
+    Parameters follow Simulation/constants.py:30-47 (``width``, ``height``, ``wind``, ``a_speed``,
+    ``n_actions``, ``make_rivers``, ``allow_dig_toggle``, rewards) and Simulation/utility.py:94-102
+    (``heat``, ``fuel``, ``threshold``), plus ``seed`` (key of the shared Philox stream),
+    ``extra_ignitions``, ``auto_reset`` and ``env_id_base`` (global id of env 0 when a batch is
+    sharded over several GPUs).
+
+    Observations are ``[N, W, H, 3]`` (x is the slow axis, exactly ``World.get_state``'s layout,
+    environment.py:399-402) so ``obs.flatten(1)`` feeds the reference's ``Flatten`` + ``Dense``
+    networks unchanged (DQN.py:209-212).
+    """
+
+    def __init__(self, n_envs: int, device=None, obs_dtype: torch.dtype = torch.uint8, **metadata):
+        if not torch.cuda.is_available():
+            raise _lib.WildfireError("BatchedForestFire needs a CUDA device (no CPU fallback)")
+        self.METADATA = make_metadata(**metadata)
+        m = self.METADATA
+        self.n_envs = int(n_envs)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.width, self.height = int(m["width"]), int(m["height"])
+        self.n_actions = int(m["n_actions"])
+        if obs_dtype not in (torch.uint8, torch.float32):
+            raise ValueError("obs_dtype must be torch.uint8 or torch.float32")
+        self.obs_dtype = obs_dtype
+        self._obs_code = _lib.WF_OBS_U8 if obs_dtype == torch.uint8 else _lib.WF_OBS_F32
+
+        L = _lib.lib()
+        self._cfg = config_from_metadata(m)
+        h = C.c_void_p()
+        _lib.check(L.wf_create(C.byref(self._cfg), self.n_envs, self.device.index, C.byref(h)))
+        self._h = h
+        self.kernel_family = L.wf_kernel_family(h).decode()
+
+        N, W, H = self.n_envs, self.width, self.height
+        with torch.cuda.device(self.device):
+            self._obs = torch.empty((N, W, H, 3), dtype=obs_dtype, device=self.device)
+            self._reward = torch.empty((N,), dtype=torch.float64, device=self.device)
+            self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        nw = C.c_int32()
+        coef = (C.c_double * (27 * 4))()
+        speed = (C.c_double * 27)()
+        vec = (C.c_int32 * 54)()
+        _lib.check(L.wf_get_wind_table(h, coef, speed, vec, C.byref(nw)))
+        self.wind_coef = np.array(coef[: nw.value * 4]).reshape(nw.value, 4)
+        self.wind_speed_table = np.array(speed[: nw.value])
+        self.wind_vector_table = np.array(vec[: nw.value * 2]).reshape(nw.value, 2)
+        self._host = None
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().wf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_i32(self, t, shape):
+        t = torch.as_tensor(t, device=self.device)
+        if t.dtype != torch.int32:
+            t = t.to(torch.int32)
+        t = t.contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, mask=None, starts=None) -> torch.Tensor:
+        """``ForestFire.reset()`` (forest_fire.py:52-54) for every env, or those with ``mask[n] != 0``.
+
+        ``starts``: optional ``[N, 2]`` int agent start cells (negative x = draw from the stream).
+        Returns the observation batch ``[N, W, H, 3]``.
+        """
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if tuple(m.shape) != (self.n_envs,):
+                raise ValueError("mask must have shape [n_envs]")
+        s = None if starts is None else self._as_i32(starts, (self.n_envs, 2))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_reset(self._h, _ptr(m), _ptr(s), _ptr(self._obs), self._obs_code, self._stream()))
+        return self._obs
+
+    def step(self, actions):
+        """``ForestFire.step(action)`` (forest_fire.py:30-49) for the whole batch.
+
+        ``actions``: ``[N]`` ints, 0..3 = N,S,E,W; 4 = dig toggle iff ``allow_dig_toggle``; other = no-op.
+        Returns ``(obs [N,W,H,3], reward float64 [N], done bool [N], {})``.  The returned tensors are
+        the handle's persistent buffers (overwritten by the next call).
+        """
+        a = self._as_i32(actions, (self.n_envs,))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_step(self._h, _ptr(a), _ptr(self._obs), self._obs_code, _ptr(self._reward),
+                                          _ptr(self._done), self._stream()))
+        return self._obs, self._reward, self._done.view(torch.bool), {}
+
+    def rollout(self, k_steps: int, actions=None, obs: bool = True, out=None):
+        """``k_steps`` consecutive ``step`` calls in one launch (state stays on chip in between).
+
+        ``actions``: ``[K, N]`` ints or ``None`` = draw from the shared ACTION stream.
+        ``out``: optional ``(obs_or_None, reward, done_u8)`` buffers to write into.
+        Returns ``(obs [K,N,W,H,3] or None, reward [K,N], done [K,N])``.
+        """
+        K, N = int(k_steps), self.n_envs
+        a = None if actions is None else self._as_i32(actions, (K, N))
+        with torch.cuda.device(self.device):
+            if out is not None:
+                o, r, d = out
+            else:
+                o = (torch.empty((K, N, self.width, self.height, 3), dtype=self.obs_dtype, device=self.device)
+                     if obs else None)
+                r = torch.empty((K, N), dtype=torch.float64, device=self.device)
+                d = torch.empty((K, N), dtype=torch.uint8, device=self.device)
+            _lib.check(_lib.lib().wf_rollout(self._h, K, _ptr(a), _ptr(o), self._obs_code, _ptr(r), _ptr(d),
+                                             self._stream()))
+        return o, r, d.view(torch.bool)
+
+    def step_host(self, actions):
+        """Host-buffer step through ``wf_step_host``: H2D actions, step, D2H obs/reward/done, sync.
+
+        Uses page-locked staging arrays owned by this object; returns numpy views of them.
+        """
+        if self._host is None:
+            N, W, H = self.n_envs, self.width, self.height
+            self._host = dict(
+                actions=torch.empty((N,), dtype=torch.int32).pin_memory(),
+                obs=torch.empty((N, W, H, 3), dtype=self.obs_dtype).pin_memory(),
+                reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
+                done=torch.empty((N,), dtype=torch.uint8).pin_memory())
+        hb = self._host
+        hb["actions"].numpy()[:] = actions
+        _lib.check(_lib.lib().wf_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), self._obs_code,
+                                           _ptr(hb["reward"]), _ptr(hb["done"])))
+        return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), {}
+
+    def observe(self) -> torch.Tensor:
+        """``World.get_state()`` (environment.py:399-402) without stepping."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_get_obs(self._h, _ptr(self._obs), self._obs_code, self._stream()))
+        return self._obs
+
+    # ------------------------------------------------------------------------------------------
+    def get_state(self) -> dict:
+        """Canonical planes of every env (``env[x, y, layer]`` order) as torch tensors.
+
+        ``temp`` is rebuilt from the exact per-direction hit counters (``hits``) with the env's heat
+        quanta: temp = sum_d hits[d] * coef[wind_id][d] (environment.py:286-290); it is only
+        meaningful on grass cells.
+        """
+        N, W, H = self.n_envs, self.width, self.height
+        dev = self.device
+        out = {k: torch.empty((N, W, H), dtype=torch.uint8, device=dev)
+               for k in ("type", "burning", "fm_inf", "fuel", "apos")}
+        out["hits"] = torch.empty((N, W, H, 4), dtype=torch.uint8, device=dev)
+        out["scalars"] = torch.empty((N, _lib.WF_NSCALARS), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().wf_get_state(self._h, _ptr(out["type"]), _ptr(out["burning"]), _ptr(out["fm_inf"]),
+                                               _ptr(out["fuel"]), _ptr(out["hits"]), _ptr(out["apos"]),
+                                               _ptr(out["scalars"]), self._stream()))
+        coef = torch.as_tensor(self.wind_coef, device=dev)[out["scalars"][:, _lib.S_WIND_ID].long()]  # [N, 4]
+        out["temp"] = (out["hits"].double() * coef[:, None, None, :]).sum(-1)
+        return out
+
+    def set_state(self, type=None, burning=None, fm_inf=None, fuel=None, hits=None, scalars=None):
+        """Overwrite planes / scalars (parity injection, checkpoint restore).  ``None`` = keep."""
+        N, W, H = self.n_envs, self.width, self.height
+
+        def u8(t, shape):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, device=self.device).to(torch.uint8).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"expected shape {shape}, got {tuple(t.shape)}")
+            return t
+
+        t_, b_, f_, fu_ = (u8(v, (N, W, H)) for v in (type, burning, fm_inf, fuel))
+        h_ = u8(hits, (N, W, H, 4))
+        s_ = None if scalars is None else self._as_i32(scalars, (N, _lib.WF_NSCALARS))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_set_state(self._h, _ptr(t_), _ptr(b_), _ptr(f_), _ptr(fu_), _ptr(h_), _ptr(s_),
+                                               self._stream()))
+
+    def set_fire_to(self, cells):
+        """``World.set_fire_to(cell)`` (environment.py:233-246); ``cells``: ``[N, 2]`` ints, x < 0 = skip."""
+        c = self._as_i32(cells, (self.n_envs, 2))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_set_fire_to(self._h, _ptr(c), self._stream()))
+
+    def stats(self) -> dict:
+        buf = (C.c_int64 * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_stats(self._h, buf, self._stream()))
+        keys = ("env_steps", "episodes", "deaths", "contained", "burnouts", "ticks")
+        return {k: int(buf[i]) for i, k in enumerate(keys)}
+
+    def reset_stats(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().wf_stats_reset(self._h, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().wf_launch_count(self._h))
+
+    @property
+    def state_bytes_per_env(self) -> int:
+        return int(_lib.lib().wf_state_bytes_per_env(self._h))
+
+    @staticmethod
+    def heat_coefficients(wind_speed: float, wind_vector, heat: float = 0.3):
+        """Heat quantum per direction (N, S, E, W as seen from the burning cell), the reference's
+        own expression: ``wind_speed * heat * (angle + distance) ** -1`` (environment.py:260-290)."""
+        wx, wy = wind_vector
+        out = []
+        for cx, cy in ((0, -1), (0, 1), (1, 0), (-1, 0)):
+            angle = abs(math.atan2(wx * cy - wy * cx, wx * cx + wy * cy))
+            out.append(wind_speed * heat * (angle + 1) ** (-1))
+        return out

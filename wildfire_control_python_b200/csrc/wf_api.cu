@@ -1,0 +1,520 @@
+// wf_api.cu -- the C ABI of libwildfire_b200.so (include/wildfire.h): handle lifetime, argument
+// checks, wind table, state import/export kernels and dispatch to the two kernel families.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "wf_families.cuh"
+
+
+using namespace wf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define WF_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(WF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+struct wf_env {
+    wf_config cfg;
+    int32_t N, device;
+    bool tile;
+    DevState st;
+    StepCfg sc;
+    WindTable wind_host;
+    int32_t n_wind;
+    WindTable* wind_dev;
+    int32_t a_iter;  // METADATA['a_speed_iter']: one per handle, not reset by reset() (Q8)
+    int64_t launches;
+    TileState* tstate;
+    // wf_step_host staging
+    cudaStream_t hstream;
+    int32_t* h_actions;
+    void* h_obs;
+    size_t h_obs_bytes;
+    double* h_reward;
+    uint8_t* h_done;
+};
+
+// ---------------------------------------------------------------------------------------------
+// canonical-plane export / import (parity injection, checkpoint) -- works for both layouts
+__global__ void get_state_kernel(DevState s, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, uint8_t* fuel,
+                                 uint8_t* hits, uint8_t* apos) {
+    const size_t cells = (size_t)s.N * s.W * s.H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i % s.H), x = (int)((i / s.H) % s.W), env = (int)(i / ((size_t)s.H * s.W));
+        const int w = y >> 5, b = y & 31;
+        auto bit = [&](int p) { return (s.planes[word_index(s, p, env, x, w)] >> b) & 1u; };
+        if (type) type[i] = bit(P_G) ? WF_GRASS : bit(P_F) ? WF_FIRE : bit(P_BT) ? WF_BURNT : bit(P_D) ? WF_DIRT : WF_WATER;
+        if (burning) burning[i] = (uint8_t)bit(P_B);
+        if (fm_inf) fm_inf[i] = (uint8_t)bit(P_I);
+        if (fuel) {
+            uint32_t f = 0;
+            for (int q = 0; q < s.FB; ++q) f |= bit(P_FU0 + q) << q;
+            fuel[i] = (uint8_t)f;
+        }
+        if (hits) reinterpret_cast<uint32_t*>(hits)[i] = s.hits[i];
+        if (apos) {
+            const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+            apos[i] = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && sc[WF_S_AY] == y) ? 1 : 0;
+        }
+    }
+}
+
+__global__ void set_state_kernel(DevState s, const uint8_t* type, const uint8_t* burning, const uint8_t* fm_inf,
+                                 const uint8_t* fuel, const uint8_t* hits) {
+    const size_t words = (size_t)s.N * s.W * s.HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % s.HW), x = (int)((i / s.HW) % s.W), env = (int)(i / ((size_t)s.HW * s.W));
+        const int y0 = w * 32, ny = min(32, s.H - y0);
+        const size_t cell0 = ((size_t)env * s.W + x) * s.H + y0;
+        if (type) {
+            uint32_t m[5] = {0, 0, 0, 0, 0};
+            for (int b = 0; b < ny; ++b) {
+                const int t = type[cell0 + b];
+                m[t < 5 ? t : 0] |= 1u << b;
+            }
+            s.planes[word_index(s, P_G, env, x, w)] = m[0];
+            s.planes[word_index(s, P_F, env, x, w)] = m[1];
+            s.planes[word_index(s, P_BT, env, x, w)] = m[2];
+            s.planes[word_index(s, P_D, env, x, w)] = m[3];
+            s.planes[word_index(s, P_WT, env, x, w)] = m[4];
+        }
+        if (burning) {
+            uint32_t m = 0;
+            for (int b = 0; b < ny; ++b) m |= (burning[cell0 + b] ? 1u : 0u) << b;
+            s.planes[word_index(s, P_B, env, x, w)] = m;
+        }
+        if (fm_inf) {
+            uint32_t m = 0;
+            for (int b = 0; b < ny; ++b) m |= (fm_inf[cell0 + b] ? 1u : 0u) << b;
+            s.planes[word_index(s, P_I, env, x, w)] = m;
+        }
+        if (fuel) {
+            for (int q = 0; q < s.FB; ++q) {
+                uint32_t m = 0;
+                for (int b = 0; b < ny; ++b) m |= ((uint32_t)(fuel[cell0 + b] >> q) & 1u) << b;
+                s.planes[word_index(s, P_FU0 + q, env, x, w)] = m;
+            }
+        }
+        if (hits)
+            for (int b = 0; b < ny; ++b) s.hits[cell0 + b] = reinterpret_cast<const uint32_t*>(hits)[cell0 + b];
+    }
+}
+
+__global__ void set_scalars_kernel(DevState s, const int32_t* scalars) {
+    const size_t n = (size_t)s.N * WF_NSCALARS;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        s.scal[i] = scalars[i];
+}
+
+// World.set_fire_to(cell), environment.py:233-246, one thread per env.
+__global__ void set_fire_kernel(DevState s, const int32_t* cells) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.N) return;
+    const int x = cells[2 * env], y = cells[2 * env + 1];
+    if (x < 0 || x >= s.W || y < 0 || y >= s.H) return;
+    const int w = y >> 5;
+    const uint32_t bit = 1u << (y & 31);
+    s.planes[word_index(s, P_G, env, x, w)] &= ~bit;
+    s.planes[word_index(s, P_BT, env, x, w)] &= ~bit;
+    s.planes[word_index(s, P_D, env, x, w)] &= ~bit;
+    s.planes[word_index(s, P_WT, env, x, w)] &= ~bit;
+    s.planes[word_index(s, P_F, env, x, w)] |= bit;
+    s.planes[word_index(s, P_B, env, x, w)] |= bit;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    if (x == 0 || x == s.W - 1 || y == 0 || y == s.H - 1) sc[WF_S_FIRE_AT_BORDER] = 1;
+    sc[WF_S_N_BURNING] += 1;
+}
+
+// World.get_state() without stepping, generic layout (used by wf_get_obs).
+__global__ void get_obs_kernel(DevState s, void* obs, int dtype) {
+    const size_t cells = (size_t)s.N * s.W * s.H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i % s.H), x = (int)((i / s.H) % s.W), env = (int)(i / ((size_t)s.H * s.W));
+        const int w = y >> 5, b = y & 31;
+        const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+        const uint32_t a = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && sc[WF_S_AY] == y) ? 1u : 0u;
+        const uint32_t f = (s.planes[word_index(s, P_F, env, x, w)] >> b) & 1u;
+        const uint32_t d = ((s.planes[word_index(s, P_I, env, x, w)] >> b) & 1u) ^ 1u;
+        if (dtype == WF_OBS_U8) {
+            uint8_t* o = static_cast<uint8_t*>(obs) + 3 * i;
+            o[0] = (uint8_t)a; o[1] = (uint8_t)f; o[2] = (uint8_t)d;
+        } else {
+            float* o = static_cast<float*>(obs) + 3 * i;
+            o[0] = (float)a; o[1] = (float)f; o[2] = (float)d;
+        }
+    }
+}
+
+__global__ void philox_kat_kernel(const uint32_t* in, uint32_t* out) {
+    philox4x32_10(in[0], in[1], in[2], in[3], in[4], in[5], out);
+}
+
+// ---------------------------------------------------------------------------------------------
+static void build_wind_table(const wf_config& c, WindTable& t, int32_t& n) {
+    // World.apply_heat_from_to / get_distance_and_angle, environment.py:260-290, evaluated once per
+    // (wind, direction) with the same libm calls CPython makes (math.atan2, float ** -1 -> pow).
+    static const int DX[4] = {0, 0, 1, -1}, DY[4] = {-1, 1, 0, 0};
+    std::memset(&t, 0, sizeof(t));
+    auto fill = [&](int id, double speed, int wx, int wy) {
+        t.speed[id] = speed; t.wx[id] = wx; t.wy[id] = wy;
+        for (int d = 0; d < 4; ++d) {
+            const int cx = DX[d], cy = DY[d];
+            const double angle = std::fabs(std::atan2((double)(wx * cy - wy * cx), (double)(wx * cx + wy * cy)));
+            const double env_factor = std::pow(angle + 1.0, -1.0);
+            t.coef[id][d] = speed * c.heat * env_factor;
+        }
+        const double c0 = t.coef[id][0];
+        t.uniform[id] = (t.coef[id][1] == c0 && t.coef[id][2] == c0 && t.coef[id][3] == c0) ? 1 : 0;
+        t.kmin[id] = 0x7fffffff;
+        if (t.uniform[id] && c0 > 0.0) {  // the reference adds the quantum once per hit, in float64
+            double temp = 0.0;
+            for (int k = 1; k <= 1024; ++k) {
+                temp += c0;
+                if (temp > c.threshold) { t.kmin[id] = k; break; }
+            }
+        }
+    };
+    if (c.wind_random) {
+        static const double speeds[3] = {0.0, 0.7, 0.85};  // environment.py:189
+        n = 27;
+        for (int si = 0; si < 3; ++si)
+            for (int wx = -1; wx <= 1; ++wx)
+                for (int wy = -1; wy <= 1; ++wy) fill(si * 9 + (wx + 1) * 3 + (wy + 1), speeds[si], wx, wy);
+    } else {
+        n = 1;
+        fill(0, c.wind_speed, c.wind_x, c.wind_y);
+    }
+}
+
+extern "C" {
+
+void wf_default_config(wf_config* c, int32_t size) {  // constants.py:30-47, utility.py:94-102
+    std::memset(c, 0, sizeof(*c));
+    c->width = c->height = size;
+    c->n_actions = 4;
+    c->a_speed = 1;
+    c->wind_speed = 0.54;
+    c->death_penalty = -1000.0;
+    c->contained_bonus = 1000.0;
+    c->default_reward = -1.0;
+    c->heat = 0.3;
+    c->threshold = 3.0;
+    c->fuel = 20;
+    c->radius = 1;
+}
+
+const char* wf_last_error(void) { return g_err.c_str(); }
+int wf_abi_version(void) { return WF_ABI_VERSION; }
+
+int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out) {
+    if (!cfg || !out) return fail(WF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const wf_config& c = *cfg;
+    if (n_envs < 1) return fail(WF_ERR_INVALID, "n_envs must be >= 1");
+    if (c.width < 10 || c.height < 10)
+        return fail(WF_ERR_INVALID, "width and height must be >= 10 (get_agent_location asserts it, utility.py:68)");
+    if (c.width < c.height)
+        return fail(WF_ERR_INVALID, "width < height: the reference's border_points use [HEIGHT-1, y] "
+                                    "(environment.py:222) and raise on such maps");
+    if (c.radius != 1) return fail(WF_ERR_INVALID, "only grass radius 1 (4-neighbour stencil) is implemented");
+    if (c.fuel < 1 || c.fuel > 255) return fail(WF_ERR_INVALID, "fuel must be in 1..255");
+    if (c.a_speed < 1) return fail(WF_ERR_INVALID, "a_speed must be >= 1");
+    if (c.n_actions < 1) return fail(WF_ERR_INVALID, "n_actions must be >= 1");
+    if (c.extra_ignitions < 0) return fail(WF_ERR_INVALID, "extra_ignitions must be >= 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(WF_ERR_CUDA, "no CUDA device: libwildfire_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(WF_ERR_INVALID, "bad device index");
+    WF_CUDA(cudaSetDevice(device));
+
+    wf_env* e = new (std::nothrow) wf_env();
+    if (!e) return fail(WF_ERR_INVALID, "out of host memory");
+    std::memset(static_cast<void*>(e), 0, sizeof(*e));
+    e->cfg = c;
+    e->N = n_envs;
+    e->device = device;
+    e->tile = (c.width > 32 || c.height > 32);
+    e->a_iter = c.a_speed;
+    DevState& s = e->st;
+    s.N = n_envs; s.W = c.width; s.H = c.height;
+    s.HW = (c.height + 31) / 32;
+    s.RS = e->tile ? c.width : (c.width <= 16 ? 16 : 32);
+    s.FB = c.fuel <= 31 ? 5 : 8;
+    s.NP = 7 + s.FB + (e->tile ? tile_extra_planes() : 0);
+    StepCfg& sc = e->sc;
+    sc.n_actions = c.n_actions; sc.a_speed = c.a_speed; sc.allow_dig_toggle = c.allow_dig_toggle;
+    sc.make_rivers = c.make_rivers; sc.wind_random = c.wind_random; sc.fuel = c.fuel;
+    sc.extra_ignitions = c.extra_ignitions; sc.auto_reset = c.auto_reset;
+    sc.death_penalty = c.death_penalty; sc.contained_bonus = c.contained_bonus;
+    sc.default_reward = c.default_reward; sc.threshold = c.threshold;
+    sc.key0 = (uint32_t)(c.seed & 0xffffffffu); sc.key1 = (uint32_t)(c.seed >> 32);
+    sc.env_id_base = c.env_id_base;
+    build_wind_table(c, e->wind_host, e->n_wind);
+
+    const size_t plane_words = (size_t)s.NP * s.N * s.RS * s.HW;
+    const size_t cells = (size_t)s.N * s.W * s.H;
+    auto cleanup = [&](int code, const std::string& m) { wf_destroy(e); return fail(code, m); };
+#define WF_CUDA_C(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) return cleanup(WF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    WF_CUDA_C(cudaMalloc(&s.planes, plane_words * sizeof(uint32_t)));
+    WF_CUDA_C(cudaMemset(s.planes, 0, plane_words * sizeof(uint32_t)));
+    WF_CUDA_C(cudaMalloc(&s.hits, cells * sizeof(uint32_t)));
+    WF_CUDA_C(cudaMemset(s.hits, 0, cells * sizeof(uint32_t)));
+    WF_CUDA_C(cudaMalloc(&s.scal, (size_t)s.N * WF_NSCALARS * sizeof(int32_t)));
+    WF_CUDA_C(cudaMemset(s.scal, 0, (size_t)s.N * WF_NSCALARS * sizeof(int32_t)));
+    WF_CUDA_C(cudaMalloc(&s.stats, ST_N * sizeof(unsigned long long)));
+    WF_CUDA_C(cudaMemset(s.stats, 0, ST_N * sizeof(unsigned long long)));
+    WF_CUDA_C(cudaMalloc(&e->wind_dev, sizeof(WindTable)));
+    WF_CUDA_C(cudaMemcpy(e->wind_dev, &e->wind_host, sizeof(WindTable), cudaMemcpyHostToDevice));
+    s.wind = e->wind_dev;
+    if (e->tile) WF_CUDA_C(tile_create(&e->tstate, s, sc));
+    // episode counter starts at -1 so that the first reset() opens episode 0 (like the oracle)
+    {
+        std::string init((size_t)s.N * WF_NSCALARS * sizeof(int32_t), '\0');
+        int32_t* p = reinterpret_cast<int32_t*>(&init[0]);
+        for (int i = 0; i < s.N; ++i) p[(size_t)i * WF_NSCALARS + WF_S_EPISODE] = -1;
+        WF_CUDA_C(cudaMemcpy(s.scal, p, init.size(), cudaMemcpyHostToDevice));
+    }
+#undef WF_CUDA_C
+    *out = e;
+    return WF_OK;
+}
+
+void wf_destroy(wf_env* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->tstate) tile_destroy(e->tstate);
+    cudaFree(e->st.planes); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
+    cudaFree(e->wind_dev);
+    cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
+    if (e->hstream) cudaStreamDestroy(e->hstream);
+    delete e;
+}
+
+const char* wf_kernel_family(const wf_env* e) { return e ? (e->tile ? "tile" : "warp") : ""; }
+int64_t wf_launch_count(const wf_env* e) { return e ? e->launches : 0; }
+int64_t wf_state_bytes_per_env(const wf_env* e) {
+    if (!e) return 0;
+    const DevState& s = e->st;
+    return (int64_t)s.NP * s.RS * s.HW * 4 + (int64_t)s.W * s.H * 4 + WF_NSCALARS * 4;
+}
+
+static int check_obs(const void* obs, int32_t dtype) {
+    if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32) return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8 or WF_OBS_F32");
+    if (obs && (reinterpret_cast<uintptr_t>(obs) & 15u)) return fail(WF_ERR_INVALID, "obs pointer must be 16-byte aligned");
+    return WF_OK;
+}
+
+static uint32_t magic_for(int H) { return (uint32_t)((0x100000000ull + (uint64_t)H - 1) / (uint64_t)H); }
+
+int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* obs_dev, int32_t obs_dtype,
+             void* stream) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->tile) {
+        TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, 1};
+        WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
+    } else {
+        WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H)};
+        WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
+        e->launches += 1;
+    }
+    return WF_OK;
+}
+
+static int advance_a_iter(wf_env* e, int k_steps) {
+    int it = e->a_iter;
+    for (int k = 0; k < k_steps; ++k) {
+        it -= 1;
+        if (it == 0) it = e->cfg.a_speed;
+    }
+    return it;
+}
+
+int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype,
+               double* reward_dev, uint8_t* done_dev, void* stream) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    if (k_steps < 1) return fail(WF_ERR_INVALID, "k_steps must be >= 1");
+    if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->tile) {
+        const DevState& s = e->st;
+        const size_t esz = (size_t)s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
+        if (!actions_dev) return fail(WF_ERR_INVALID, "tile family: wf_rollout needs explicit actions");
+        for (int k = 0; k < k_steps; ++k) {  // tile family: one tick per launch group
+            int it = e->a_iter - 1;
+            const int do_tick = (it == 0);
+            if (do_tick) it = e->cfg.a_speed;
+            TileIO io{actions_dev + (size_t)k * s.N,
+                      obs_dev ? static_cast<char*>(obs_dev) + (size_t)k * s.N * esz : nullptr,
+                      reward_dev ? reward_dev + (size_t)k * s.N : nullptr,
+                      done_dev ? done_dev + (size_t)k * s.N : nullptr,
+                      nullptr, nullptr, obs_dtype, do_tick, 0};
+            WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
+            e->a_iter = it;
+        }
+        return WF_OK;
+    }
+    WarpIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0,
+              magic_for(e->st.H)};
+    WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
+    e->launches += 1;
+    e->a_iter = advance_a_iter(e, k_steps);
+    return WF_OK;
+}
+
+int wf_step(wf_env* e, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype, double* reward_dev,
+            uint8_t* done_dev, void* stream) {
+    if (!actions_dev) return fail(WF_ERR_INVALID, "wf_step: actions_dev is null");
+    return wf_rollout(e, 1, actions_dev, obs_dev, obs_dtype, reward_dev, done_dev, stream);
+}
+
+int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
+                 uint8_t* done_host) {
+    if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
+    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32) return fail(WF_ERR_INVALID, "bad obs_dtype");
+    WF_CUDA(cudaSetDevice(e->device));
+    const DevState& s = e->st;
+    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
+    if (!e->hstream) WF_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+    if (!e->h_actions) {
+        WF_CUDA(cudaMalloc(&e->h_actions, (size_t)s.N * sizeof(int32_t)));
+        WF_CUDA(cudaMalloc(&e->h_reward, (size_t)s.N * sizeof(double)));
+        WF_CUDA(cudaMalloc(&e->h_done, (size_t)s.N));
+    }
+    if (obs_host && e->h_obs_bytes < obs_bytes) {
+        cudaFree(e->h_obs);
+        e->h_obs = nullptr;
+        WF_CUDA(cudaMalloc(&e->h_obs, obs_bytes));
+        e->h_obs_bytes = obs_bytes;
+    }
+    WF_CUDA(cudaMemcpyAsync(e->h_actions, actions_host, (size_t)s.N * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
+    int rc = wf_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, obs_dtype, e->h_reward, e->h_done, e->hstream);
+    if (rc != WF_OK) return rc;
+    if (obs_host) WF_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, obs_bytes, cudaMemcpyDeviceToHost, e->hstream));
+    if (reward_host) WF_CUDA(cudaMemcpyAsync(reward_host, e->h_reward, (size_t)s.N * sizeof(double), cudaMemcpyDeviceToHost, e->hstream));
+    if (done_host) WF_CUDA(cudaMemcpyAsync(done_host, e->h_done, (size_t)s.N, cudaMemcpyDeviceToHost, e->hstream));
+    WF_CUDA(cudaStreamSynchronize(e->hstream));
+    return WF_OK;
+}
+
+static int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+int wf_get_state(wf_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, uint8_t* fuel, uint8_t* hits,
+                 uint8_t* apos, int32_t* scalars, void* stream) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevState& s = e->st;
+    if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
+    if (type || burning || fm_inf || fuel || hits || apos) {
+        get_state_kernel<<<grid_for((size_t)s.N * s.W * s.H), 256, 0, st>>>(s, type, burning, fm_inf, fuel, hits, apos);
+        WF_CUDA(cudaGetLastError());
+        e->launches += 1;
+    }
+    if (scalars)
+        WF_CUDA(cudaMemcpyAsync(scalars, s.scal, (size_t)s.N * WF_NSCALARS * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return WF_OK;
+}
+
+int wf_set_state(wf_env* e, const uint8_t* type, const uint8_t* burning, const uint8_t* fm_inf, const uint8_t* fuel,
+                 const uint8_t* hits, const int32_t* scalars, void* stream) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevState& s = e->st;
+    if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
+    if (type || burning || fm_inf || fuel || hits) {
+        set_state_kernel<<<grid_for((size_t)s.N * s.W * s.HW), 256, 0, st>>>(s, type, burning, fm_inf, fuel, hits);
+        WF_CUDA(cudaGetLastError());
+        e->launches += 1;
+    }
+    if (scalars) {
+        set_scalars_kernel<<<grid_for((size_t)s.N * WF_NSCALARS), 256, 0, st>>>(s, scalars);
+        WF_CUDA(cudaGetLastError());
+        e->launches += 1;
+    }
+    if (e->tile) WF_CUDA(tile_after_set_state(e->tstate, e->st, e->sc, st, &e->launches));
+    return WF_OK;
+}
+
+int wf_set_fire_to(wf_env* e, const int32_t* cells_dev, void* stream) {
+    if (!e || !cells_dev) return fail(WF_ERR_INVALID, "null argument");
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    set_fire_kernel<<<(e->N + 127) / 128, 128, 0, st>>>(e->st, cells_dev);
+    WF_CUDA(cudaGetLastError());
+    e->launches += 1;
+    if (e->tile) WF_CUDA(tile_after_set_state(e->tstate, e->st, e->sc, st, &e->launches));
+    return WF_OK;
+}
+
+int wf_get_obs(wf_env* e, void* obs_dev, int32_t obs_dtype, void* stream) {
+    if (!e || !obs_dev) return fail(WF_ERR_INVALID, "null argument");
+    if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
+    WF_CUDA(cudaSetDevice(e->device));
+    const DevState& s = e->st;
+    get_obs_kernel<<<grid_for((size_t)s.N * s.W * s.H), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, obs_dev, obs_dtype);
+    WF_CUDA(cudaGetLastError());
+    e->launches += 1;
+    return WF_OK;
+}
+
+int wf_get_wind_table(const wf_env* e, double* coef_host, double* speed_host, int32_t* vec_host, int32_t* n_wind) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    if (n_wind) *n_wind = e->n_wind;
+    for (int i = 0; i < e->n_wind; ++i) {
+        if (coef_host) for (int d = 0; d < 4; ++d) coef_host[4 * i + d] = e->wind_host.coef[i][d];
+        if (speed_host) speed_host[i] = e->wind_host.speed[i];
+        if (vec_host) { vec_host[2 * i] = e->wind_host.wx[i]; vec_host[2 * i + 1] = e->wind_host.wy[i]; }
+    }
+    return WF_OK;
+}
+
+int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_host[4]) {
+    if (!ctr_key_host || !out_host) return fail(WF_ERR_INVALID, "null argument");
+    WF_CUDA(cudaSetDevice(device));
+    uint32_t* buf = nullptr;
+    WF_CUDA(cudaMalloc(&buf, 10 * sizeof(uint32_t)));
+    WF_CUDA(cudaMemcpy(buf, ctr_key_host, 6 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    philox_kat_kernel<<<1, 1>>>(buf, buf + 6);
+    cudaError_t err = cudaMemcpy(out_host, buf + 6, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    WF_CUDA(err);
+    return WF_OK;
+}
+
+int wf_stats(wf_env* e, int64_t out_host[8], void* stream) {
+    if (!e || !out_host) return fail(WF_ERR_INVALID, "null argument");
+    WF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WF_CUDA(cudaMemcpyAsync(out_host, e->st.stats, ST_N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    WF_CUDA(cudaStreamSynchronize(st));
+    return WF_OK;
+}
+
+int wf_stats_reset(wf_env* e, void* stream) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    WF_CUDA(cudaSetDevice(e->device));
+    WF_CUDA(cudaMemsetAsync(e->st.stats, 0, ST_N * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+    return WF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// wf_common.cuh -- shared device-side definitions of libwildfire_b200 (sm_100a).
+//
+// State layout in HBM (both kernel families)
+// ------------------------------------------
+// Every per-cell flag of the reference's env[x, y, layer] array (environment.py:38-50)
+// that can change is a BIT-PLANE: one uint32 word holds 32 consecutive y of one row x.
+//     word(plane, env, x, w) = planes[((plane * N + env) * RS + x) * HW + w]
+// with HW = ceil(H / 32) words per row and RS = row stride (warp family: lanes per env,
+// tile family: W).  Planes (one-hot cell type + the two flags type cannot express, Q7):
+//     G grass  F fire(type==1)  BT burnt  D dirt  WT water  B burning_cells  I fire_mobility==inf
+//     FU0.. fuel, bit-sliced (FB planes)     S0/S1 heat-source mask, ping-pong (tile family)
+// The `temp` layer is kept as exact per-direction hit counters, one uint32 per cell:
+//     hits[(env * W + x) * H + y] = n_N | n_S << 8 | n_E << 16 | n_W << 24
+// (temp = sum_d n_d * coef[d], environment.py:286-290), touched only where heat arrives.
+// `gray` is a pure function of type; heat/threshold/agent_mobility never change -> scalars.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wildfire.h"
+#include "wf_philox.cuh"
+
+namespace wf {
+
+enum Plane : int { P_G = 0, P_F, P_BT, P_D, P_WT, P_B, P_I, P_FU0 };  // + FB fuel planes (+ S0, S1, R for tiles)
+
+constexpr int kMaxWind = 27;  // 3 speeds x 9 vectors (environment.py:189-190) or 1 fixed entry
+
+// Read-only per-handle table, one entry per distinct wind the handle can meet.
+struct WindTable {
+    double coef[kMaxWind][4];  // heat quantum for displacement d: 0 N(0,-1) 1 S(0,+1) 2 E(+1,0) 3 W(-1,0)
+    int32_t kmin[kMaxWind];    // uniform winds: hits needed to ignite (sequential float64 sum, as the reference adds)
+    int32_t uniform[kMaxWind]; // all four quanta bit-identical
+    double speed[kMaxWind];
+    int32_t wx[kMaxWind], wy[kMaxWind];
+};
+
+// Device-side global statistics (int64 counters).
+enum Stat : int { ST_STEPS = 0, ST_EPISODES, ST_DEATHS, ST_CONTAINED, ST_BURNOUTS, ST_TICKS, ST_N = 8 };
+
+struct DevState {
+    uint32_t* planes;   // [NP][N][RS][HW]
+    uint32_t* hits;     // [N][W][H]
+    int32_t* scal;      // [N][WF_NSCALARS]
+    const WindTable* wind;
+    unsigned long long* stats;  // [ST_N]
+    int32_t N, W, H, RS, HW, FB, NP;
+};
+
+struct StepCfg {
+    int32_t n_actions, a_speed, allow_dig_toggle, make_rivers, wind_random, fuel, extra_ignitions, auto_reset;
+    double death_penalty, contained_bonus, default_reward, threshold;
+    uint32_t key0, key1;
+    int64_t env_id_base;
+};
+
+__device__ __forceinline__ size_t word_index(const DevState& s, int plane, int env, int x, int w) {
+    return (((size_t)plane * s.N + env) * s.RS + x) * s.HW + w;
+}
+
+// circle_points(0, 0, r) for r = 1, 2, 3 -- Simulation/utility.py:8-52, in the reference's
+// list order (checked against the oracle's literal restatement in tests/test_parity_gpu.py).
+__constant__ const int8_t kCircle[3][16][2] = {
+    {{1, 0}, {-1, 0}, {0, -1}, {0, 1}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}},
+    {{2, 0}, {-2, 0}, {0, -2}, {0, 2}, {2, 1}, {-2, 1}, {2, -1}, {-2, -1}, {1, 2}, {-1, 2}, {1, -2}, {-1, -2}},
+    {{3, 0}, {-3, 0}, {0, -3}, {0, 3}, {3, 1}, {-3, 1}, {3, -1}, {-3, -1}, {1, 3}, {-1, 3}, {1, -3}, {-1, -3},
+     {2, 2}, {-2, 2}, {2, -2}, {-2, -2}}};
+__constant__ const int32_t kCircleLen[3] = {8, 12, 16};
+
+// Sequential reader of the RESET stream (oracle/philox.py: stream 0, draw k = word k&3 of block k>>2).
+struct ResetDraws {
+    uint32_t env, episode, key0, key1, k;
+    uint32_t blk[4];
+    __device__ __forceinline__ ResetDraws(uint32_t env_, uint32_t ep_, uint32_t k0, uint32_t k1)
+        : env(env_), episode(ep_), key0(k0), key1(k1), k(0) {}
+    __device__ __forceinline__ uint32_t next() {
+        if ((k & 3u) == 0u) philox4x32_10(env, episode, k >> 2, kStreamReset, key0, key1, blk);
+        uint32_t r = (k & 3u) == 0u ? blk[0] : (k & 3u) == 1u ? blk[1] : (k & 3u) == 2u ? blk[2] : blk[3];
+        ++k;
+        return r;
+    }
+};
+
+// Ignition test of a heated grass cell -- World.apply_heat_from_to, environment.py:286-294.
+__device__ __forceinline__ bool ignites(uint32_t hits, const WindTable* wt, int wid, double threshold) {
+    const int n0 = hits & 255u, n1 = (hits >> 8) & 255u, n2 = (hits >> 16) & 255u, n3 = hits >> 24;
+    if (wt->uniform[wid]) return (n0 + n1 + n2 + n3) >= wt->kmin[wid];
+    const double* c = wt->coef[wid];
+    double t = __dmul_rn((double)n0, c[0]);
+    t = __dadd_rn(t, __dmul_rn((double)n1, c[1]));
+    t = __dadd_rn(t, __dmul_rn((double)n2, c[2]));
+    t = __dadd_rn(t, __dmul_rn((double)n3, c[3]));
+    return t > threshold;
+}
+
+// Fill every run of set bits of `free` that contains a bit of `seed` (seed must be a subset of free).
+// (free + seed) carries through a run from the seed upwards; the brev pair does the same downwards.
+__device__ __forceinline__ uint32_t hfill(uint32_t seed, uint32_t free_) {
+    uint32_t up = ((free_ + seed) ^ free_) & free_;
+    uint32_t rf = __brev(free_), rs = __brev(seed);
+    uint32_t dn = __brev(((rf + rs) ^ rf) & rf);
+    return seed | up | dn;
+}
+
+}  // namespace wf

@@ -1,0 +1,37 @@
+// wf_families.cuh -- launch interfaces of the two kernel families (warp: W,H <= 32; tile: larger).
+#pragma once
+#include "wf_common.cuh"
+
+namespace wf {
+
+struct WarpIO {
+    const int32_t* actions;  // [K][N] or nullptr (ACTION stream)
+    void* obs;               // [K][N][W][H][3] or nullptr
+    double* reward;          // [K][N] or nullptr
+    uint8_t* done;           // [K][N] or nullptr
+    const uint8_t* mask;     // reset mode: [N] or nullptr
+    const wf_init* init;     // reset mode: [N] or nullptr
+    int32_t obs_dtype, K, a_iter0, reset_mode;
+    uint32_t magicH;         // ceil(2^32 / H)
+};
+cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
+
+struct TileIO {
+    const int32_t* actions;  // [N]
+    void* obs;               // [N][W][H][3] or nullptr
+    double* reward;          // [N] or nullptr
+    uint8_t* done;           // [N] or nullptr
+    const uint8_t* mask;     // reset mode
+    const wf_init* init;     // reset mode
+    int32_t obs_dtype, do_tick, reset_mode;
+};
+struct TileState;
+int tile_extra_planes();
+cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg& c);
+void tile_destroy(TileState* t);
+cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io,
+                               cudaStream_t stream, int64_t* launches);
+cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg& c, cudaStream_t stream,
+                                 int64_t* launches);
+
+}  // namespace wf

@@ -1,0 +1,430 @@
+// wf_warp.cu -- "warp" kernel family: grids with W <= 32 and H <= 32.
+//
+// One environment is held by L = 16 or 32 lanes of a warp (two 14x14 envs per warp): lane x owns
+// row x of every bit-plane as ONE 32-bit register (bit y = cell (x, y)), so a whole env lives in
+// the register file.  The reference's per-burning-cell Python loop (forest_fire.py:85-106) becomes
+// word-parallel boolean algebra; the 4-neighbour stencil is two shifts (y +- 1) and two warp
+// shuffles (x +- 1); the A* containment search (environment.py:342-377, pyastar/astar.cpp) becomes
+// a bitboard flood fill from the border; per-env reductions are warp ballots.  wf_rollout keeps
+// the planes in registers across K steps, so HBM only sees actions in and obs/reward/done out.
+#include "wf_families.cuh"
+
+namespace wf {
+
+// Row x of every plane, one register each (constant indices only, so it never leaves the RF).
+template <int FB>
+struct Rows {
+    uint32_t G, F, BT, D, WT, B, I;
+    uint32_t FU[FB];
+    __device__ __forceinline__ uint32_t get(int p) const {
+        switch (p) {
+            case P_G: return G; case P_F: return F; case P_BT: return BT; case P_D: return D;
+            case P_WT: return WT; case P_B: return B; case P_I: return I; default: return FU[p - P_FU0];
+        }
+    }
+    __device__ __forceinline__ void set(int p, uint32_t v) {
+        switch (p) {
+            case P_G: G = v; break; case P_F: F = v; break; case P_BT: BT = v; break; case P_D: D = v; break;
+            case P_WT: WT = v; break; case P_B: B = v; break; case P_I: I = v; break; default: FU[p - P_FU0] = v;
+        }
+    }
+};
+
+struct Agent {
+    int ax, ay, alive, dead, digging, vis, running, fab, latched, wid, nburn;
+    uint32_t episode, t;
+};
+
+constexpr int kWarpsPerBlock = 4;
+
+template <int FB>
+__device__ __forceinline__ void dig(Rows<FB>& r, int x, int ax, int ay) {  // Agent.dig, environment.py:123-133
+    if (x == ax) {
+        const uint32_t bit = 1u << ay;
+        if (!(r.D & bit)) {
+            r.G &= ~bit; r.F &= ~bit; r.BT &= ~bit; r.WT &= ~bit;
+            r.D |= bit;
+            r.I |= bit;
+        }
+    }
+}
+
+template <int FB>
+__device__ __forceinline__ void set_fire(Rows<FB>& r, int x, int fx, int fy) {  // World.set_fire_to, environment.py:233-246
+    if (x == fx) {
+        const uint32_t bit = 1u << fy;
+        r.G &= ~bit; r.BT &= ~bit; r.D &= ~bit; r.WT &= ~bit;
+        r.F |= bit;
+        r.B |= bit;
+    }
+}
+
+// World.reset -- environment.py:186-212 (+ reset_map :59-95, Agent.__init__ :100-113,
+// get_agent_location utility.py:66-78).  Runs per env group; no warp collectives inside.
+template <int L, int FB>
+__device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepCfg& c, const wf_init* init,
+                           int env, int x, uint32_t validmask) {
+    const int W = s.W, H = s.H;
+    a.episode += 1u;
+    a.t = 0u;
+    ResetDraws dr((uint32_t)(c.env_id_base + env), a.episode, c.key0, c.key1);
+    if (c.wind_random) {  // :188-190
+        const int si = dr.next() % 3u, wx = dr.next() % 3u, wy = dr.next() % 3u;
+        a.wid = si * 9 + wx * 3 + wy;
+    } else {
+        a.wid = 0;
+    }
+    r.G = validmask;
+    r.F = r.BT = r.D = r.WT = r.B = r.I = 0u;
+#pragma unroll
+    for (int k = 0; k < FB; ++k) r.FU[k] = ((c.fuel >> k) & 1) ? validmask : 0u;
+    uint32_t* hits = s.hits + (size_t)env * W * H;
+    for (int i = x; i < W * H; i += L) hits[i] = 0u;  // temp layer := 0
+
+    const int cx = W / 2, cy = H / 2;  // get_fire_location, utility.py:61-64
+    if (c.make_rivers) {               // reset_map :69-95; every lane replays the same draws
+        int river_x = dr.next() % (uint32_t)W;
+        int river_y = 1 + dr.next() % 3u;
+        while (river_y < H - (1 + (int)(dr.next() % 3u))) {
+            if (x == river_x) {
+                const uint32_t bit = 1u << river_y;
+                r.G &= ~bit;
+                r.WT |= bit;
+                r.I |= bit;
+            }
+            const int new_y = river_y + 1;
+            int new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+            for (;;) {  // `not a <= new_x < b and not (new_x, new_y) == fire`; the chain short-circuits b
+                const int lo = 1 + dr.next() % 3u;
+                bool chain = false;
+                if (lo <= new_x) chain = new_x < W - (1 + (int)(dr.next() % 3u));
+                if (chain || (new_x == cx && new_y == cy)) break;
+                new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+            }
+            river_x = new_x;
+            river_y = new_y;
+        }
+    }
+    set_fire(r, x, cx, cy);  // :203
+    int ax, ay;
+    if (init != nullptr && init[env].ax >= 0) {
+        ax = init[env].ax;
+        ay = init[env].ay;
+    } else {
+        const int rad = dr.next() % 3u;  // radius - 1, utility.py:70
+        const int idx = dr.next() % (uint32_t)kCircleLen[rad];
+        ax = cx + kCircle[rad][idx][0];
+        ay = cy + kCircle[rad][idx][1];
+    }
+    a.ax = ax; a.ay = ay;
+    a.alive = 1; a.dead = 0; a.digging = 1; a.vis = 1;
+    dig(r, x, ax, ay);  // Agent.__init__ digs its start cell, :112-113
+    a.running = 1;
+    a.latched = 0;  // reset_border_points(), :211
+    a.fab = 0;      // :212
+    for (int k = 0; k < c.extra_ignitions; ++k) {  // World.set_fire_to after reset (IGNITE stream)
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, w);
+        const int ix = w[0] % (uint32_t)W, iy = w[1] % (uint32_t)H;
+        set_fire(r, x, ix, iy);
+        if (ix == 0 || ix == W - 1 || iy == 0 || iy == H - 1) a.fab = 1;
+    }
+}
+
+// World.get_state -- environment.py:399-402: [agent_pos, type == fire, fire_mobility != inf].
+// The three row masks of every lane are staged in shared memory, then the env's L lanes write the
+// [W][H][3] block with consecutive lanes on consecutive 4-byte words (coalesced).
+template <int L>
+__device__ __forceinline__ void emit_obs(void* obs_env, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
+                                         uint32_t (*stage)[32], int lane, int sub, int x, int W, int H,
+                                         uint32_t magicH, bool valid_env) {
+    __syncwarp();
+    stage[0][lane] = arow;
+    stage[1][lane] = frow;
+    stage[2][lane] = freerow;
+    __syncwarp();
+    if (!valid_env) return;
+    const int nbytes = W * H * 3;
+    const uint32_t* s0 = &stage[0][sub * L];
+    auto bit_of = [&](int b) -> uint32_t {  // element b of the flattened (x*H + y)*3 + ch block
+        const uint32_t cell = __umulhi((uint32_t)b, 1431655766u);  // b / 3
+        const uint32_t ch = b - 3u * cell;
+        const uint32_t xx = __umulhi(cell, magicH);  // cell / H
+        const uint32_t yy = cell - xx * H;
+        return (s0[ch * 32 + xx] >> yy) & 1u;
+    };
+    if (dtype == WF_OBS_U8) {
+        uint8_t* o8 = static_cast<uint8_t*>(obs_env);
+        if ((nbytes & 3) == 0) {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
+            for (int j = x; j < (nbytes >> 2); j += L) {
+                const int b = 4 * j;
+                o32[j] = bit_of(b) | (bit_of(b + 1) << 8) | (bit_of(b + 2) << 16) | (bit_of(b + 3) << 24);
+            }
+        } else {
+            for (int b = x; b < nbytes; b += L) o8[b] = (uint8_t)bit_of(b);
+        }
+    } else {
+        float* of = static_cast<float*>(obs_env);
+        for (int b = x; b < nbytes; b += L) of[b] = bit_of(b) ? 1.0f : 0.0f;
+    }
+}
+
+template <int L, int FB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, StepCfg c, WarpIO io) {
+    constexpr int EPW = 32 / L;  // envs per warp
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    __shared__ uint32_t stage_all[kWarpsPerBlock][3][32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / L, x = lane % L;
+    const int env = (blockIdx.x * kWarpsPerBlock + warp) * EPW + sub;
+    const bool valid_env = env < s.N;
+    const int W = s.W, H = s.H;
+    const uint32_t colmask = (H == 32) ? 0xffffffffu : ((1u << H) - 1u);
+    const uint32_t validmask = (valid_env && x < W) ? colmask : 0u;
+    // Literal border_points (environment.py:215-222): rows x == 0 and x == HEIGHT-1, columns 0 and H-1.
+    const uint32_t seedmask = (x == 0 || x == H - 1) ? validmask : (validmask & (1u | (1u << (H - 1))));
+    const uint32_t edgemask = (x == 0 || x == W - 1) ? validmask : (validmask & (1u | (1u << (H - 1))));
+    auto group_bits = [&](uint32_t ballot) -> uint32_t { return (ballot >> (sub * L)) & GMASK; };
+    uint32_t(*stage)[32] = stage_all[warp];
+
+    // ---------------- load ----------------
+    Rows<FB> r;
+    Agent a;
+    {
+#pragma unroll
+        for (int p = 0; p < 7 + FB; ++p) r.set(p, valid_env ? s.planes[word_index(s, p, env, x, 0)] : 0u);
+        int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+        if (valid_env) {
+            const int4* sp = reinterpret_cast<const int4*>(s.scal + (size_t)env * WF_NSCALARS);
+            v0 = sp[0]; v1 = sp[1]; v2 = sp[2]; v3 = sp[3];
+        }
+        a.alive = v0.x; a.ax = v0.y; a.ay = v0.z; a.dead = v0.w;
+        a.digging = v1.x; a.vis = v1.y; a.running = v1.z; a.fab = v1.w;
+        a.latched = v2.x; a.episode = (uint32_t)v2.y; a.t = (uint32_t)v2.z; a.wid = v2.w;
+        a.nburn = v3.z;
+    }
+    if (!valid_env) { a.running = 0; a.alive = 0; a.ax = a.ay = 0; a.wid = 0; }
+
+    long long n_steps_done = 0;
+
+    if (io.reset_mode) {
+        // ---------------- ForestFire.reset() ----------------
+        const bool doit = valid_env && (io.mask == nullptr || io.mask[env] != 0);
+        if (doit) reset_rows<L, FB>(r, a, s, c, io.init, env, x, validmask);
+        __syncwarp();
+        if (io.obs != nullptr) {
+            const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
+            emit_obs<L>(static_cast<char*>(io.obs) + (size_t)(valid_env ? env : 0) * esz, io.obs_dtype,
+                        (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stage, lane, sub, x, W, H,
+                        io.magicH, valid_env);
+        }
+    } else {
+        // ---------------- K x ForestFire.step(action) ----------------
+        int it = io.a_iter0;
+        for (int k = 0; k < io.K; ++k) {
+            const bool act = valid_env && a.running;  // finished envs are frozen (reward 0, done 1)
+            int action;
+            if (io.actions != nullptr) {
+                action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
+            } else {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, a.t, kStreamAction, c.key0, c.key1, w);
+                action = (int)(w[0] % (uint32_t)c.n_actions);
+            }
+            // ---- action: Agent.move :141-155 / toggle_digging :136-138 (agents[0] exists while alive)
+            {
+                const bool mv = act && a.alive && action >= 0 && action < 4;
+                const int nx = a.ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
+                const int ny = a.ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
+                const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
+                const int src_lane = sub * L + (inb ? nx : 0);
+                const uint32_t wrow = __shfl_sync(FULL, r.WT, src_lane);
+                const uint32_t frow = __shfl_sync(FULL, r.F, src_lane);
+                if (mv) {
+                    a.vis = 0;  // agent_pos cleared before the validity test (Q1)
+                    if (inb && !((wrow >> ny) & 1u)) {
+                        a.ax = nx; a.ay = ny; a.vis = 1;
+                        const bool onfire = (frow >> ny) & 1u;
+                        if (a.digging && !onfire) dig(r, x, nx, ny);
+                        if (onfire) a.dead = 1;
+                    }
+                }
+                if (act && a.alive && c.allow_dig_toggle && action == 4) {
+                    a.digging ^= 1;
+                    if (a.digging) dig(r, x, a.ax, a.ay);
+                }
+            }
+            // ---- fire tick: ForestFire.update, forest_fire.py:85-106 (every a_speed steps)
+            it -= 1;
+            const bool do_tick = (it == 0);
+            if (do_tick) it = c.a_speed;
+            uint32_t ign_edge = 0u;
+            if (do_tick) {
+                // Agent.is_dead :116-120 -- dead flag or standing on a type==fire cell
+                const uint32_t frow = __shfl_sync(FULL, r.F, sub * L + a.ax);
+                if (act && a.alive && (a.dead || ((frow >> a.ay) & 1u))) {
+                    a.vis = 0;
+                    a.alive = 0;
+                    if (x == 0) atomicAdd(&s.stats[ST_DEATHS], 1ull);
+                }
+                const uint32_t Bt = act ? r.B : 0u;  // burning set as of tick start (:90)
+                // reduce_fuel :297-307 on every burning cell: bit-sliced decrement with borrow
+                uint32_t borrow = Bt;
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const uint32_t f = r.FU[q];
+                    r.FU[q] = f ^ borrow;
+                    borrow &= ~f;
+                }
+                uint32_t nz = 0u;
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    r.FU[q] &= ~borrow;  // fuel was already 0: stays 0 (<= 0 -> burnt)
+                    nz |= r.FU[q];
+                }
+                const uint32_t out = Bt & ~nz;  // burnt out this tick
+                const uint32_t src = Bt & nz;   // still burning: heats its neighbours
+                r.BT |= out;
+                r.F &= ~out; r.D &= ~out; r.WT &= ~out; r.G &= ~out;
+                r.B &= ~out;
+                // get_neighbours :311-326 (radius 1) + apply_heat_from_to :278-294
+                uint32_t up = __shfl_up_sync(FULL, src, 1, L);
+                uint32_t dn = __shfl_down_sync(FULL, src, 1, L);
+                if (x == 0) up = 0u;
+                if (x == L - 1) dn = 0u;
+                const uint32_t h0 = r.G & (src >> 1);  // d = N (0,-1): source at y+1
+                const uint32_t h1 = r.G & (src << 1);  // d = S (0,+1): source at y-1
+                const uint32_t h2 = r.G & up;          // d = E (+1,0): source at x-1
+                const uint32_t h3 = r.G & dn;          // d = W (-1,0): source at x+1
+                uint32_t m = h0 | h1 | h2 | h3, ign = 0u;
+                uint32_t* hrow = s.hits + ((size_t)(valid_env ? env : 0) * W + x) * H;
+                while (m) {
+                    const int y = __ffs(m) - 1;
+                    m &= m - 1u;
+                    const uint32_t v = hrow[y] + (((h0 >> y) & 1u) | (((h1 >> y) & 1u) << 8) |
+                                                  (((h2 >> y) & 1u) << 16) | (((h3 >> y) & 1u) << 24));
+                    hrow[y] = v;
+                    if (ignites(v, s.wind, a.wid, c.threshold)) ign |= 1u << y;
+                }
+                r.G &= ~ign;  // set_fire_to :233-246
+                r.F |= ign;
+                r.B |= ign;
+                ign_edge = ign & edgemask;
+            }
+            __syncwarp();
+            const uint32_t any_edge = group_bits(__ballot_sync(FULL, ign_edge != 0u));
+            const uint32_t anyB = group_bits(__ballot_sync(FULL, r.B != 0u));
+            if (do_tick && act) {
+                if (any_edge) a.fab = 1;
+                if (!a.alive || !anyB) a.running = 0;  // :105-106
+            }
+            // ---- World.get_reward, environment.py:342-390
+            const bool check = act && !a.fab && !a.latched && anyB;
+            bool contained = false;
+            if (__any_sync(FULL, check)) {
+                const uint32_t free_ = ~r.I & validmask;
+                uint32_t reach = free_ & seedmask;
+                for (;;) {  // flood fill: cells with a finite-cost 4-connected path to a finite border point
+                    uint32_t n = hfill(reach, free_);
+                    uint32_t u = __shfl_up_sync(FULL, n, 1, L), d = __shfl_down_sync(FULL, n, 1, L);
+                    if (x == 0) u = 0u;
+                    if (x == L - 1) d = 0u;
+                    n |= (u | d) & free_;
+                    const bool changed = (n != reach);
+                    reach = n;
+                    if (!__any_sync(FULL, changed)) break;
+                }
+                uint32_t u = __shfl_up_sync(FULL, reach, 1, L), d = __shfl_down_sync(FULL, reach, 1, L);
+                if (x == 0) u = 0u;
+                if (x == L - 1) d = 0u;
+                // A* ignores the start cell's own cost (astar.cpp:89-90, Q5): a burning cell reaches the
+                // border iff it or one of its 4 neighbours is in `reach`.
+                const uint32_t near = reach | (reach << 1) | (reach >> 1) | u | d;
+                contained = !group_bits(__ballot_sync(FULL, (r.B & near) != 0u));
+            }
+            double rew = 0.0;
+            if (act) {
+                if (check && contained) {
+                    a.latched = 1;  // border_points left empty: bonus is paid once (Q4)
+                    rew = c.contained_bonus;
+                    if (x == 0) atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+                } else if (!a.alive) {
+                    rew = c.death_penalty;
+                } else if (!anyB) {
+                    rew = 1.0;  // placeholder: burn-out fraction computed below
+                } else {
+                    rew = c.default_reward;
+                }
+            }
+            const bool burnout = act && !(check && contained) && a.alive && !anyB;
+            if (__any_sync(FULL, burnout)) {  // np.count_nonzero(type == grass) / (W * H), :385-387
+                int cnt = __popc(r.G);
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o, L);
+                if (burnout) rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)cnt, (double)(W * H)));
+            }
+            const bool done = valid_env && !a.running;
+            if (act) {
+                a.t += 1u;
+                n_steps_done += 1;
+                if (done && x == 0) {
+                    atomicAdd(&s.stats[ST_EPISODES], 1ull);
+                    if (a.alive) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
+                }
+            }
+            if (valid_env && x == 0) {
+                if (io.reward != nullptr) io.reward[(size_t)k * s.N + env] = rew;
+                if (io.done != nullptr) io.done[(size_t)k * s.N + env] = done ? 1 : 0;
+            }
+            // ---- auto-reset (batched-env convention: the returned obs is the new episode's first)
+            if (c.auto_reset && act && done) reset_rows<L, FB>(r, a, s, c, nullptr, env, x, validmask);
+            __syncwarp();
+            if (io.obs != nullptr) {
+                const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
+                emit_obs<L>(static_cast<char*>(io.obs) + ((size_t)k * s.N + (valid_env ? env : 0)) * esz, io.obs_dtype,
+                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stage, lane, sub, x, W,
+                            H, io.magicH, valid_env);
+            }
+        }
+    }
+
+    // ---------------- store ----------------
+    {
+        int nb = __popc(r.B);
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) nb += __shfl_xor_sync(FULL, nb, o, L);
+        a.nburn = nb;
+    }
+    if (valid_env) {
+#pragma unroll
+        for (int p = 0; p < 7 + FB; ++p) s.planes[word_index(s, p, env, x, 0)] = r.get(p);
+        if (x == 0) {
+            int4* sp = reinterpret_cast<int4*>(s.scal + (size_t)env * WF_NSCALARS);
+            sp[0] = make_int4(a.alive, a.ax, a.ay, a.dead);
+            sp[1] = make_int4(a.digging, a.vis, a.running, a.fab);
+            sp[2] = make_int4(a.latched, (int)a.episode, (int)a.t, a.wid);
+            sp[3] = make_int4(s.wind->wx[a.wid], s.wind->wy[a.wid], a.nburn, 0);
+            if (n_steps_done) atomicAdd(&s.stats[ST_STEPS], (unsigned long long)n_steps_done);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher (called from wf_api.cu)
+cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream) {
+    const int L = s.RS;
+    const int epw = 32 / L;
+    const int envs_per_block = kWarpsPerBlock * epw;
+    const dim3 grid((s.N + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
+    if (L == 16 && s.FB == 5) warp_kernel<16, 5><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 16 && s.FB == 8) warp_kernel<16, 8><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 32 && s.FB == 5) warp_kernel<32, 5><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 32 && s.FB == 8) warp_kernel<32, 8><<<grid, block, 0, stream>>>(s, c, io);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace wf
