@@ -478,6 +478,11 @@ void wfo_get_scalars(const wfo_env* e, int32_t out[16]) {
 
 double wfo_get_wind_speed(const wfo_env* e) { return e->wind_speed; }
 
+/* METADATA['a_speed_iter'] is ONE process-wide counter in the reference (constants.py:41,
+ * forest_fire.py:40-43).  A batch that steps in lockstep shares it; an env that sat out some
+ * steps (finished, waiting for reset) must be re-synchronised by the harness. */
+void wfo_set_a_speed_iter(wfo_env* e, int v) { e->a_speed_iter = v; }
+
 void wfo_get_coef(const wfo_env* e, double coef[4]) {
     static const int DX[4] = {0, 0, 1, -1}, DY[4] = {-1, 1, 0, 0};
     for (int d = 0; d < 4; ++d) {

@@ -60,6 +60,7 @@ void wfo_get_planes(const wfo_env* e, uint8_t* type, uint8_t* burning, uint8_t* 
  * [7]=n_border_points [8]=episode [9]=t [10]=a_speed_iter [11]=wind_x [12]=wind_y [13]=n_burning */
 void wfo_get_scalars(const wfo_env* e, int32_t out[16]);
 double wfo_get_wind_speed(const wfo_env* e);
+void wfo_set_a_speed_iter(wfo_env* e, int v); /* the reference's counter is process-global (Q8) */
 /* Directional heat quanta: d = 0 N(0,-1) 1 S(0,+1) 2 E(+1,0) 3 W(-1,0) (displacement source->target). */
 void wfo_get_coef(const wfo_env* e, double coef[4]);
 /* World.set_fire_to((x, y)) -- environment.py:233-246. */

@@ -59,6 +59,7 @@ def lib():
         L.wfo_get_wind_speed.restype = C.c_double
         L.wfo_get_wind_speed.argtypes = [p]
         L.wfo_get_coef.argtypes = [p, f64p]
+        L.wfo_set_a_speed_iter.argtypes = [p, C.c_int]
         L.wfo_set_fire_to.argtypes = [p, C.c_int, C.c_int]
         L.wfo_set_planes.argtypes = [p, u8p, u8p, u8p, i32p, f64p]
         L.wfo_set_agent.argtypes = [p] + [C.c_int] * 6
@@ -134,6 +135,9 @@ class OracleEnv:
         if rc != 0:
             raise IndexError("list index out of range (step on an env without agent)")
         return o, r.value, bool(d.value), {}
+
+    def set_a_speed_iter(self, v):
+        lib().wfo_set_a_speed_iter(self.h, int(v))
 
     def set_fire_to(self, x, y):
         lib().wfo_set_fire_to(self.h, int(x), int(y))

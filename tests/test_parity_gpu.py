@@ -92,9 +92,14 @@ def test_step_matches_oracle_batch(cfg):
     for e in orc:
         e.reset()
     compare_states("reset", gpu, orc, obs=obs)
+    a_speed = cfg.get("a_speed", 1)
+    a_iter = a_speed  # METADATA['a_speed_iter']: one counter per process in the reference, per handle here
     for s in range(STEPS):
         acts = [e.random_action() for e in orc]
         frozen = [not e.planes()["running"] for e in orc]
+        for e in orc:
+            e.set_a_speed_iter(a_iter)
+        a_iter = a_speed if a_iter == 1 else a_iter - 1
         obs, rew, done, _ = gpu.step(torch.tensor(acts, dtype=torch.int32, device="cuda"))
         rew, done = to_np(rew), to_np(done)
         for i, e in enumerate(orc):
