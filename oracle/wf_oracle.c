@@ -567,3 +567,84 @@ int64_t wfo_rollout(const wfo_config* cfg, int64_t env_id_base, int n_envs, int 
     if (episodes) *episodes = eps;
     return total;
 }
+
+/* ---- persistent batch (bench.py --impl reference): same envs stepped call after call ---- */
+struct wfo_batch {
+    wfo_config cfg;
+    int n_envs, n_threads;
+    wfo_env** envs;
+    uint8_t** obs; /* one scratch observation per thread */
+};
+
+typedef struct {
+    struct wfo_batch* b;
+    int tid, n_steps;
+    int64_t total, eps;
+    double sum;
+} batch_job;
+
+static void* batch_worker(void* arg) {
+    batch_job* j = (batch_job*)arg;
+    struct wfo_batch* b = j->b;
+    int64_t total = 0, eps = 0;
+    double sum = 0.0;
+    uint8_t* obs = b->obs[j->tid];
+    const int nb = b->cfg.width * b->cfg.height * 3;
+    const int per = (b->n_envs + b->n_threads - 1) / b->n_threads; /* contiguous block per thread */
+    const int lo = j->tid * per, hi = lo + per < b->n_envs ? lo + per : b->n_envs;
+    for (int i = lo; i < hi; ++i) {
+        wfo_env* e = b->envs[i];
+        for (int s = 0; s < j->n_steps; ++s) {
+            double r; int d;
+            wfo_step(e, wfo_stream_action(e), obs, &r, &d);
+            sum += r + obs[(s * 7 + i) % nb];
+            total += 1;
+            if (d) { wfo_reset(e); eps += 1; }
+        }
+    }
+    j->total = total; j->eps = eps; j->sum = sum;
+    return NULL;
+}
+
+struct wfo_batch* wfo_batch_create(const wfo_config* cfg, int64_t env_id_base, int n_envs, int n_threads) {
+    struct wfo_batch* b = (struct wfo_batch*)calloc(1, sizeof(*b));
+    b->cfg = *cfg;
+    b->n_envs = n_envs;
+    b->n_threads = n_threads < 1 ? 1 : (n_threads > n_envs ? n_envs : n_threads);
+    b->envs = (wfo_env**)calloc((size_t)n_envs, sizeof(wfo_env*));
+    b->obs = (uint8_t**)calloc((size_t)b->n_threads, sizeof(uint8_t*));
+    for (int t = 0; t < b->n_threads; ++t) b->obs[t] = (uint8_t*)malloc((size_t)cfg->width * cfg->height * 3 + 64);
+    for (int i = 0; i < n_envs; ++i) {
+        b->envs[i] = wfo_create(cfg, env_id_base + i);
+        wfo_reset(b->envs[i]);
+    }
+    return b;
+}
+
+void wfo_batch_destroy(struct wfo_batch* b) {
+    if (!b) return;
+    for (int i = 0; i < b->n_envs; ++i) wfo_destroy(b->envs[i]);
+    for (int t = 0; t < b->n_threads; ++t) free(b->obs[t]);
+    free(b->envs); free(b->obs); free(b);
+}
+
+/* n_steps ForestFire.step calls on every env (ACTION-stream actions, reset on done). */
+int64_t wfo_batch_step(struct wfo_batch* b, int n_steps, double* checksum, int64_t* episodes) {
+    batch_job* jobs = (batch_job*)calloc((size_t)b->n_threads, sizeof(batch_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)b->n_threads, sizeof(pthread_t));
+    for (int t = 0; t < b->n_threads; ++t) {
+        jobs[t].b = b; jobs[t].tid = t; jobs[t].n_steps = n_steps;
+        if (b->n_threads > 1) pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+        else batch_worker(&jobs[t]);
+    }
+    int64_t total = 0, eps = 0;
+    double sum = 0.0;
+    for (int t = 0; t < b->n_threads; ++t) {
+        if (b->n_threads > 1) pthread_join(th[t], NULL);
+        total += jobs[t].total; eps += jobs[t].eps; sum += jobs[t].sum;
+    }
+    free(jobs); free(th);
+    if (checksum) *checksum += sum;
+    if (episodes) *episodes += eps;
+    return total;
+}

@@ -76,6 +76,12 @@ void wfo_set_agent(wfo_env* e, int alive, int ax, int ay, int visible, int dead,
 int64_t wfo_rollout(const wfo_config* cfg, int64_t env_id_base, int n_envs, int n_steps,
                     int n_threads, double* checksum, int64_t* episodes);
 
+/* Persistent batch for bench.py --impl reference: envs live across calls. */
+typedef struct wfo_batch wfo_batch;
+wfo_batch* wfo_batch_create(const wfo_config* cfg, int64_t env_id_base, int n_envs, int n_threads);
+void wfo_batch_destroy(wfo_batch* b);
+int64_t wfo_batch_step(wfo_batch* b, int n_steps, double* checksum, int64_t* episodes);
+
 #ifdef __cplusplus
 }
 #endif

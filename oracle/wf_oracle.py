@@ -66,6 +66,11 @@ def lib():
         L.wfo_rollout.restype = C.c_int64
         L.wfo_rollout.argtypes = [C.POINTER(Config), C.c_int64, C.c_int, C.c_int, C.c_int, f64p,
                                   C.POINTER(C.c_int64)]
+        L.wfo_batch_create.restype = p
+        L.wfo_batch_create.argtypes = [C.POINTER(Config), C.c_int64, C.c_int, C.c_int]
+        L.wfo_batch_destroy.argtypes = [p]
+        L.wfo_batch_step.restype = C.c_int64
+        L.wfo_batch_step.argtypes = [p, C.c_int, f64p, C.POINTER(C.c_int64)]
         L.wfo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -186,6 +191,25 @@ def rollout(cfg: dict, n_envs: int, n_steps: int, n_threads: int = 0, env_id_bas
     eps = C.c_int64()
     n = lib().wfo_rollout(C.byref(c), env_id_base, n_envs, n_steps, n_threads, C.byref(chk), C.byref(eps))
     return int(n), int(eps.value), float(chk.value)
+
+
+class OracleBatch:
+    """Persistent batch of oracle envs stepped with stream actions by ``n_threads`` host threads."""
+
+    def __init__(self, cfg: dict, n_envs: int, n_threads: int = 1, env_id_base: int = 0):
+        self.cfg = make_config(cfg)
+        self.n_envs, self.n_threads = n_envs, max(1, min(n_threads, n_envs))
+        self.h = lib().wfo_batch_create(C.byref(self.cfg), env_id_base, n_envs, self.n_threads)
+        self.checksum = C.c_double(0.0)
+        self.episodes = C.c_int64(0)
+
+    def step(self, n_steps: int = 1) -> int:
+        return int(lib().wfo_batch_step(self.h, n_steps, C.byref(self.checksum), C.byref(self.episodes)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().wfo_batch_destroy(self.h)
+            self.h = None
 
 
 def philox(ctr, key):
