@@ -80,6 +80,12 @@ SCENARIOS = [
     dict(width=32, height=32, seed=105, wind=[0.85, (-1, 1)], extra_ignitions=5),
     dict(width=17, height=13, seed=106, wind=[0.7, (0, 1)]),
     dict(width=11, height=11, seed=107, fuel=40, threshold=5.0, heat=0.35),
+    # tile family (W or H > 32): several words per row, ragged last word, rivers, wind, ignitions
+    dict(width=40, height=40, seed=108, extra_ignitions=3),
+    dict(width=64, height=64, seed=109, wind="random", make_rivers=True, extra_ignitions=6),
+    dict(width=100, height=70, seed=110, wind=[0.85, (1, 0)], extra_ignitions=10, a_speed=2),
+    dict(width=48, height=33, seed=111, allow_dig_toggle=True, n_actions=6, wind=[0.85, (0, -1)], extra_ignitions=2),
+    dict(width=33, height=20, seed=112, fuel=50, threshold=4.0),
 ]
 
 
@@ -121,8 +127,9 @@ def test_step_matches_oracle_batch(cfg):
 
 
 @pytest.mark.parametrize("cfg", [dict(width=14, height=14, seed=201),
-                                 dict(width=12, height=12, seed=202, wind="random", make_rivers=True, a_speed=2)],
-                         ids=["c2", "rivers_wind_aspeed2"])
+                                 dict(width=12, height=12, seed=202, wind="random", make_rivers=True, a_speed=2),
+                                 dict(width=40, height=36, seed=203, wind="random", extra_ignitions=2)],
+                         ids=["c2", "rivers_wind_aspeed2", "tile_40x36"])
 def test_fused_rollout_matches_oracle(cfg):
     """wf_rollout: K steps in one launch, actions from the ACTION stream, auto-reset on done."""
     N, K = 67, 300
@@ -146,6 +153,60 @@ def test_fused_rollout_matches_oracle(cfg):
     compare_states("after rollout", gpu, orc)
     st = gpu.stats()
     assert st["episodes"] == n_done and st["env_steps"] == N * K
+
+
+@pytest.mark.parametrize("cfg", [dict(width=14, height=14, seed=601), dict(width=20, height=20, seed=602, make_rivers=True),
+                                 dict(width=40, height=40, seed=603), dict(width=72, height=64, seed=604, a_speed=2),
+                                 dict(width=64, height=64, seed=605, make_rivers=True, wind="random")],
+                         ids=lambda c: f"{c['width']}x{c['height']}_s{c['seed']}")
+def test_scripted_containment_matches_oracle(cfg):
+    """Every env walks a ring of its own radius round the fire (containment bonus, latch, burn-out
+    reward), then takes stream actions; resets are applied as soon as an env finishes."""
+    from oracle.policies import ring_actions
+    N, STEPS = 12, 260
+    gpu, orc = make_pair(N, cfg)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    W, H = cfg["width"], cfg["height"]
+
+    def plan_for(i):
+        p = orc[i].planes()
+        return ring_actions(p["ax"], p["ay"], W // 2, H // 2, 2 + i % 4)
+
+    plans = [plan_for(i) for i in range(N)]
+    tcount = [0] * N
+    a_speed = cfg.get("a_speed", 1)
+    a_iter = a_speed
+    n_contained = 0
+    for s in range(STEPS):
+        acts = []
+        for i, e in enumerate(orc):
+            a = e.random_action()
+            if tcount[i] < len(plans[i]):
+                a = plans[i][tcount[i]]
+            acts.append(a)
+            e.set_a_speed_iter(a_iter)
+        a_iter = a_speed if a_iter == 1 else a_iter - 1
+        obs, rew, done, _ = gpu.step(torch.tensor(acts, dtype=torch.int32, device="cuda"))
+        rew, done = to_np(rew), to_np(done)
+        m = np.zeros(N, np.uint8)
+        for i, e in enumerate(orc):
+            _, r, d, _ = e.step(acts[i])
+            tcount[i] += 1
+            assert rew[i] == r, f"step {s} env {i}: reward {rew[i]} != {r}"
+            assert bool(done[i]) == d, f"step {s} env {i}: done"
+            n_contained += int(r == 1000)
+            m[i] = d
+        compare_states(f"step {s}", gpu, orc, obs=obs)
+        if m.any():
+            obs = gpu.reset(mask=torch.from_numpy(m).cuda())
+            for i in np.nonzero(m)[0]:
+                orc[i].reset()
+                plans[i] = plan_for(i)
+                tcount[i] = 0
+            compare_states(f"reset after step {s}", gpu, orc, obs=obs)
+    assert n_contained >= N // 2
 
 
 def test_rollout_equals_repeated_step():

@@ -93,6 +93,9 @@ class BatchedForestFire:
             self._obs = torch.empty((N, W, H, 3), dtype=obs_dtype, device=self.device)
             self._reward = torch.empty((N,), dtype=torch.float64, device=self.device)
             self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        self._done_bool = self._done.view(torch.bool)
+        self._obs_ptr, self._reward_ptr, self._done_ptr = self._obs.data_ptr(), self._reward.data_ptr(), self._done.data_ptr()
+        self._wf_step = L.wf_step
         nw = C.c_int32()
         coef = (C.c_double * (27 * 4))()
         speed = (C.c_double * 27)()
@@ -119,10 +122,8 @@ class BatchedForestFire:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _as_i32(self, t, shape):
-        t = torch.as_tensor(t, device=self.device)
-        if t.dtype != torch.int32:
-            t = t.to(torch.int32)
-        t = t.contiguous()
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.int32 and t.is_cuda and t.is_contiguous()):
+            t = torch.as_tensor(t, device=self.device).to(torch.int32).contiguous()
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
@@ -152,10 +153,11 @@ class BatchedForestFire:
         the handle's persistent buffers (overwritten by the next call).
         """
         a = self._as_i32(actions, (self.n_envs,))
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().wf_step(self._h, _ptr(a), _ptr(self._obs), self._obs_code, _ptr(self._reward),
-                                          _ptr(self._done), self._stream()))
-        return self._obs, self._reward, self._done.view(torch.bool), {}
+        rc = self._wf_step(self._h, a.data_ptr(), self._obs_ptr, self._obs_code, self._reward_ptr, self._done_ptr,
+                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc)
+        return self._obs, self._reward, self._done_bool, {}
 
     def rollout(self, k_steps: int, actions=None, obs: bool = True, out=None):
         """``k_steps`` consecutive ``step`` calls in one launch (state stays on chip in between).

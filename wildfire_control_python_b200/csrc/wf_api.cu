@@ -357,12 +357,11 @@ int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs
     if (e->tile) {
         const DevState& s = e->st;
         const size_t esz = (size_t)s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
-        if (!actions_dev) return fail(WF_ERR_INVALID, "tile family: wf_rollout needs explicit actions");
         for (int k = 0; k < k_steps; ++k) {  // tile family: one tick per launch group
             int it = e->a_iter - 1;
             const int do_tick = (it == 0);
             if (do_tick) it = e->cfg.a_speed;
-            TileIO io{actions_dev + (size_t)k * s.N,
+            TileIO io{actions_dev ? actions_dev + (size_t)k * s.N : nullptr,
                       obs_dev ? static_cast<char*>(obs_dev) + (size_t)k * s.N * esz : nullptr,
                       reward_dev ? reward_dev + (size_t)k * s.N : nullptr,
                       done_dev ? done_dev + (size_t)k * s.N : nullptr,

@@ -1,13 +1,643 @@
-// wf_tile.cu -- "tile" kernel family: grids wider or taller than 32 cells (256x256, 1024x1024).
+// wf_tile.cu -- "tile" kernel family: grids wider or taller than 32 cells (256x256, 1024x1024 ...).
+//
+// Same bit-plane state as the warp family (wf_common.cuh) but resident in HBM: a row x of H cells is
+// HW = ceil(H/32) words, one thread owns one word (32 cells) per tick.  Per tick a word reads
+//   * the heat-source mask S (1 bit/cell: burning and fuel >= 2) of itself and its 4 neighbours,
+//   * its grass / fire / burning / fm_inf words,
+// and ONLY IF it burns or receives heat the fuel planes and the hit counters of the heated cells.
+// It writes the next source mask (ping-pong), whatever changed, and 96 bytes of observation.
+// The per-burning-cell Python loop (forest_fire.py:85-106) is boolean algebra on words; the A*
+// containment search (environment.py:342-377) is a persistent "reach" plane R (cells with a finite
+// 4-connected path to a finite border point) that is re-flooded only when a dig may disconnect it.
+//
+// One step = agent_kernel (1 thread/env: move/dig/reap + local articulation test)
+//          -> flood_kernel (1 block/env, exits at once unless flagged)
+//          -> tile_step_kernel (the HBM-bound stencil + obs + per-env reductions)
+//          -> finish_kernel (1 thread/env: reward, done, latch, stats)
+//          [-> reset kernels for the envs that finished, when auto_reset]
 #include "wf_families.cuh"
 
 namespace wf {
-struct TileState { int dummy; };
-int tile_extra_planes() { return 0; }
-cudaError_t tile_create(TileState** out, const DevState&, const StepCfg&) { *out = new TileState(); return cudaSuccess; }
-void tile_destroy(TileState* t) { delete t; }
-cudaError_t launch_tile_family(TileState*, const DevState&, const StepCfg&, const TileIO&, cudaStream_t, int64_t*) {
-    return cudaErrorNotSupported;
+
+constexpr int kTileThreads = 256;
+
+struct TileState {
+    int32_t* acc;         // [N][4]: burning cells, grass cells, ignition-on-edge flag, burning-touches-reach flag
+    int32_t* need_flood;  // [N]
+    uint8_t* do_reset;    // [N]
+    int32_t cur;          // which of the two S planes holds the sources of the NEXT tick
+    int32_t P_S0, P_S1, P_R;
+    int32_t flood_smem_ok;
+};
+
+int tile_extra_planes() { return 3; }
+
+__device__ __forceinline__ uint32_t valid_word(int H, int w) {
+    const int rem = H - 32 * w;
+    return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 }
-cudaError_t tile_after_set_state(TileState*, const DevState&, const StepCfg&, cudaStream_t, int64_t*) { return cudaSuccess; }
+
+// Literal border_points (environment.py:215-222): (x,0) (x,H-1) for all x; (0,y) (H-1,y) for all y.
+__device__ __forceinline__ uint32_t seed_word(int W, int H, int x, int w) {
+    const uint32_t v = valid_word(H, w);
+    if (x == 0 || x == H - 1) return v;
+    uint32_t m = 0u;
+    if (w == 0) m |= 1u;
+    if (w == (H - 1) >> 5) m |= 1u << ((H - 1) & 31);
+    return m & v;
+}
+__device__ __forceinline__ uint32_t edge_word(int W, int H, int x, int w) {
+    const uint32_t v = valid_word(H, w);
+    if (x == 0 || x == W - 1) return v;
+    uint32_t m = 0u;
+    if (w == 0) m |= 1u;
+    if (w == (H - 1) >> 5) m |= 1u << ((H - 1) & 31);
+    return m & v;
+}
+
+__device__ __forceinline__ uint32_t& plane_word(const DevState& s, int p, int env, int x, int w) {
+    return s.planes[word_index(s, p, env, x, w)];
+}
+__device__ __forceinline__ bool get_bit(const DevState& s, int p, int env, int x, int y) {
+    return (s.planes[word_index(s, p, env, x, y >> 5)] >> (y & 31)) & 1u;
+}
+
+// Agent.dig (environment.py:123-133) on planes in HBM + incremental maintenance of the reach plane.
+__device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, int y) {
+    const int w = y >> 5;
+    const uint32_t bit = 1u << (y & 31);
+    uint32_t& D = plane_word(s, P_D, env, x, w);
+    if (D & bit) return;
+    plane_word(s, P_G, env, x, w) &= ~bit;
+    plane_word(s, P_F, env, x, w) &= ~bit;
+    plane_word(s, P_BT, env, x, w) &= ~bit;
+    plane_word(s, P_WT, env, x, w) &= ~bit;
+    D |= bit;
+    uint32_t& I = plane_word(s, P_I, env, x, w);
+    const bool was_free = !(I & bit);
+    I |= bit;
+    if (!was_free) return;
+    uint32_t& R = plane_word(s, t.P_R, env, x, w);
+    if (!(R & bit)) return;  // the cell had no path to the border: nobody reached the border through it
+    R &= ~bit;
+    // Does removing this cell possibly disconnect its neighbours from the border?  Its free 4-neighbours
+    // were all in R.  If they stay connected to each other through the ring of 8 surrounding cells,
+    // every path through the dug cell can be re-routed and R is unchanged elsewhere ("simple point").
+    const int W = s.W, H = s.H;
+    const bool on_seed = (x == 0 || x == H - 1 || y == 0 || y == H - 1);
+    bool f[8];  // N, NE, E, SE, S, SW, W, NW  (screen coordinates: N = y-1, E = x+1)
+    const int dx[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int nx = x + dx[k], ny = y + dy[k];
+        f[k] = (nx >= 0 && nx < W && ny >= 0 && ny < H) && !get_bit(s, P_I, env, nx, ny);
+    }
+    int n4 = 0, groups = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        if (!f[k]) continue;
+        n4++;
+        // this 4-neighbour starts a new group unless it is ring-connected to the previous 4-neighbour
+        const int pk = (k + 6) & 7, pd = (k + 7) & 7;
+        if (!(f[pk] && f[pd])) groups++;
+    }
+    if (n4 == 4 && groups == 0) groups = 1;  // full ring
+    if (on_seed ? n4 > 0 : groups > 1) t.need_flood[env] = 1;
+}
+
+// World.set_fire_to (environment.py:233-246) on planes in HBM (keeps the source mask consistent).
+__device__ void tile_set_fire(const DevState& s, const TileState& t, int env, int x, int y, int32_t* sc) {
+    const int w = y >> 5;
+    const uint32_t bit = 1u << (y & 31);
+    plane_word(s, P_G, env, x, w) &= ~bit;
+    plane_word(s, P_BT, env, x, w) &= ~bit;
+    plane_word(s, P_D, env, x, w) &= ~bit;
+    plane_word(s, P_WT, env, x, w) &= ~bit;
+    plane_word(s, P_F, env, x, w) |= bit;
+    plane_word(s, P_B, env, x, w) |= bit;
+    uint32_t ge2 = 0u;
+    for (int q = 1; q < s.FB; ++q) ge2 |= plane_word(s, P_FU0 + q, env, x, w);
+    if (ge2 & bit) plane_word(s, t.cur ? t.P_S1 : t.P_S0, env, x, w) |= bit;
+    if (x == 0 || x == s.W - 1 || y == 0 || y == s.H - 1) sc[WF_S_FIRE_AT_BORDER] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
+// steps, Agent.is_dead (:116-120).  One thread per env.
+__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.N) return;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    int32_t* acc = t.acc + 4 * env;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0;
+    sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
+    if (!sc[WF_S_RUNNING]) return;
+    int action;
+    if (actions != nullptr) {
+        action = actions[env];
+    } else {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T], kStreamAction,
+                      c.key0, c.key1, w);
+        action = (int)(w[0] % (uint32_t)c.n_actions);
+    }
+    int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
+    if (sc[WF_S_ALIVE]) {
+        if (action >= 0 && action < 4) {
+            sc[WF_S_VISIBLE] = 0;  // Q1
+            const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
+            const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
+            if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
+                ax = nx; ay = ny;
+                sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
+                const bool onfire = get_bit(s, P_F, env, nx, ny);
+                if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny);
+                if (onfire) sc[WF_S_DEAD] = 1;
+            }
+        }
+        if (c.allow_dig_toggle && action == 4) {
+            sc[WF_S_DIGGING] ^= 1;
+            if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay);
+        }
+        if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
+            sc[WF_S_VISIBLE] = 0;
+            sc[WF_S_ALIVE] = 0;
+            atomicAdd(&s.stats[ST_DEATHS], 1ull);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reach plane: R = finite cells 4-connected to a finite border point (flood from the border over
+// ~fm_inf).  One block per env; in-place monotone relaxation until a whole sweep changes nothing.
+__global__ void __launch_bounds__(1024) flood_kernel(DevState s, TileState t) {
+    const int env = blockIdx.x;
+    if (!t.need_flood[env]) return;
+    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
+    uint32_t* R = &plane_word(s, t.P_R, env, 0, 0);
+    const uint32_t* I = &plane_word(s, P_I, env, 0, 0);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const int x = i / HW, w = i - x * HW;
+        R[i] = seed_word(W, H, x, w) & ~I[i];
+    }
+    __syncthreads();
+    for (;;) {
+        int changed = 0;
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+            const int x = i / HW, w = i - x * HW;
+            const uint32_t free_ = ~I[i] & valid_word(H, w);
+            if (!free_) continue;
+            const uint32_t old = R[i];
+            uint32_t n = old;
+            if (x > 0) n |= R[i - HW];
+            if (x < W - 1) n |= R[i + HW];
+            if (w > 0) n |= R[i - 1] >> 31;
+            if (w < HW - 1) n |= R[i + 1] << 31;
+            n = hfill(n & free_, free_);
+            if (n != old) {
+                R[i] = n;
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (threadIdx.x == 0) t.need_flood[env] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The hot kernel.  mode 0: step (tick iff do_tick), mode 1: observation only, for envs with do_reset set.
+template <int FB>
+__global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, StepCfg c, TileState t, void* obs,
+                                                                 int obs_dtype, int do_tick, int mode) {
+    __shared__ uint32_t spread3[256];
+    __shared__ int red[4];
+    const int env = blockIdx.y;
+    if (mode == 1 && !t.do_reset[env]) return;
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
+        spread3[v] = o;
+    }
+    if (threadIdx.x < 4) red[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    const bool act = mode == 0 && sc[WF_S_RESERVED] != 0;
+    int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
+    if (i < nwords) {
+        const int x = i / HW, w = i - x * HW;
+        const uint32_t valid = valid_word(H, w);
+        const size_t base = word_index(s, 0, env, 0, 0) + i;  // + plane * pstride
+        const size_t pstride = (size_t)s.N * s.RS * s.HW;
+        uint32_t* P = s.planes + base;
+        uint32_t G = P[P_G * pstride], F = P[P_F * pstride], B = P[P_B * pstride];
+        const uint32_t I = P[P_I * pstride];
+        if (act && do_tick) {
+            const uint32_t* Sc = P + (size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride;
+            uint32_t* Sn = P + (size_t)(t.cur ? t.P_S0 : t.P_S1) * pstride;
+            const uint32_t S = Sc[0];
+            const uint32_t Sup = x > 0 ? Sc[-HW] : 0u, Sdn = x < W - 1 ? Sc[HW] : 0u;
+            const uint32_t Sprev = w > 0 ? Sc[-1] : 0u, Snext = w < HW - 1 ? Sc[1] : 0u;
+            const uint32_t h0 = G & ((S >> 1) | (Snext << 31));  // d = N (0,-1): source at y+1
+            const uint32_t h1 = G & ((S << 1) | (Sprev >> 31));  // d = S (0,+1): source at y-1
+            const uint32_t h2 = G & Sup;                         // d = E (+1,0): source at x-1
+            const uint32_t h3 = G & Sdn;                         // d = W (-1,0): source at x+1
+            uint32_t m = h0 | h1 | h2 | h3;
+            uint32_t Snew = 0u;
+            if (B | m) {  // active word
+                uint32_t FU[FB];
+#pragma unroll
+                for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
+                uint32_t BT = P[P_BT * pstride], D = P[P_D * pstride], WT = P[P_WT * pstride];
+                // reduce_fuel :297-307
+                uint32_t borrow = B;
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    const uint32_t f = FU[q];
+                    FU[q] = f ^ borrow;
+                    borrow &= ~f;
+                }
+                uint32_t nz = 0u;
+#pragma unroll
+                for (int q = 0; q < FB; ++q) {
+                    FU[q] &= ~borrow;
+                    nz |= FU[q];
+                }
+                const uint32_t out = B & ~nz;
+                if (B) {
+#pragma unroll
+                    for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
+                }
+                if (out) {
+                    BT |= out; F &= ~out; D &= ~out; WT &= ~out; G &= ~out; B &= ~out;
+                    P[P_BT * pstride] = BT; P[P_D * pstride] = D; P[P_WT * pstride] = WT;
+                }
+                // apply_heat_from_to :278-294 on the heated grass cells
+                uint32_t ign = 0u;
+                if (m) {
+                    const int wid = sc[WF_S_WIND_ID];
+                    const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
+                    uint32_t* hrow = s.hits + ((size_t)env * W + x) * H + 32 * w;
+                    while (m) {
+                        const int y = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const uint32_t v = hrow[y] + (((h0 >> y) & 1u) | (((h1 >> y) & 1u) << 8) |
+                                                      (((h2 >> y) & 1u) << 16) | (((h3 >> y) & 1u) << 24));
+                        hrow[y] = v;
+                        const bool ig = kmin >= 0 ? (int)__dp4a(v, 0x01010101u, 0u) >= kmin
+                                                  : ignites(v, s.wind, wid, c.threshold);
+                        if (ig) ign |= 1u << y;
+                    }
+                }
+                G &= ~ign; F |= ign; B |= ign;
+                if (ign | out) {
+                    P[P_G * pstride] = G; P[P_F * pstride] = F; P[P_B * pstride] = B;
+                }
+                if (ign & edge_word(W, H, x, w)) my_edge = 1;
+                // sources of the next tick: burning with fuel >= 2.  Cells ignited now still hold the reset fuel.
+                uint32_t ge2 = 0u;
+#pragma unroll
+                for (int q = 1; q < FB; ++q) ge2 |= FU[q];
+                Snew = B & ge2;
+            }
+            Sn[0] = Snew;
+        }
+        my_nb = __popc(B);
+        my_ng = __popc(G);
+        if (mode == 0 && B) {  // does a burning cell sit in, or next to, the border-connected region?
+            const uint32_t* R = P + (size_t)t.P_R * pstride;
+            uint32_t near = R[0];
+            near |= (near << 1) | (near >> 1);
+            if (x > 0) near |= R[-HW];
+            if (x < W - 1) near |= R[HW];
+            if (w > 0) near |= R[-1] >> 31;
+            if (w < HW - 1) near |= R[1] << 31;
+            if (B & near) my_touch = 1;
+        }
+        // ---- World.get_state :399-402 -> 32 cells x 3 channels
+        if (obs != nullptr) {
+            const uint32_t arow = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && (sc[WF_S_AY] >> 5) == w) ? 1u << (sc[WF_S_AY] & 31) : 0u;
+            const uint32_t freerow = ~I & valid;
+            const int ncell = min(32, H - 32 * w);
+            const size_t e0 = (((size_t)env * W + x) * H + 32 * w) * 3;  // first output element of this word
+            uint32_t r[3];
+            {
+                uint32_t p[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    p[k] = spread3[(arow >> (8 * k)) & 255u] | (spread3[(F >> (8 * k)) & 255u] << 1) |
+                           (spread3[(freerow >> (8 * k)) & 255u] << 2);
+                r[0] = p[0] | (p[1] << 24);
+                r[1] = (p[1] >> 8) | (p[2] << 16);
+                r[2] = (p[2] >> 16) | (p[3] << 8);
+            }
+            if (obs_dtype == WF_OBS_U8) {
+                uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
+                if (ncell == 32 && (reinterpret_cast<uintptr_t>(o8) & 15u) == 0) {
+                    uint4* o = reinterpret_cast<uint4*>(o8);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {  // 16 stream bits -> 16 bytes
+                        const uint32_t bits = (r[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                        uint4 v;
+                        v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+                        v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+                        v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+                        v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+                        o[k] = v;
+                    }
+                } else {
+                    for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
+                }
+            } else {
+                float* of = static_cast<float*>(obs) + e0;
+                for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+            }
+        }
+    }
+    if (mode == 1) return;
+    // ---- per-env reductions: warp shuffle -> shared -> one atomic per block and quantity
+    const unsigned FULL = 0xffffffffu;
+    for (int o = 16; o > 0; o >>= 1) {
+        my_nb += __shfl_xor_sync(FULL, my_nb, o);
+        my_ng += __shfl_xor_sync(FULL, my_ng, o);
+    }
+    my_edge = __any_sync(FULL, my_edge);
+    my_touch = __any_sync(FULL, my_touch);
+    if ((threadIdx.x & 31) == 0) {
+        if (my_nb) atomicAdd(&red[0], my_nb);
+        if (my_ng) atomicAdd(&red[1], my_ng);
+        if (my_edge) atomicOr(&red[2], 1);
+        if (my_touch) atomicOr(&red[3], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && red[threadIdx.x]) {
+        int32_t* acc = t.acc + 4 * env;
+        if (threadIdx.x < 2) atomicAdd(&acc[threadIdx.x], red[threadIdx.x]);
+        else atomicOr(&acc[threadIdx.x], 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ForestFire.step part 3: RUNNING flag (forest_fire.py:105-106), World.get_reward (environment.py:342-390).
+__global__ void finish_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.N) return;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    const int32_t* acc = t.acc + 4 * env;
+    const bool act = sc[WF_S_RESERVED] != 0;
+    double rew = 0.0;
+    if (act) {
+        const bool anyB = acc[0] > 0;
+        sc[WF_S_N_BURNING] = acc[0];
+        if (do_tick) {
+            if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
+            if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
+        }
+        const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
+        if (check && !acc[3]) {
+            sc[WF_S_LATCHED] = 1;
+            rew = c.contained_bonus;
+            atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+        } else if (!sc[WF_S_ALIVE]) {
+            rew = c.death_penalty;
+        } else if (!anyB) {
+            rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
+        } else {
+            rew = c.default_reward;
+        }
+        sc[WF_S_T] += 1;
+        atomicAdd(&s.stats[ST_STEPS], 1ull);
+        if (!sc[WF_S_RUNNING]) {
+            atomicAdd(&s.stats[ST_EPISODES], 1ull);
+            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
+        }
+    }
+    const bool is_done = !sc[WF_S_RUNNING];
+    if (reward) reward[env] = rew;
+    if (done) done[env] = is_done ? 1 : 0;
+    t.do_reset[env] = (c.auto_reset && act && is_done) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// World.reset (environment.py:186-212) for flagged envs: planes in parallel, then the sequential part.
+template <int FB>
+__global__ void __launch_bounds__(kTileThreads) reset_planes_kernel(DevState s, StepCfg c, TileState t) {
+    const int env = blockIdx.y;
+    if (!t.do_reset[env]) return;
+    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const int x = i / HW, w = i - x * HW;
+    const uint32_t valid = valid_word(H, w);
+    const size_t pstride = (size_t)s.N * s.RS * s.HW;
+    uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+    P[P_G * pstride] = valid;
+    P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
+    P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
+#pragma unroll
+    for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
+    P[(size_t)t.P_S0 * pstride] = 0u;
+    P[(size_t)t.P_S1 * pstride] = 0u;
+    P[(size_t)t.P_R * pstride] = valid;
+    uint32_t* hrow = s.hits + ((size_t)env * W + x) * H + 32 * w;
+    const int ncell = min(32, H - 32 * w);
+    for (int b = 0; b < ncell; ++b) hrow[b] = 0u;
+}
+
+__global__ void reset_agent_kernel(DevState s, StepCfg c, TileState t, const wf_init* init) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= s.N || !t.do_reset[env]) return;
+    const int W = s.W, H = s.H;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;
+    ResetDraws dr((uint32_t)(c.env_id_base + env), episode, c.key0, c.key1);
+    int wid = 0;
+    if (c.wind_random) {
+        const int si = dr.next() % 3u, wx = dr.next() % 3u, wy = dr.next() % 3u;
+        wid = si * 9 + wx * 3 + wy;
+    }
+    const int cx = W / 2, cy = H / 2;
+    if (c.make_rivers) {  // reset_map :69-95
+        int river_x = dr.next() % (uint32_t)W;
+        int river_y = 1 + dr.next() % 3u;
+        while (river_y < H - (1 + (int)(dr.next() % 3u))) {
+            const uint32_t bit = 1u << (river_y & 31);
+            plane_word(s, P_G, env, river_x, river_y >> 5) &= ~bit;
+            plane_word(s, P_WT, env, river_x, river_y >> 5) |= bit;
+            plane_word(s, P_I, env, river_x, river_y >> 5) |= bit;
+            const int new_y = river_y + 1;
+            int new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+            for (;;) {
+                const int lo = 1 + dr.next() % 3u;
+                bool chain = false;
+                if (lo <= new_x) chain = new_x < W - (1 + (int)(dr.next() % 3u));
+                if (chain || (new_x == cx && new_y == cy)) break;
+                new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+            }
+            river_x = new_x;
+            river_y = new_y;
+        }
+    }
+    sc[WF_S_FIRE_AT_BORDER] = 0;
+    tile_set_fire(s, t, env, cx, cy, sc);
+    int ax, ay;
+    if (init != nullptr && init[env].ax >= 0) {
+        ax = init[env].ax; ay = init[env].ay;
+    } else {
+        const int rad = dr.next() % 3u;
+        const int idx = dr.next() % (uint32_t)kCircleLen[rad];
+        ax = cx + kCircle[rad][idx][0];
+        ay = cy + kCircle[rad][idx][1];
+    }
+    {  // Agent.__init__ digs its start cell (:112-113); the reach plane is re-flooded below anyway
+        const uint32_t bit = 1u << (ay & 31);
+        const int w = ay >> 5;
+        plane_word(s, P_G, env, ax, w) &= ~bit; plane_word(s, P_F, env, ax, w) &= ~bit;
+        plane_word(s, P_BT, env, ax, w) &= ~bit; plane_word(s, P_WT, env, ax, w) &= ~bit;
+        plane_word(s, P_D, env, ax, w) |= bit; plane_word(s, P_I, env, ax, w) |= bit;
+    }
+    sc[WF_S_FIRE_AT_BORDER] = 0;  // :212
+    for (int k = 0; k < c.extra_ignitions; ++k) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(c.env_id_base + env), episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, w);
+        tile_set_fire(s, t, env, (int)(w[0] % (uint32_t)W), (int)(w[1] % (uint32_t)H), sc);
+    }
+    sc[WF_S_ALIVE] = 1; sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_DEAD] = 0; sc[WF_S_DIGGING] = 1;
+    sc[WF_S_VISIBLE] = 1; sc[WF_S_RUNNING] = 1; sc[WF_S_LATCHED] = 0;
+    sc[WF_S_EPISODE] = (int32_t)episode; sc[WF_S_T] = 0; sc[WF_S_WIND_ID] = wid;
+    sc[WF_S_WIND_X] = s.wind->wx[wid]; sc[WF_S_WIND_Y] = s.wind->wy[wid];
+    int nb = 0;  // burning cells = distinct ignition cells; counted by the first tile_step, approximate here
+    sc[WF_S_N_BURNING] = nb;
+    t.need_flood[env] = 1;
+}
+
+// number of burning cells after a reset / set_state (exact), one block per env
+__global__ void count_burning_kernel(DevState s, TileState t, int only_reset) {
+    const int env = blockIdx.x;
+    if (only_reset && !t.do_reset[env]) return;
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const int nwords = s.W * s.HW;
+    const uint32_t* B = &plane_word(s, P_B, env, 0, 0);
+    int n = 0;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) n += __popc(B[i]);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&total, n);
+    __syncthreads();
+    if (threadIdx.x == 0) s.scal[(size_t)env * WF_NSCALARS + WF_S_N_BURNING] = total;
+}
+
+__global__ void set_reset_mask_kernel(TileState t, const uint8_t* mask, int n) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < n) t.do_reset[env] = (mask == nullptr || mask[env]) ? 1 : 0;
+}
+
+// S := B & (fuel >= 2), need_flood := 1 for every env (after wf_set_state / wf_set_fire_to)
+__global__ void rebuild_sources_kernel(DevState s, TileState t) {
+    const int env = blockIdx.y;
+    const int nwords = s.W * s.HW;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) t.need_flood[env] = 1;
+    if (i >= nwords) return;
+    const size_t pstride = (size_t)s.N * s.RS * s.HW;
+    uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+    uint32_t ge2 = 0u;
+    for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * pstride];
+    P[(size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride] = P[P_B * pstride] & ge2;
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
+    TileState* t = new TileState();
+    t->cur = 0;
+    t->P_S0 = 7 + s.FB;
+    t->P_S1 = 8 + s.FB;
+    t->P_R = 9 + s.FB;
+    t->flood_smem_ok = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->acc, (size_t)s.N * 4 * sizeof(int32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->need_flood, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->do_reset, (size_t)s.N)) != cudaSuccess) return e;
+    cudaMemset(t->acc, 0, (size_t)s.N * 4 * sizeof(int32_t));
+    cudaMemset(t->need_flood, 0, (size_t)s.N * sizeof(int32_t));
+    cudaMemset(t->do_reset, 0, (size_t)s.N);
+    *out = t;
+    return cudaSuccess;
+}
+
+void tile_destroy(TileState* t) {
+    if (!t) return;
+    cudaFree(t->acc); cudaFree(t->need_flood); cudaFree(t->do_reset);
+    delete t;
+}
+
+template <int FB>
+static cudaError_t run_reset(TileState* t, const DevState& s, const StepCfg& c, const wf_init* init, void* obs,
+                             int obs_dtype, cudaStream_t st, int64_t* launches) {
+    const int nwords = s.W * s.HW;
+    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
+    reset_planes_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t);
+    reset_agent_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, init);
+    flood_kernel<<<s.N, 1024, 0, st>>>(s, *t);
+    count_burning_kernel<<<s.N, 256, 0, st>>>(s, *t, 1);
+    *launches += 4;
+    if (obs) {
+        tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, obs, obs_dtype, 0, 1);
+        *launches += 1;
+    }
+    return cudaGetLastError();
+}
+
+template <int FB>
+static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st,
+                              int64_t* launches) {
+    const int nwords = s.W * s.HW;
+    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
+    if (io.reset_mode) {
+        set_reset_mask_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(*t, io.mask, s.N);
+        *launches += 1;
+        // obs of envs that are NOT reset must still be delivered: write all, then the reset ones again
+        cudaError_t e = run_reset<FB>(t, s, c, io.init, nullptr, io.obs_dtype, st, launches);
+        if (e != cudaSuccess) return e;
+        if (io.obs) {
+            set_reset_mask_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(*t, nullptr, s.N);
+            tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.obs, io.obs_dtype, 0, 1);
+            *launches += 2;
+        }
+        return cudaGetLastError();
+    }
+    agent_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick);
+    flood_kernel<<<s.N, 1024, 0, st>>>(s, *t);
+    tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.obs, io.obs_dtype, io.do_tick, 0);
+    if (io.do_tick) t->cur ^= 1;
+    finish_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick);
+    *launches += 4;
+    if (c.auto_reset) {
+        cudaError_t e = run_reset<FB>(t, s, c, nullptr, io.obs, io.obs_dtype, st, launches);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io,
+                               cudaStream_t stream, int64_t* launches) {
+    if (s.FB == 5) return run_family<5>(t, s, c, io, stream, launches);
+    return run_family<8>(t, s, c, io, stream, launches);
+}
+
+cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg&, cudaStream_t stream,
+                                 int64_t* launches) {
+    const int nwords = s.W * s.HW;
+    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
+    rebuild_sources_kernel<<<grid, kTileThreads, 0, stream>>>(s, *t);
+    flood_kernel<<<s.N, 1024, 0, stream>>>(s, *t);
+    count_burning_kernel<<<s.N, 256, 0, stream>>>(s, *t, 0);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
 }  // namespace wf

@@ -32,7 +32,9 @@ struct Rows {
 
 struct Agent {
     int ax, ay, alive, dead, digging, vis, running, fab, latched, wid, nburn;
+    int kmin;  // uniform wind: total hits that ignite a cell; -1 = direction-dependent quanta
     uint32_t episode, t;
+    __device__ __forceinline__ void refresh_wind(const WindTable* wt) { kmin = wt->uniform[wid] ? wt->kmin[wid] : -1; }
 };
 
 constexpr int kWarpsPerBlock = 4;
@@ -132,41 +134,60 @@ __device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepC
 }
 
 // World.get_state -- environment.py:399-402: [agent_pos, type == fire, fire_mobility != inf].
-// The three row masks of every lane are staged in shared memory, then the env's L lanes write the
-// [W][H][3] block with consecutive lanes on consecutive 4-byte words (coalesced).
+// Output element e = (x*H + y)*3 + ch of an env is ONE BIT, so the env's whole [W][H][3] block is a
+// bit stream: row x contributes 3H bits (its three masks interleaved bit by bit) at bit offset 3H*x.
+// Each lane interleaves its row with a 256-entry "spread by 3" table, ORs it into the env's stream in
+// shared memory, and then consecutive lanes expand consecutive nibbles of the stream into consecutive
+// 4-byte words of the output (coalesced 64/128-byte stores, ~7 instructions per word).
+constexpr int kStreamWords = 100;  // 3*32*32/32 = 96 words + spill-over of the last row's funnel shift
+
 template <int L>
 __device__ __forceinline__ void emit_obs(void* obs_env, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
-                                         uint32_t (*stage)[32], int lane, int sub, int x, int W, int H,
-                                         uint32_t magicH, bool valid_env) {
+                                         uint32_t* stream_warp, const uint32_t* spread3, int sub, int x, int W, int H,
+                                         bool valid_env) {
+    constexpr int EPW = 32 / L;
+    uint32_t* stream = stream_warp + sub * (kStreamWords / EPW);
+    const int nbits = W * H * 3;
+    const int nw = (nbits + 31) >> 5;
     __syncwarp();
-    stage[0][lane] = arow;
-    stage[1][lane] = frow;
-    stage[2][lane] = freerow;
+    for (int w = x; w < nw + 4 && w < kStreamWords / EPW; w += L) stream[w] = 0u;
+    __syncwarp();
+    if (x < W) {
+        auto piece = [&](int p) -> uint32_t {  // cells 8p..8p+7 of this row -> 24 interleaved bits
+            return spread3[(arow >> (8 * p)) & 255u] | (spread3[(frow >> (8 * p)) & 255u] << 1) |
+                   (spread3[(freerow >> (8 * p)) & 255u] << 2);
+        };
+        const uint32_t p0 = piece(0), p1 = piece(1);
+        uint32_t r0 = p0 | (p1 << 24), r1 = p1 >> 8, r2 = 0u;
+        if (L == 32 && H > 16) {
+            const uint32_t p2 = piece(2), p3 = piece(3);
+            r1 |= p2 << 16;
+            r2 = (p2 >> 16) | (p3 << 8);
+        }
+        const int start = 3 * H * x, w0 = start >> 5, sh = start & 31;
+        const uint32_t c0 = r0 << sh, c1 = __funnelshift_l(r0, r1, sh), c2 = __funnelshift_l(r1, r2, sh),
+                       c3 = __funnelshift_l(r2, 0u, sh);
+        if (c0) atomicOr(&stream[w0], c0);
+        if (c1) atomicOr(&stream[w0 + 1], c1);
+        if (c2) atomicOr(&stream[w0 + 2], c2);
+        if (c3) atomicOr(&stream[w0 + 3], c3);
+    }
     __syncwarp();
     if (!valid_env) return;
-    const int nbytes = W * H * 3;
-    const uint32_t* s0 = &stage[0][sub * L];
-    auto bit_of = [&](int b) -> uint32_t {  // element b of the flattened (x*H + y)*3 + ch block
-        const uint32_t cell = __umulhi((uint32_t)b, 1431655766u);  // b / 3
-        const uint32_t ch = b - 3u * cell;
-        const uint32_t xx = __umulhi(cell, magicH);  // cell / H
-        const uint32_t yy = cell - xx * H;
-        return (s0[ch * 32 + xx] >> yy) & 1u;
-    };
     if (dtype == WF_OBS_U8) {
         uint8_t* o8 = static_cast<uint8_t*>(obs_env);
-        if ((nbytes & 3) == 0) {
+        if ((nbits & 3) == 0) {
             uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
-            for (int j = x; j < (nbytes >> 2); j += L) {
-                const int b = 4 * j;
-                o32[j] = bit_of(b) | (bit_of(b + 1) << 8) | (bit_of(b + 2) << 16) | (bit_of(b + 3) << 24);
+            for (int j = x; j < (nbits >> 2); j += L) {  // output word j = stream bits 4j..4j+3, one per byte
+                const uint32_t nib = (stream[j >> 3] >> ((j & 7) * 4)) & 15u;
+                o32[j] = (nib * 0x00204081u) & 0x01010101u;
             }
         } else {
-            for (int b = x; b < nbytes; b += L) o8[b] = (uint8_t)bit_of(b);
+            for (int b = x; b < nbits; b += L) o8[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
         }
     } else {
         float* of = static_cast<float*>(obs_env);
-        for (int b = x; b < nbytes; b += L) of[b] = bit_of(b) ? 1.0f : 0.0f;
+        for (int b = x; b < nbits; b += L) of[b] = ((stream[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
     }
 }
 
@@ -175,7 +196,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
-    __shared__ uint32_t stage_all[kWarpsPerBlock][3][32];
+    __shared__ uint32_t stream_all[kWarpsPerBlock][kStreamWords];
+    __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
+        spread3[v] = o;
+    }
+    __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / L, x = lane % L;
@@ -188,7 +217,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     const uint32_t seedmask = (x == 0 || x == H - 1) ? validmask : (validmask & (1u | (1u << (H - 1))));
     const uint32_t edgemask = (x == 0 || x == W - 1) ? validmask : (validmask & (1u | (1u << (H - 1))));
     auto group_bits = [&](uint32_t ballot) -> uint32_t { return (ballot >> (sub * L)) & GMASK; };
-    uint32_t(*stage)[32] = stage_all[warp];
+    uint32_t* stream_warp = stream_all[warp];
 
     // ---------------- load ----------------
     Rows<FB> r;
@@ -207,19 +236,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
         a.nburn = v3.z;
     }
     if (!valid_env) { a.running = 0; a.alive = 0; a.ax = a.ay = 0; a.wid = 0; }
+    a.refresh_wind(s.wind);
 
     long long n_steps_done = 0;
 
     if (io.reset_mode) {
         // ---------------- ForestFire.reset() ----------------
         const bool doit = valid_env && (io.mask == nullptr || io.mask[env] != 0);
-        if (doit) reset_rows<L, FB>(r, a, s, c, io.init, env, x, validmask);
+        if (doit) {
+            reset_rows<L, FB>(r, a, s, c, io.init, env, x, validmask);
+            a.refresh_wind(s.wind);
+        }
         __syncwarp();
         if (io.obs != nullptr) {
             const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
             emit_obs<L>(static_cast<char*>(io.obs) + (size_t)(valid_env ? env : 0) * esz, io.obs_dtype,
-                        (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stage, lane, sub, x, W, H,
-                        io.magicH, valid_env);
+                        (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, sub, x,
+                        W, H, valid_env);
         }
     } else {
         // ---------------- K x ForestFire.step(action) ----------------
@@ -307,7 +340,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                     const uint32_t v = hrow[y] + (((h0 >> y) & 1u) | (((h1 >> y) & 1u) << 8) |
                                                   (((h2 >> y) & 1u) << 16) | (((h3 >> y) & 1u) << 24));
                     hrow[y] = v;
-                    if (ignites(v, s.wind, a.wid, c.threshold)) ign |= 1u << y;
+                    const bool ig = a.kmin >= 0 ? (int)__dp4a(v, 0x01010101u, 0u) >= a.kmin
+                                                : ignites(v, s.wind, a.wid, c.threshold);
+                    if (ig) ign |= 1u << y;
                 }
                 r.G &= ~ign;  // set_fire_to :233-246
                 r.F |= ign;
@@ -380,13 +415,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                 if (io.done != nullptr) io.done[(size_t)k * s.N + env] = done ? 1 : 0;
             }
             // ---- auto-reset (batched-env convention: the returned obs is the new episode's first)
-            if (c.auto_reset && act && done) reset_rows<L, FB>(r, a, s, c, nullptr, env, x, validmask);
+            if (c.auto_reset && act && done) {
+                reset_rows<L, FB>(r, a, s, c, nullptr, env, x, validmask);
+                a.refresh_wind(s.wind);
+            }
             __syncwarp();
             if (io.obs != nullptr) {
                 const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
                 emit_obs<L>(static_cast<char*>(io.obs) + ((size_t)k * s.N + (valid_env ? env : 0)) * esz, io.obs_dtype,
-                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stage, lane, sub, x, W,
-                            H, io.magicH, valid_env);
+                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, sub,
+                            x, W, H, valid_env);
             }
         }
     }
