@@ -279,3 +279,22 @@ def test_errors_are_reported_not_thrown():
         BatchedForestFire(1, width=8, height=8)
     with pytest.raises(L.WildfireError, match="HEIGHT-1"):
         BatchedForestFire(1, width=10, height=12)
+
+
+def test_trajectories_do_not_depend_on_sharding():
+    """Two handles with env_id_base 0 / 16 (16 envs each) == one handle with 32 envs."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    cfg = dict(width=14, height=14, seed=901, wind="random", auto_reset=True)
+    whole = BatchedForestFire(32, **cfg)
+    lo = BatchedForestFire(16, env_id_base=0, **cfg)
+    hi = BatchedForestFire(16, env_id_base=16, **cfg)
+    o = whole.reset()
+    assert torch.equal(o[:16], lo.reset()) and torch.equal(o[16:], hi.reset())
+    ow, rw, dw = whole.rollout(200)
+    ol, rl, dl = lo.rollout(200)
+    oh, rh, dh = hi.rollout(200)
+    assert torch.equal(ow[:, :16], ol) and torch.equal(ow[:, 16:], oh)
+    assert torch.equal(rw[:, :16], rl) and torch.equal(rw[:, 16:], rh)
+    assert torch.equal(dw[:, :16], dl) and torch.equal(dw[:, 16:], dh)
+    a, b, c = whole.stats(), lo.stats(), hi.stats()
+    assert all(a[k] == b[k] + c[k] for k in a)

@@ -10,11 +10,12 @@
 // containment search (environment.py:342-377) is a persistent "reach" plane R (cells with a finite
 // 4-connected path to a finite border point) that is re-flooded only when a dig may disconnect it.
 //
-// One step = agent_kernel (1 thread/env: move/dig/reap + local articulation test)
-//          -> flood_kernel (1 block/env, exits at once unless flagged)
-//          -> tile_step_kernel (the HBM-bound stencil + obs + per-env reductions)
-//          -> finish_kernel (1 thread/env: reward, done, latch, stats)
-//          [-> reset kernels for the envs that finished, when auto_reset]
+// One step = pre_kernel  (1 CTA/env: thread 0 moves/digs/reaps + local articulation test; the CTA
+//                         re-floods R only when that test says a dig may have disconnected something)
+//          -> tile_tick_kernel (the stencil: fuel, heat, ignition, per-env reductions)
+//          -> post_kernel (1 CTA/env: thread 0 computes reward/done/latch; if the env finished and
+//                          auto_reset is on, the CTA re-initialises it: World.reset)
+//          -> obs_kernel  (World.get_state of every env: 2 bits/cell in, 3 bytes/cell out)
 #include "wf_families.cuh"
 
 namespace wf {
@@ -24,7 +25,6 @@ constexpr int kTileThreads = 256;
 struct TileState {
     int32_t* acc;         // [N][4]: burning cells, grass cells, ignition-on-edge flag, burning-touches-reach flag
     int32_t* need_flood;  // [N]
-    uint8_t* do_reset;    // [N]
     int32_t cur;          // which of the two S planes holds the sources of the NEXT tick
     int32_t P_S0, P_S1, P_R;
     int32_t flood_smem_ok;
@@ -122,57 +122,9 @@ __device__ void tile_set_fire(const DevState& s, const TileState& t, int env, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
-// steps, Agent.is_dead (:116-120).  One thread per env.
-__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= s.N) return;
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    int32_t* acc = t.acc + 4 * env;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0;
-    sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
-    if (!sc[WF_S_RUNNING]) return;
-    int action;
-    if (actions != nullptr) {
-        action = actions[env];
-    } else {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T], kStreamAction,
-                      c.key0, c.key1, w);
-        action = (int)(w[0] % (uint32_t)c.n_actions);
-    }
-    int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
-    if (sc[WF_S_ALIVE]) {
-        if (action >= 0 && action < 4) {
-            sc[WF_S_VISIBLE] = 0;  // Q1
-            const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
-            const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
-            if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
-                ax = nx; ay = ny;
-                sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
-                const bool onfire = get_bit(s, P_F, env, nx, ny);
-                if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny);
-                if (onfire) sc[WF_S_DEAD] = 1;
-            }
-        }
-        if (c.allow_dig_toggle && action == 4) {
-            sc[WF_S_DIGGING] ^= 1;
-            if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay);
-        }
-        if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
-            sc[WF_S_VISIBLE] = 0;
-            sc[WF_S_ALIVE] = 0;
-            atomicAdd(&s.stats[ST_DEATHS], 1ull);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Reach plane: R = finite cells 4-connected to a finite border point (flood from the border over
-// ~fm_inf).  One block per env; in-place monotone relaxation until a whole sweep changes nothing.
-__global__ void __launch_bounds__(1024) flood_kernel(DevState s, TileState t) {
-    const int env = blockIdx.x;
-    if (!t.need_flood[env]) return;
+// ~fm_inf).  Whole CTA; in-place monotone relaxation until a full sweep changes nothing.
+__device__ void flood_block(const DevState& s, const TileState& t, int env) {
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
     uint32_t* R = &plane_word(s, t.P_R, env, 0, 0);
     const uint32_t* I = &plane_word(s, P_I, env, 0, 0);
@@ -204,37 +156,73 @@ __global__ void __launch_bounds__(1024) flood_kernel(DevState s, TileState t) {
     if (threadIdx.x == 0) t.need_flood[env] = 0;
 }
 
+// ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
+// steps, Agent.is_dead (:116-120).  One CTA per env; only thread 0 works unless R must be re-flooded.
+__global__ void pre_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
+    const int env = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+        int32_t* acc = t.acc + 4 * env;
+        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+        sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
+        if (sc[WF_S_RUNNING]) {
+            int action;
+            if (actions != nullptr) {
+                action = actions[env];
+            } else {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T],
+                              kStreamAction, c.key0, c.key1, w);
+                action = (int)(w[0] % (uint32_t)c.n_actions);
+            }
+            int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
+            if (sc[WF_S_ALIVE]) {
+                if (action >= 0 && action < 4) {
+                    sc[WF_S_VISIBLE] = 0;  // Q1
+                    const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
+                    const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
+                    if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
+                        ax = nx; ay = ny;
+                        sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
+                        const bool onfire = get_bit(s, P_F, env, nx, ny);
+                        if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny);
+                        if (onfire) sc[WF_S_DEAD] = 1;
+                    }
+                }
+                if (c.allow_dig_toggle && action == 4) {
+                    sc[WF_S_DIGGING] ^= 1;
+                    if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay);
+                }
+                if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
+                    sc[WF_S_VISIBLE] = 0;
+                    sc[WF_S_ALIVE] = 0;
+                    atomicAdd(&s.stats[ST_DEATHS], 1ull);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (t.need_flood[env]) flood_block(s, t, env);
+}
+
 // ---------------------------------------------------------------------------------------------
-// The hot kernel.  mode 0: step (tick iff do_tick), mode 1: observation only, for envs with do_reset set.
+// The stencil.  One thread per word (32 cells).
 template <int FB>
-__global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, StepCfg c, TileState t, void* obs,
-                                                                 int obs_dtype, int do_tick, int mode) {
-    __shared__ uint32_t spread3[256];
+__global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, StepCfg c, TileState t, int do_tick) {
     __shared__ int red[4];
     const int env = blockIdx.y;
-    if (mode == 1 && !t.do_reset[env]) return;
-    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
-        uint32_t o = 0u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
-        spread3[v] = o;
-    }
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     __syncthreads();
-
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const bool act = mode == 0 && sc[WF_S_RESERVED] != 0;
+    const bool act = sc[WF_S_RESERVED] != 0;
     int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
     if (i < nwords) {
         const int x = i / HW, w = i - x * HW;
-        const uint32_t valid = valid_word(H, w);
-        const size_t base = word_index(s, 0, env, 0, 0) + i;  // + plane * pstride
         const size_t pstride = (size_t)s.N * s.RS * s.HW;
-        uint32_t* P = s.planes + base;
-        uint32_t G = P[P_G * pstride], F = P[P_F * pstride], B = P[P_B * pstride];
-        const uint32_t I = P[P_I * pstride];
+        uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+        uint32_t G = P[P_G * pstride], B = P[P_B * pstride];
         if (act && do_tick) {
             const uint32_t* Sc = P + (size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride;
             uint32_t* Sn = P + (size_t)(t.cur ? t.P_S0 : t.P_S1) * pstride;
@@ -247,11 +235,10 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
             const uint32_t h3 = G & Sdn;                         // d = W (-1,0): source at x+1
             uint32_t m = h0 | h1 | h2 | h3;
             uint32_t Snew = 0u;
-            if (B | m) {  // active word
+            if (B | m) {  // active word: it burns or it is heated
                 uint32_t FU[FB];
 #pragma unroll
                 for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
-                uint32_t BT = P[P_BT * pstride], D = P[P_D * pstride], WT = P[P_WT * pstride];
                 // reduce_fuel :297-307
                 uint32_t borrow = B;
 #pragma unroll
@@ -271,9 +258,13 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
 #pragma unroll
                     for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
                 }
-                if (out) {
-                    BT |= out; F &= ~out; D &= ~out; WT &= ~out; G &= ~out; B &= ~out;
-                    P[P_BT * pstride] = BT; P[P_D * pstride] = D; P[P_WT * pstride] = WT;
+                uint32_t F = 0u;
+                if (out) {  // type := burnt whatever it was (a dug-while-burning cell is dirt, Q7)
+                    F = P[P_F * pstride];
+                    P[P_BT * pstride] |= out;
+                    P[P_D * pstride] &= ~out;
+                    P[P_WT * pstride] &= ~out;
+                    F &= ~out; G &= ~out; B &= ~out;
                 }
                 // apply_heat_from_to :278-294 on the heated grass cells
                 uint32_t ign = 0u;
@@ -292,12 +283,13 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
                         if (ig) ign |= 1u << y;
                     }
                 }
-                G &= ~ign; F |= ign; B |= ign;
                 if (ign | out) {
+                    if (!out) F = P[P_F * pstride];
+                    G &= ~ign; F |= ign; B |= ign;
                     P[P_G * pstride] = G; P[P_F * pstride] = F; P[P_B * pstride] = B;
                 }
                 if (ign & edge_word(W, H, x, w)) my_edge = 1;
-                // sources of the next tick: burning with fuel >= 2.  Cells ignited now still hold the reset fuel.
+                // sources of the next tick: burning with fuel >= 2 (cells ignited now hold the reset fuel)
                 uint32_t ge2 = 0u;
 #pragma unroll
                 for (int q = 1; q < FB; ++q) ge2 |= FU[q];
@@ -307,7 +299,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
         }
         my_nb = __popc(B);
         my_ng = __popc(G);
-        if (mode == 0 && B) {  // does a burning cell sit in, or next to, the border-connected region?
+        if (B) {  // does a burning cell sit in, or next to, the border-connected region?
             const uint32_t* R = P + (size_t)t.P_R * pstride;
             uint32_t near = R[0];
             near |= (near << 1) | (near >> 1);
@@ -317,47 +309,7 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
             if (w < HW - 1) near |= R[1] << 31;
             if (B & near) my_touch = 1;
         }
-        // ---- World.get_state :399-402 -> 32 cells x 3 channels
-        if (obs != nullptr) {
-            const uint32_t arow = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && (sc[WF_S_AY] >> 5) == w) ? 1u << (sc[WF_S_AY] & 31) : 0u;
-            const uint32_t freerow = ~I & valid;
-            const int ncell = min(32, H - 32 * w);
-            const size_t e0 = (((size_t)env * W + x) * H + 32 * w) * 3;  // first output element of this word
-            uint32_t r[3];
-            {
-                uint32_t p[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    p[k] = spread3[(arow >> (8 * k)) & 255u] | (spread3[(F >> (8 * k)) & 255u] << 1) |
-                           (spread3[(freerow >> (8 * k)) & 255u] << 2);
-                r[0] = p[0] | (p[1] << 24);
-                r[1] = (p[1] >> 8) | (p[2] << 16);
-                r[2] = (p[2] >> 16) | (p[3] << 8);
-            }
-            if (obs_dtype == WF_OBS_U8) {
-                uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
-                if (ncell == 32 && (reinterpret_cast<uintptr_t>(o8) & 15u) == 0) {
-                    uint4* o = reinterpret_cast<uint4*>(o8);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {  // 16 stream bits -> 16 bytes
-                        const uint32_t bits = (r[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                        uint4 v;
-                        v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-                        v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-                        v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-                        v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-                        o[k] = v;
-                    }
-                } else {
-                    for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
-                }
-            } else {
-                float* of = static_cast<float*>(obs) + e0;
-                for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
-            }
-        }
     }
-    if (mode == 1) return;
     // ---- per-env reductions: warp shuffle -> shared -> one atomic per block and quantity
     const unsigned FULL = 0xffffffffu;
     for (int o = 16; o > 0; o >>= 1) {
@@ -381,173 +333,249 @@ __global__ void __launch_bounds__(kTileThreads) tile_step_kernel(DevState s, Ste
 }
 
 // ---------------------------------------------------------------------------------------------
-// ForestFire.step part 3: RUNNING flag (forest_fire.py:105-106), World.get_reward (environment.py:342-390).
-__global__ void finish_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= s.N) return;
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const int32_t* acc = t.acc + 4 * env;
-    const bool act = sc[WF_S_RESERVED] != 0;
-    double rew = 0.0;
-    if (act) {
-        const bool anyB = acc[0] > 0;
-        sc[WF_S_N_BURNING] = acc[0];
-        if (do_tick) {
-            if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
-            if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
-        }
-        const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
-        if (check && !acc[3]) {
-            sc[WF_S_LATCHED] = 1;
-            rew = c.contained_bonus;
-            atomicAdd(&s.stats[ST_CONTAINED], 1ull);
-        } else if (!sc[WF_S_ALIVE]) {
-            rew = c.death_penalty;
-        } else if (!anyB) {
-            rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
-        } else {
-            rew = c.default_reward;
-        }
-        sc[WF_S_T] += 1;
-        atomicAdd(&s.stats[ST_STEPS], 1ull);
-        if (!sc[WF_S_RUNNING]) {
-            atomicAdd(&s.stats[ST_EPISODES], 1ull);
-            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
-        }
+// World.get_state :399-402 for every env: [agent_pos, type == fire, fire_mobility != inf].
+// One thread per word: 2 plane words in, 96 bytes (32 cells x 3 channels) out.
+__global__ void __launch_bounds__(kTileThreads) obs_kernel(DevState s, void* obs, int obs_dtype) {
+    __shared__ uint32_t spread3[256];
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
+        spread3[v] = o;
     }
-    const bool is_done = !sc[WF_S_RUNNING];
-    if (reward) reward[env] = rew;
-    if (done) done[env] = is_done ? 1 : 0;
-    t.do_reset[env] = (c.auto_reset && act && is_done) ? 1 : 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// World.reset (environment.py:186-212) for flagged envs: planes in parallel, then the sequential part.
-template <int FB>
-__global__ void __launch_bounds__(kTileThreads) reset_planes_kernel(DevState s, StepCfg c, TileState t) {
+    __syncthreads();
     const int env = blockIdx.y;
-    if (!t.do_reset[env]) return;
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwords) return;
     const int x = i / HW, w = i - x * HW;
-    const uint32_t valid = valid_word(H, w);
+    const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
     const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
-    P[P_G * pstride] = valid;
-    P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
-    P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
-#pragma unroll
-    for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
-    P[(size_t)t.P_S0 * pstride] = 0u;
-    P[(size_t)t.P_S1 * pstride] = 0u;
-    P[(size_t)t.P_R * pstride] = valid;
-    uint32_t* hrow = s.hits + ((size_t)env * W + x) * H + 32 * w;
+    const uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+    const uint32_t F = P[P_F * pstride];
+    const uint32_t freerow = ~P[P_I * pstride] & valid_word(H, w);
+    const uint32_t arow = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && (sc[WF_S_AY] >> 5) == w) ? 1u << (sc[WF_S_AY] & 31) : 0u;
     const int ncell = min(32, H - 32 * w);
-    for (int b = 0; b < ncell; ++b) hrow[b] = 0u;
-}
-
-__global__ void reset_agent_kernel(DevState s, StepCfg c, TileState t, const wf_init* init) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= s.N || !t.do_reset[env]) return;
-    const int W = s.W, H = s.H;
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;
-    ResetDraws dr((uint32_t)(c.env_id_base + env), episode, c.key0, c.key1);
-    int wid = 0;
-    if (c.wind_random) {
-        const int si = dr.next() % 3u, wx = dr.next() % 3u, wy = dr.next() % 3u;
-        wid = si * 9 + wx * 3 + wy;
+    const size_t e0 = (((size_t)env * W + x) * H + 32 * w) * 3;  // first output element of this word
+    uint32_t r[3];
+    {
+        uint32_t p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            p[k] = spread3[(arow >> (8 * k)) & 255u] | (spread3[(F >> (8 * k)) & 255u] << 1) |
+                   (spread3[(freerow >> (8 * k)) & 255u] << 2);
+        r[0] = p[0] | (p[1] << 24);
+        r[1] = (p[1] >> 8) | (p[2] << 16);
+        r[2] = (p[2] >> 16) | (p[3] << 8);
     }
-    const int cx = W / 2, cy = H / 2;
-    if (c.make_rivers) {  // reset_map :69-95
-        int river_x = dr.next() % (uint32_t)W;
-        int river_y = 1 + dr.next() % 3u;
-        while (river_y < H - (1 + (int)(dr.next() % 3u))) {
-            const uint32_t bit = 1u << (river_y & 31);
-            plane_word(s, P_G, env, river_x, river_y >> 5) &= ~bit;
-            plane_word(s, P_WT, env, river_x, river_y >> 5) |= bit;
-            plane_word(s, P_I, env, river_x, river_y >> 5) |= bit;
-            const int new_y = river_y + 1;
-            int new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
-            for (;;) {
-                const int lo = 1 + dr.next() % 3u;
-                bool chain = false;
-                if (lo <= new_x) chain = new_x < W - (1 + (int)(dr.next() % 3u));
-                if (chain || (new_x == cx && new_y == cy)) break;
-                new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+    if (obs_dtype == WF_OBS_U8) {
+        uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
+        if (ncell == 32 && (reinterpret_cast<uintptr_t>(o8) & 15u) == 0) {
+            uint4* o = reinterpret_cast<uint4*>(o8);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {  // 16 stream bits -> 16 bytes
+                const uint32_t bits = (r[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                uint4 v;
+                v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+                v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+                v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+                v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+                o[k] = v;
             }
-            river_x = new_x;
-            river_y = new_y;
+        } else {
+            for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
         }
-    }
-    sc[WF_S_FIRE_AT_BORDER] = 0;
-    tile_set_fire(s, t, env, cx, cy, sc);
-    int ax, ay;
-    if (init != nullptr && init[env].ax >= 0) {
-        ax = init[env].ax; ay = init[env].ay;
     } else {
-        const int rad = dr.next() % 3u;
-        const int idx = dr.next() % (uint32_t)kCircleLen[rad];
-        ax = cx + kCircle[rad][idx][0];
-        ay = cy + kCircle[rad][idx][1];
+        float* of = static_cast<float*>(obs) + e0;
+        for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
     }
-    {  // Agent.__init__ digs its start cell (:112-113); the reach plane is re-flooded below anyway
-        const uint32_t bit = 1u << (ay & 31);
-        const int w = ay >> 5;
-        plane_word(s, P_G, env, ax, w) &= ~bit; plane_word(s, P_F, env, ax, w) &= ~bit;
-        plane_word(s, P_BT, env, ax, w) &= ~bit; plane_word(s, P_WT, env, ax, w) &= ~bit;
-        plane_word(s, P_D, env, ax, w) |= bit; plane_word(s, P_I, env, ax, w) |= bit;
-    }
-    sc[WF_S_FIRE_AT_BORDER] = 0;  // :212
-    for (int k = 0; k < c.extra_ignitions; ++k) {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)(c.env_id_base + env), episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, w);
-        tile_set_fire(s, t, env, (int)(w[0] % (uint32_t)W), (int)(w[1] % (uint32_t)H), sc);
-    }
-    sc[WF_S_ALIVE] = 1; sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_DEAD] = 0; sc[WF_S_DIGGING] = 1;
-    sc[WF_S_VISIBLE] = 1; sc[WF_S_RUNNING] = 1; sc[WF_S_LATCHED] = 0;
-    sc[WF_S_EPISODE] = (int32_t)episode; sc[WF_S_T] = 0; sc[WF_S_WIND_ID] = wid;
-    sc[WF_S_WIND_X] = s.wind->wx[wid]; sc[WF_S_WIND_Y] = s.wind->wy[wid];
-    int nb = 0;  // burning cells = distinct ignition cells; counted by the first tile_step, approximate here
-    sc[WF_S_N_BURNING] = nb;
-    t.need_flood[env] = 1;
 }
 
-// number of burning cells after a reset / set_state (exact), one block per env
-__global__ void count_burning_kernel(DevState s, TileState t, int only_reset) {
-    const int env = blockIdx.x;
-    if (only_reset && !t.do_reset[env]) return;
-    __shared__ int total;
-    if (threadIdx.x == 0) total = 0;
+// ---------------------------------------------------------------------------------------------
+// World.reset (environment.py:186-212) of one env by one CTA.
+template <int FB>
+__device__ void reset_block(const DevState& s, const StepCfg& c, const TileState& t, const wf_init* init, int env) {
+    __shared__ int sh_fab, sh_nb;
+    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
+    const size_t pstride = (size_t)s.N * s.RS * s.HW;
+    uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {  // reset_map :59-67
+        const int x = i / HW, w = i - x * HW;
+        const uint32_t valid = valid_word(H, w);
+        uint32_t* P = P0 + i;
+        P[P_G * pstride] = valid;
+        P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
+        P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
+#pragma unroll
+        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
+        P[(size_t)t.P_S0 * pstride] = 0u;
+        P[(size_t)t.P_S1 * pstride] = 0u;
+    }
+    uint32_t* hits = s.hits + (size_t)env * W * H;
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) hits[i] = 0u;
+    if (threadIdx.x == 0) { sh_fab = 0; sh_nb = 0; }
     __syncthreads();
-    const int nwords = s.W * s.HW;
-    const uint32_t* B = &plane_word(s, P_B, env, 0, 0);
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;  // every thread reads the old value ...
+    __syncthreads();                                            // ... before thread 0 overwrites it
+    if (threadIdx.x == 0) {
+        ResetDraws dr((uint32_t)(c.env_id_base + env), episode, c.key0, c.key1);
+        int wid = 0;
+        if (c.wind_random) {  // :188-190
+            const int si = dr.next() % 3u, wx = dr.next() % 3u, wy = dr.next() % 3u;
+            wid = si * 9 + wx * 3 + wy;
+        }
+        const int cx = W / 2, cy = H / 2;
+        if (c.make_rivers) {  // reset_map :69-95
+            int river_x = dr.next() % (uint32_t)W;
+            int river_y = 1 + dr.next() % 3u;
+            while (river_y < H - (1 + (int)(dr.next() % 3u))) {
+                const uint32_t bit = 1u << (river_y & 31);
+                plane_word(s, P_G, env, river_x, river_y >> 5) &= ~bit;
+                plane_word(s, P_WT, env, river_x, river_y >> 5) |= bit;
+                plane_word(s, P_I, env, river_x, river_y >> 5) |= bit;
+                const int new_y = river_y + 1;
+                int new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+                for (;;) {
+                    const int lo = 1 + dr.next() % 3u;
+                    bool chain = false;
+                    if (lo <= new_x) chain = new_x < W - (1 + (int)(dr.next() % 3u));
+                    if (chain || (new_x == cx && new_y == cy)) break;
+                    new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
+                }
+                river_x = new_x;
+                river_y = new_y;
+            }
+        }
+        tile_set_fire(s, t, env, cx, cy, sc);  // :203
+        int ax, ay;
+        if (init != nullptr && init[env].ax >= 0) {
+            ax = init[env].ax; ay = init[env].ay;
+        } else {
+            const int rad = dr.next() % 3u;
+            const int idx = dr.next() % (uint32_t)kCircleLen[rad];
+            ax = cx + kCircle[rad][idx][0];
+            ay = cy + kCircle[rad][idx][1];
+        }
+        {  // Agent.__init__ digs its start cell (:112-113); R is re-flooded below
+            const uint32_t bit = 1u << (ay & 31);
+            const int w = ay >> 5;
+            plane_word(s, P_G, env, ax, w) &= ~bit; plane_word(s, P_F, env, ax, w) &= ~bit;
+            plane_word(s, P_BT, env, ax, w) &= ~bit; plane_word(s, P_WT, env, ax, w) &= ~bit;
+            plane_word(s, P_D, env, ax, w) |= bit; plane_word(s, P_I, env, ax, w) |= bit;
+        }
+        sc[WF_S_ALIVE] = 1; sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_DEAD] = 0; sc[WF_S_DIGGING] = 1;
+        sc[WF_S_VISIBLE] = 1; sc[WF_S_RUNNING] = 1; sc[WF_S_LATCHED] = 0;
+        sc[WF_S_EPISODE] = (int32_t)episode; sc[WF_S_T] = 0; sc[WF_S_WIND_ID] = wid;
+        sc[WF_S_WIND_X] = s.wind->wx[wid]; sc[WF_S_WIND_Y] = s.wind->wy[wid];
+        sc[WF_S_FIRE_AT_BORDER] = 0;  // :212
+    }
+    __syncthreads();
+    // extra ignitions: World.set_fire_to after reset() (IGNITE stream).  set_fire_to is idempotent and
+    // commutes with itself, so the k-th ignitions run in parallel with atomics.
+    const int scur = t.cur ? t.P_S1 : t.P_S0;
+    for (int k = threadIdx.x; k < c.extra_ignitions; k += blockDim.x) {
+        uint32_t wd[4];
+        philox4x32_10((uint32_t)(c.env_id_base + env), episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, wd);
+        const int x = (int)(wd[0] % (uint32_t)W), y = (int)(wd[1] % (uint32_t)H), w = y >> 5;
+        const uint32_t bit = 1u << (y & 31);
+        atomicAnd(&plane_word(s, P_G, env, x, w), ~bit);
+        atomicAnd(&plane_word(s, P_BT, env, x, w), ~bit);
+        atomicAnd(&plane_word(s, P_D, env, x, w), ~bit);
+        atomicAnd(&plane_word(s, P_WT, env, x, w), ~bit);
+        atomicOr(&plane_word(s, P_F, env, x, w), bit);
+        atomicOr(&plane_word(s, P_B, env, x, w), bit);
+        if (c.fuel >= 2) atomicOr(&plane_word(s, scur, env, x, w), bit);
+        if (x == 0 || x == W - 1 || y == 0 || y == H - 1) sh_fab = 1;
+    }
+    __syncthreads();
+    flood_block(s, t, env);
     int n = 0;
+    const uint32_t* B = &plane_word(s, P_B, env, 0, 0);
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) n += __popc(B[i]);
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&total, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sh_nb, n);
     __syncthreads();
-    if (threadIdx.x == 0) s.scal[(size_t)env * WF_NSCALARS + WF_S_N_BURNING] = total;
+    if (threadIdx.x == 0) {
+        sc[WF_S_N_BURNING] = sh_nb;
+        if (sh_fab) sc[WF_S_FIRE_AT_BORDER] = 1;
+    }
 }
 
-__global__ void set_reset_mask_kernel(TileState t, const uint8_t* mask, int n) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env < n) t.do_reset[env] = (mask == nullptr || mask[env]) ? 1 : 0;
+// ForestFire.step part 3 (thread 0): RUNNING flag (forest_fire.py:105-106), World.get_reward
+// (environment.py:342-390); then, for envs that finished (auto_reset) or are masked (wf_reset), World.reset.
+template <int FB>
+__global__ void post_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick,
+                            int reset_mode, const uint8_t* mask, const wf_init* init) {
+    __shared__ int sh_reset;
+    const int env = blockIdx.x;
+    if (threadIdx.x == 0) {
+        if (reset_mode) {
+            sh_reset = (mask == nullptr || mask[env]) ? 1 : 0;
+        } else {
+            int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+            const int32_t* acc = t.acc + 4 * env;
+            const bool act = sc[WF_S_RESERVED] != 0;
+            double rew = 0.0;
+            if (act) {
+                const bool anyB = acc[0] > 0;
+                sc[WF_S_N_BURNING] = acc[0];
+                if (do_tick) {
+                    if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
+                    if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
+                }
+                const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
+                if (check && !acc[3]) {
+                    sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
+                    rew = c.contained_bonus;
+                    atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+                } else if (!sc[WF_S_ALIVE]) {
+                    rew = c.death_penalty;
+                } else if (!anyB) {
+                    rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
+                } else {
+                    rew = c.default_reward;
+                }
+                sc[WF_S_T] += 1;
+                atomicAdd(&s.stats[ST_STEPS], 1ull);
+                if (!sc[WF_S_RUNNING]) {
+                    atomicAdd(&s.stats[ST_EPISODES], 1ull);
+                    if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
+                }
+            }
+            const bool is_done = !sc[WF_S_RUNNING];
+            if (reward) reward[env] = rew;
+            if (done) done[env] = is_done ? 1 : 0;
+            sh_reset = (c.auto_reset && act && is_done) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (sh_reset) reset_block<FB>(s, c, t, init, env);
 }
 
-// S := B & (fuel >= 2), need_flood := 1 for every env (after wf_set_state / wf_set_fire_to)
-__global__ void rebuild_sources_kernel(DevState s, TileState t) {
-    const int env = blockIdx.y;
+// S := B & (fuel >= 2), R re-flooded, n_burning recounted (after wf_set_state / wf_set_fire_to)
+__global__ void rebuild_kernel(DevState s, TileState t) {
+    __shared__ int sh_nb;
+    const int env = blockIdx.x;
     const int nwords = s.W * s.HW;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) t.need_flood[env] = 1;
-    if (i >= nwords) return;
     const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
-    uint32_t ge2 = 0u;
-    for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * pstride];
-    P[(size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride] = P[P_B * pstride] & ge2;
+    uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
+    if (threadIdx.x == 0) sh_nb = 0;
+    __syncthreads();
+    int n = 0;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+        uint32_t* P = P0 + i;
+        uint32_t ge2 = 0u;
+        for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * pstride];
+        const uint32_t B = P[P_B * pstride];
+        P[(size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride] = B & ge2;
+        n += __popc(B);
+    }
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sh_nb, n);
+    __syncthreads();
+    if (threadIdx.x == 0) s.scal[(size_t)env * WF_NSCALARS + WF_S_N_BURNING] = sh_nb;
+    flood_block(s, t, env);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,64 +589,39 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     cudaError_t e;
     if ((e = cudaMalloc(&t->acc, (size_t)s.N * 4 * sizeof(int32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&t->need_flood, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->do_reset, (size_t)s.N)) != cudaSuccess) return e;
     cudaMemset(t->acc, 0, (size_t)s.N * 4 * sizeof(int32_t));
     cudaMemset(t->need_flood, 0, (size_t)s.N * sizeof(int32_t));
-    cudaMemset(t->do_reset, 0, (size_t)s.N);
     *out = t;
     return cudaSuccess;
 }
 
 void tile_destroy(TileState* t) {
     if (!t) return;
-    cudaFree(t->acc); cudaFree(t->need_flood); cudaFree(t->do_reset);
+    cudaFree(t->acc); cudaFree(t->need_flood);
     delete t;
 }
 
-template <int FB>
-static cudaError_t run_reset(TileState* t, const DevState& s, const StepCfg& c, const wf_init* init, void* obs,
-                             int obs_dtype, cudaStream_t st, int64_t* launches) {
-    const int nwords = s.W * s.HW;
-    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
-    reset_planes_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t);
-    reset_agent_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, init);
-    flood_kernel<<<s.N, 1024, 0, st>>>(s, *t);
-    count_burning_kernel<<<s.N, 256, 0, st>>>(s, *t, 1);
-    *launches += 4;
-    if (obs) {
-        tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, obs, obs_dtype, 0, 1);
-        *launches += 1;
-    }
-    return cudaGetLastError();
-}
+static int cta_threads(const DevState& s) { return s.W * s.HW >= 8192 ? 1024 : 256; }
 
 template <int FB>
 static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st,
                               int64_t* launches) {
     const int nwords = s.W * s.HW;
     const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
+    const int ct = cta_threads(s);
     if (io.reset_mode) {
-        set_reset_mask_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(*t, io.mask, s.N);
+        post_kernel<FB><<<s.N, ct, 0, st>>>(s, c, *t, nullptr, nullptr, 0, 1, io.mask, io.init);
         *launches += 1;
-        // obs of envs that are NOT reset must still be delivered: write all, then the reset ones again
-        cudaError_t e = run_reset<FB>(t, s, c, io.init, nullptr, io.obs_dtype, st, launches);
-        if (e != cudaSuccess) return e;
-        if (io.obs) {
-            set_reset_mask_kernel<<<(s.N + 255) / 256, 256, 0, st>>>(*t, nullptr, s.N);
-            tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.obs, io.obs_dtype, 0, 1);
-            *launches += 2;
-        }
-        return cudaGetLastError();
+    } else {
+        pre_kernel<<<s.N, ct, 0, st>>>(s, c, *t, io.actions, io.do_tick);
+        tile_tick_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.do_tick);
+        if (io.do_tick) t->cur ^= 1;
+        post_kernel<FB><<<s.N, ct, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick, 0, nullptr, nullptr);
+        *launches += 3;
     }
-    agent_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick);
-    flood_kernel<<<s.N, 1024, 0, st>>>(s, *t);
-    tile_step_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.obs, io.obs_dtype, io.do_tick, 0);
-    if (io.do_tick) t->cur ^= 1;
-    finish_kernel<<<(s.N + 127) / 128, 128, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick);
-    *launches += 4;
-    if (c.auto_reset) {
-        cudaError_t e = run_reset<FB>(t, s, c, nullptr, io.obs, io.obs_dtype, st, launches);
-        if (e != cudaSuccess) return e;
+    if (io.obs) {
+        obs_kernel<<<grid, kTileThreads, 0, st>>>(s, io.obs, io.obs_dtype);
+        *launches += 1;
     }
     return cudaGetLastError();
 }
@@ -631,12 +634,8 @@ cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c
 
 cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg&, cudaStream_t stream,
                                  int64_t* launches) {
-    const int nwords = s.W * s.HW;
-    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
-    rebuild_sources_kernel<<<grid, kTileThreads, 0, stream>>>(s, *t);
-    flood_kernel<<<s.N, 1024, 0, stream>>>(s, *t);
-    count_burning_kernel<<<s.N, 256, 0, stream>>>(s, *t, 0);
-    *launches += 3;
+    rebuild_kernel<<<s.N, cta_threads(s), 0, stream>>>(s, *t);
+    *launches += 1;
     return cudaGetLastError();
 }
 
