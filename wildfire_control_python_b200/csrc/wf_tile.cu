@@ -10,11 +10,12 @@
 // containment search (environment.py:342-377) is a persistent "reach" plane R (cells with a finite
 // 4-connected path to a finite border point) that is re-flooded only when a dig may disconnect it.
 //
-// One step = pre_kernel  (1 CTA/env: thread 0 moves/digs/reaps + local articulation test; the CTA
-//                         re-floods R only when that test says a dig may have disconnected something)
+// One step = agent_kernel (1 thread/env: move/dig/reap + local articulation test; envs whose reach
+//                          plane may have been disconnected by the dig are appended to a work list)
+//          -> flood_list_kernel (persistent CTAs drain the list: re-flood R; usually the list is empty)
 //          -> tile_tick_kernel (the stencil: fuel, heat, ignition, per-env reductions)
-//          -> post_kernel (1 CTA/env: thread 0 computes reward/done/latch; if the env finished and
-//                          auto_reset is on, the CTA re-initialises it: World.reset)
+//          -> finish_kernel (1 thread/env: reward/done/latch; finished envs go to the reset list)
+//          -> reset_list_kernel (persistent CTAs drain the list: World.reset; usually empty)
 //          -> obs_kernel  (World.get_state of every env: 2 bits/cell in, 3 bytes/cell out)
 #include "wf_families.cuh"
 
@@ -24,7 +25,10 @@ constexpr int kTileThreads = 256;
 
 struct TileState {
     int32_t* acc;         // [N][4]: burning cells, grass cells, ignition-on-edge flag, burning-touches-reach flag
-    int32_t* need_flood;  // [N]
+    int32_t* need_flood;  // [N] flag: R of this env must be re-flooded
+    int32_t* flood_list;  // [N] env ids appended by agent_kernel, + counter
+    int32_t* reset_list;  // [N] env ids appended by finish_kernel / mask_to_list_kernel, + counter
+    int32_t* counters;    // [0] = flood_list length, [1] = reset_list length
     int32_t cur;          // which of the two S planes holds the sources of the NEXT tick
     int32_t P_S0, P_S1, P_R;
     int32_t flood_smem_ok;
@@ -63,7 +67,7 @@ __device__ __forceinline__ bool get_bit(const DevState& s, int p, int env, int x
 }
 
 // Agent.dig (environment.py:123-133) on planes in HBM + incremental maintenance of the reach plane.
-__device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, int y) {
+__device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, int y, const int32_t* sc) {
     const int w = y >> 5;
     const uint32_t bit = 1u << (y & 31);
     uint32_t& D = plane_word(s, P_D, env, x, w);
@@ -77,6 +81,10 @@ __device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, 
     const bool was_free = !(I & bit);
     I |= bit;
     if (!was_free) return;
+    // get_reward only searches for a path while `not fire_at_border and len(border_points)`
+    // (environment.py:345): once either latch is set R is never read again in this episode
+    // (World.reset re-floods it), so it is not maintained.
+    if (sc[WF_S_FIRE_AT_BORDER] || sc[WF_S_LATCHED]) return;
     uint32_t& R = plane_word(s, t.P_R, env, x, w);
     if (!(R & bit)) return;  // the cell had no path to the border: nobody reached the border through it
     R &= ~bit;
@@ -102,7 +110,10 @@ __device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, 
         if (!(f[pk] && f[pd])) groups++;
     }
     if (n4 == 4 && groups == 0) groups = 1;  // full ring
-    if (on_seed ? n4 > 0 : groups > 1) t.need_flood[env] = 1;
+    if ((on_seed ? n4 > 0 : groups > 1) && !t.need_flood[env]) {
+        t.need_flood[env] = 1;
+        t.flood_list[atomicAdd(&t.counters[0], 1)] = env;
+    }
 }
 
 // World.set_fire_to (environment.py:233-246) on planes in HBM (keeps the source mask consistent).
@@ -157,165 +168,222 @@ __device__ void flood_block(const DevState& s, const TileState& t, int env) {
 }
 
 // ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
-// steps, Agent.is_dead (:116-120).  One CTA per env; only thread 0 works unless R must be re-flooded.
-__global__ void pre_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
-    const int env = blockIdx.x;
-    if (threadIdx.x == 0) {
-        int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-        int32_t* acc = t.acc + 4 * env;
-        acc[0] = acc[1] = acc[2] = acc[3] = 0;
-        sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
-        if (sc[WF_S_RUNNING]) {
-            int action;
-            if (actions != nullptr) {
-                action = actions[env];
-            } else {
-                uint32_t w[4];
-                philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T],
-                              kStreamAction, c.key0, c.key1, w);
-                action = (int)(w[0] % (uint32_t)c.n_actions);
-            }
-            int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
-            if (sc[WF_S_ALIVE]) {
-                if (action >= 0 && action < 4) {
-                    sc[WF_S_VISIBLE] = 0;  // Q1
-                    const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
-                    const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
-                    if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
-                        ax = nx; ay = ny;
-                        sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
-                        const bool onfire = get_bit(s, P_F, env, nx, ny);
-                        if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny);
-                        if (onfire) sc[WF_S_DEAD] = 1;
-                    }
-                }
-                if (c.allow_dig_toggle && action == 4) {
-                    sc[WF_S_DIGGING] ^= 1;
-                    if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay);
-                }
-                if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
-                    sc[WF_S_VISIBLE] = 0;
-                    sc[WF_S_ALIVE] = 0;
-                    atomicAdd(&s.stats[ST_DEATHS], 1ull);
-                }
-            }
+// steps, Agent.is_dead (:116-120).  One thread per env.
+__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env == 0) t.counters[1] = 0;  // the reset list was drained by the previous step
+    if (env >= s.N) return;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    int32_t* acc = t.acc + 4 * env;
+    acc[0] = acc[1] = acc[2] = acc[3] = 0;
+    sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
+    if (!sc[WF_S_RUNNING]) return;
+    int action;
+    if (actions != nullptr) {
+        action = actions[env];
+    } else {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T], kStreamAction,
+                      c.key0, c.key1, w);
+        action = (int)(w[0] % (uint32_t)c.n_actions);
+    }
+    int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
+    if (!sc[WF_S_ALIVE]) return;
+    if (action >= 0 && action < 4) {
+        sc[WF_S_VISIBLE] = 0;  // Q1
+        const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
+        const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
+        if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
+            ax = nx; ay = ny;
+            sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
+            const bool onfire = get_bit(s, P_F, env, nx, ny);
+            if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny, sc);
+            if (onfire) sc[WF_S_DEAD] = 1;
         }
     }
-    __syncthreads();
-    if (t.need_flood[env]) flood_block(s, t, env);
+    if (c.allow_dig_toggle && action == 4) {
+        sc[WF_S_DIGGING] ^= 1;
+        if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay, sc);
+    }
+    if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
+        sc[WF_S_VISIBLE] = 0;
+        sc[WF_S_ALIVE] = 0;
+        atomicAdd(&s.stats[ST_DEATHS], 1ull);
+    }
+}
+
+// Persistent CTAs drain the flood list (empty on most steps).
+__global__ void __launch_bounds__(1024) flood_list_kernel(DevState s, TileState t) {
+    const int n = t.counters[0];
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        flood_block(s, t, t.flood_list[k]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// The stencil.  One thread per word (32 cells).
+// The stencil.
+// Active word (it burns or is heated): reduce_fuel :297-307, burn-out, apply_heat_from_to :278-294,
+// set_fire_to :233-246.  Returns the word's heat sources for the next tick.
 template <int FB>
-__global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, StepCfg c, TileState t, int do_tick) {
+__device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride, uint32_t& G, uint32_t& B, uint32_t h0,
+                                                     uint32_t h1, uint32_t h2, uint32_t h3, const DevState& s,
+                                                     const StepCfg& c, uint32_t* hrow, int wid, int kmin,
+                                                     uint32_t edge, int& my_edge) {
+    uint32_t FU[FB];
+#pragma unroll
+    for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
+    uint32_t borrow = B;
+#pragma unroll
+    for (int q = 0; q < FB; ++q) {
+        const uint32_t f = FU[q];
+        FU[q] = f ^ borrow;
+        borrow &= ~f;
+    }
+    uint32_t nz = 0u;
+#pragma unroll
+    for (int q = 0; q < FB; ++q) {
+        FU[q] &= ~borrow;
+        nz |= FU[q];
+    }
+    const uint32_t out = B & ~nz;
+    if (B) {
+#pragma unroll
+        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
+    }
+    uint32_t F = 0u;
+    if (out) {  // type := burnt whatever it was (a dug-while-burning cell is dirt, Q7)
+        F = P[P_F * pstride];
+        P[P_BT * pstride] |= out;
+        P[P_D * pstride] &= ~out;
+        P[P_WT * pstride] &= ~out;
+        F &= ~out; G &= ~out; B &= ~out;
+    }
+    // Heated cells: hit counters are read-modify-written; up to 4 cells per round so that their loads
+    // are in flight together (a front usually heats 1-4 cells of a word).
+    uint32_t ign = 0u, m = h0 | h1 | h2 | h3;
+    while (m) {
+        int y[4];
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            y[j] = m ? __ffs(m) - 1 : -1;
+            m &= m - 1u;  // (0 & anything) stays 0
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = y[j] >= 0 ? hrow[y[j]] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (y[j] < 0) continue;
+            const int yy = y[j];
+            const uint32_t nv = v[j] + (((h0 >> yy) & 1u) | (((h1 >> yy) & 1u) << 8) | (((h2 >> yy) & 1u) << 16) |
+                                        (((h3 >> yy) & 1u) << 24));
+            hrow[yy] = nv;
+            const bool ig = kmin >= 0 ? (int)__dp4a(nv, 0x01010101u, 0u) >= kmin : ignites(nv, s.wind, wid, c.threshold);
+            if (ig) ign |= 1u << yy;
+        }
+    }
+    if (ign | out) {
+        if (!out) F = P[P_F * pstride];
+        G &= ~ign; F |= ign; B |= ign;
+        P[P_G * pstride] = G; P[P_F * pstride] = F; P[P_B * pstride] = B;
+    }
+    if (ign & edge) my_edge = 1;
+    uint32_t ge2 = 0u;  // sources of the next tick: burning with fuel >= 2 (new fires hold the reset fuel)
+#pragma unroll
+    for (int q = 1; q < FB; ++q) ge2 |= FU[q];
+    return B & ge2;
+}
+
+// does a burning cell of this word sit in, or next to, the border-connected region R?
+__device__ __forceinline__ bool touches_reach(const uint32_t* R, uint32_t B, int x, int w, int W, int HW) {
+    uint32_t near = R[0];
+    near |= (near << 1) | (near >> 1);
+    if (x > 0) near |= R[-HW];
+    if (x < W - 1) near |= R[HW];
+    if (w > 0) near |= R[-1] >> 31;
+    if (w < HW - 1) near |= R[1] << 31;
+    return (B & near) != 0u;
+}
+
+// VW = words per thread along y: 4 (128-bit loads; needs HW % 4 == 0) or 1.
+template <int FB, int VW>
+__global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, StepCfg c, TileState t, int do_tick,
+                                                                 int hw_shift) {
     __shared__ int red[4];
     const int env = blockIdx.y;
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
     __syncthreads();
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VW;  // first word of this thread
     const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
     const bool act = sc[WF_S_RESERVED] != 0;
+    const bool want_touch = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED];
     int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
     if (i < nwords) {
-        const int x = i / HW, w = i - x * HW;
+        const int x = hw_shift >= 0 ? (i >> hw_shift) : (i / HW);
+        const int w0 = i - x * HW;
         const size_t pstride = (size_t)s.N * s.RS * s.HW;
         uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
-        uint32_t G = P[P_G * pstride], B = P[P_B * pstride];
+        uint32_t G[VW], B[VW];
+        if (VW == 4) {
+            const uint4 g4 = *reinterpret_cast<const uint4*>(P + P_G * pstride);
+            const uint4 b4 = *reinterpret_cast<const uint4*>(P + P_B * pstride);
+            G[0] = g4.x; G[VW > 1 ? 1 : 0] = g4.y; G[VW > 2 ? 2 : 0] = g4.z; G[VW > 3 ? 3 : 0] = g4.w;
+            B[0] = b4.x; B[VW > 1 ? 1 : 0] = b4.y; B[VW > 2 ? 2 : 0] = b4.z; B[VW > 3 ? 3 : 0] = b4.w;
+        } else {
+            G[0] = P[P_G * pstride];
+            B[0] = P[P_B * pstride];
+        }
         if (act && do_tick) {
             const uint32_t* Sc = P + (size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride;
             uint32_t* Sn = P + (size_t)(t.cur ? t.P_S0 : t.P_S1) * pstride;
-            const uint32_t S = Sc[0];
-            const uint32_t Sup = x > 0 ? Sc[-HW] : 0u, Sdn = x < W - 1 ? Sc[HW] : 0u;
-            const uint32_t Sprev = w > 0 ? Sc[-1] : 0u, Snext = w < HW - 1 ? Sc[1] : 0u;
-            const uint32_t h0 = G & ((S >> 1) | (Snext << 31));  // d = N (0,-1): source at y+1
-            const uint32_t h1 = G & ((S << 1) | (Sprev >> 31));  // d = S (0,+1): source at y-1
-            const uint32_t h2 = G & Sup;                         // d = E (+1,0): source at x-1
-            const uint32_t h3 = G & Sdn;                         // d = W (-1,0): source at x+1
-            uint32_t m = h0 | h1 | h2 | h3;
-            uint32_t Snew = 0u;
-            if (B | m) {  // active word: it burns or it is heated
-                uint32_t FU[FB];
-#pragma unroll
-                for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
-                // reduce_fuel :297-307
-                uint32_t borrow = B;
-#pragma unroll
-                for (int q = 0; q < FB; ++q) {
-                    const uint32_t f = FU[q];
-                    FU[q] = f ^ borrow;
-                    borrow &= ~f;
-                }
-                uint32_t nz = 0u;
-#pragma unroll
-                for (int q = 0; q < FB; ++q) {
-                    FU[q] &= ~borrow;
-                    nz |= FU[q];
-                }
-                const uint32_t out = B & ~nz;
-                if (B) {
-#pragma unroll
-                    for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
-                }
-                uint32_t F = 0u;
-                if (out) {  // type := burnt whatever it was (a dug-while-burning cell is dirt, Q7)
-                    F = P[P_F * pstride];
-                    P[P_BT * pstride] |= out;
-                    P[P_D * pstride] &= ~out;
-                    P[P_WT * pstride] &= ~out;
-                    F &= ~out; G &= ~out; B &= ~out;
-                }
-                // apply_heat_from_to :278-294 on the heated grass cells
-                uint32_t ign = 0u;
-                if (m) {
-                    const int wid = sc[WF_S_WIND_ID];
-                    const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
-                    uint32_t* hrow = s.hits + ((size_t)env * W + x) * H + 32 * w;
-                    while (m) {
-                        const int y = __ffs(m) - 1;
-                        m &= m - 1u;
-                        const uint32_t v = hrow[y] + (((h0 >> y) & 1u) | (((h1 >> y) & 1u) << 8) |
-                                                      (((h2 >> y) & 1u) << 16) | (((h3 >> y) & 1u) << 24));
-                        hrow[y] = v;
-                        const bool ig = kmin >= 0 ? (int)__dp4a(v, 0x01010101u, 0u) >= kmin
-                                                  : ignites(v, s.wind, wid, c.threshold);
-                        if (ig) ign |= 1u << y;
-                    }
-                }
-                if (ign | out) {
-                    if (!out) F = P[P_F * pstride];
-                    G &= ~ign; F |= ign; B |= ign;
-                    P[P_G * pstride] = G; P[P_F * pstride] = F; P[P_B * pstride] = B;
-                }
-                if (ign & edge_word(W, H, x, w)) my_edge = 1;
-                // sources of the next tick: burning with fuel >= 2 (cells ignited now hold the reset fuel)
-                uint32_t ge2 = 0u;
-#pragma unroll
-                for (int q = 1; q < FB; ++q) ge2 |= FU[q];
-                Snew = B & ge2;
+            uint32_t S[VW + 2], Sup[VW], Sdn[VW], Snew[VW];
+            if (VW == 4) {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                const uint4 s4 = *reinterpret_cast<const uint4*>(Sc);
+                const uint4 u4 = x > 0 ? *reinterpret_cast<const uint4*>(Sc - HW) : z;
+                const uint4 d4 = x < W - 1 ? *reinterpret_cast<const uint4*>(Sc + HW) : z;
+                S[1] = s4.x; S[VW > 1 ? 2 : 1] = s4.y; S[VW > 2 ? 3 : 1] = s4.z; S[VW > 3 ? 4 : 1] = s4.w;
+                Sup[0] = u4.x; Sup[VW > 1 ? 1 : 0] = u4.y; Sup[VW > 2 ? 2 : 0] = u4.z; Sup[VW > 3 ? 3 : 0] = u4.w;
+                Sdn[0] = d4.x; Sdn[VW > 1 ? 1 : 0] = d4.y; Sdn[VW > 2 ? 2 : 0] = d4.z; Sdn[VW > 3 ? 3 : 0] = d4.w;
+            } else {
+                S[1] = Sc[0];
+                Sup[0] = x > 0 ? Sc[-HW] : 0u;
+                Sdn[0] = x < W - 1 ? Sc[HW] : 0u;
             }
-            Sn[0] = Snew;
+            S[0] = w0 > 0 ? Sc[-1] : 0u;
+            S[VW + 1] = w0 + VW < HW ? Sc[VW] : 0u;
+            const int wid = sc[WF_S_WIND_ID];
+            const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
+#pragma unroll
+            for (int k = 0; k < VW; ++k) {
+                const uint32_t h0 = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
+                const uint32_t h1 = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
+                const uint32_t h2 = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
+                const uint32_t h3 = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
+                uint32_t sn = 0u;
+                if (B[k] | h0 | h1 | h2 | h3) {
+                    sn = tick_active_word<FB>(P + k, pstride, G[k], B[k], h0, h1, h2, h3, s, c,
+                                              s.hits + ((size_t)env * W + x) * H + 32 * (w0 + k), wid, kmin,
+                                              edge_word(W, H, x, w0 + k), my_edge);
+                }
+                Snew[k] = sn;
+            }
+            if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(Snew[0], Snew[VW > 1 ? 1 : 0], Snew[VW > 2 ? 2 : 0], Snew[VW > 3 ? 3 : 0]);
+            else Sn[0] = Snew[0];
         }
-        my_nb = __popc(B);
-        my_ng = __popc(G);
-        if (B) {  // does a burning cell sit in, or next to, the border-connected region?
-            const uint32_t* R = P + (size_t)t.P_R * pstride;
-            uint32_t near = R[0];
-            near |= (near << 1) | (near >> 1);
-            if (x > 0) near |= R[-HW];
-            if (x < W - 1) near |= R[HW];
-            if (w > 0) near |= R[-1] >> 31;
-            if (w < HW - 1) near |= R[1] << 31;
-            if (B & near) my_touch = 1;
+#pragma unroll
+        for (int k = 0; k < VW; ++k) {
+            my_nb += __popc(B[k]);
+            my_ng += __popc(G[k]);
+            if (B[k] && want_touch && touches_reach(P + k + (size_t)t.P_R * pstride, B[k], x, w0 + k, W, HW)) my_touch = 1;
         }
     }
-    // ---- per-env reductions: warp shuffle -> shared -> one atomic per block and quantity
+    // ---- per-env reductions: warp redux -> shared -> one atomic per block and quantity
     const unsigned FULL = 0xffffffffu;
-    for (int o = 16; o > 0; o >>= 1) {
-        my_nb += __shfl_xor_sync(FULL, my_nb, o);
-        my_ng += __shfl_xor_sync(FULL, my_ng, o);
-    }
+    my_nb = __reduce_add_sync(FULL, my_nb);
+    my_ng = __reduce_add_sync(FULL, my_ng);
     my_edge = __any_sync(FULL, my_edge);
     my_touch = __any_sync(FULL, my_touch);
     if ((threadIdx.x & 31) == 0) {
@@ -347,11 +415,11 @@ __global__ void __launch_bounds__(kTileThreads) obs_kernel(DevState s, void* obs
     const int env = blockIdx.y;
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    const int x = i / HW, w = i - x * HW;
+    const int ic = min(i, nwords - 1);  // tail threads stay alive for the warp shuffles
+    const int x = ic / HW, w = ic - x * HW;
     const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
     const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    const uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+    const uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + ic;
     const uint32_t F = P[P_F * pstride];
     const uint32_t freerow = ~P[P_I * pstride] & valid_word(H, w);
     const uint32_t arow = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && (sc[WF_S_AY] >> 5) == w) ? 1u << (sc[WF_S_AY] & 31) : 0u;
@@ -368,26 +436,39 @@ __global__ void __launch_bounds__(kTileThreads) obs_kernel(DevState s, void* obs
         r[1] = (p[1] >> 8) | (p[2] << 16);
         r[2] = (p[2] >> 16) | (p[3] << 8);
     }
-    if (obs_dtype == WF_OBS_U8) {
-        uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
-        if (ncell == 32 && (reinterpret_cast<uintptr_t>(o8) & 15u) == 0) {
-            uint4* o = reinterpret_cast<uint4*>(o8);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // Fast path (warp-uniform): the warp's 32 words are 32 full words of ONE row-major run, so their
+    // 32 x 96 output bytes are contiguous.  Chunk c (16 bytes) of that run comes from word c/6: fetch its
+    // stream bits by shuffle so that every store instruction writes 512 contiguous bytes.
+    const int i0 = i - lane;
+    const bool fast = obs_dtype == WF_OBS_U8 && (H & 31) == 0 && i0 + 31 < nwords;
+    if (fast) {
+        uint8_t* base = static_cast<uint8_t*>(obs) + (((size_t)env * W) * H + (size_t)32 * i0) * 3;
+        uint4* o = reinterpret_cast<uint4*>(base);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {  // 16 stream bits -> 16 bytes
-                const uint32_t bits = (r[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                uint4 v;
-                v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-                v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-                v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-                v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-                o[k] = v;
-            }
-        } else {
-            for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
+        for (int it = 0; it < 6; ++it) {
+            const int cidx = it * 32 + lane;       // chunk index within the warp's 3072 bytes
+            const int src = cidx / 6, k = cidx - 6 * src;
+            const uint32_t a0 = __shfl_sync(FULL, r[0], src), a1 = __shfl_sync(FULL, r[1], src),
+                           a2 = __shfl_sync(FULL, r[2], src);
+            const uint32_t word = (k >> 1) == 0 ? a0 : (k >> 1) == 1 ? a1 : a2;
+            const uint32_t bits = (word >> ((k & 1) * 16)) & 0xffffu;
+            uint4 v;
+            v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+            v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+            o[cidx] = v;
         }
-    } else {
-        float* of = static_cast<float*>(obs) + e0;
-        for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+    } else if (i < nwords) {
+        if (obs_dtype == WF_OBS_U8) {
+            uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
+            for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
+        } else {
+            float* of = static_cast<float*>(obs) + e0;
+            for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+        }
     }
 }
 
@@ -411,8 +492,13 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
         P[(size_t)t.P_S0 * pstride] = 0u;
         P[(size_t)t.P_S1 * pstride] = 0u;
     }
-    uint32_t* hits = s.hits + (size_t)env * W * H;
-    for (int i = threadIdx.x; i < W * H; i += blockDim.x) hits[i] = 0u;
+    uint32_t* hits = s.hits + (size_t)env * W * H;  // temp layer := 0
+    if (((size_t)env * W * H) % 4 == 0 && (W * H) % 4 == 0) {
+        uint4* h4 = reinterpret_cast<uint4*>(hits);
+        for (int i = threadIdx.x; i < (W * H) / 4; i += blockDim.x) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = threadIdx.x; i < W * H; i += blockDim.x) hits[i] = 0u;
+    }
     if (threadIdx.x == 0) { sh_fab = 0; sh_nb = 0; }
     __syncthreads();
     int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
@@ -502,55 +588,63 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
     }
 }
 
-// ForestFire.step part 3 (thread 0): RUNNING flag (forest_fire.py:105-106), World.get_reward
-// (environment.py:342-390); then, for envs that finished (auto_reset) or are masked (wf_reset), World.reset.
-template <int FB>
-__global__ void post_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick,
-                            int reset_mode, const uint8_t* mask, const wf_init* init) {
-    __shared__ int sh_reset;
-    const int env = blockIdx.x;
-    if (threadIdx.x == 0) {
-        if (reset_mode) {
-            sh_reset = (mask == nullptr || mask[env]) ? 1 : 0;
+// ForestFire.step part 3: RUNNING flag (forest_fire.py:105-106), World.get_reward
+// (environment.py:342-390).  One thread per env; finished envs are appended to the reset list.
+__global__ void finish_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env == 0) t.counters[0] = 0;  // the flood list was drained before the tick
+    if (env >= s.N) return;
+    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+    const int32_t* acc = t.acc + 4 * env;
+    const bool act = sc[WF_S_RESERVED] != 0;
+    double rew = 0.0;
+    if (act) {
+        const bool anyB = acc[0] > 0;
+        sc[WF_S_N_BURNING] = acc[0];
+        if (do_tick) {
+            if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
+            if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
+        }
+        const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
+        if (check && !acc[3]) {
+            sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
+            rew = c.contained_bonus;
+            atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+        } else if (!sc[WF_S_ALIVE]) {
+            rew = c.death_penalty;
+        } else if (!anyB) {
+            rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
         } else {
-            int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-            const int32_t* acc = t.acc + 4 * env;
-            const bool act = sc[WF_S_RESERVED] != 0;
-            double rew = 0.0;
-            if (act) {
-                const bool anyB = acc[0] > 0;
-                sc[WF_S_N_BURNING] = acc[0];
-                if (do_tick) {
-                    if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
-                    if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
-                }
-                const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
-                if (check && !acc[3]) {
-                    sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
-                    rew = c.contained_bonus;
-                    atomicAdd(&s.stats[ST_CONTAINED], 1ull);
-                } else if (!sc[WF_S_ALIVE]) {
-                    rew = c.death_penalty;
-                } else if (!anyB) {
-                    rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
-                } else {
-                    rew = c.default_reward;
-                }
-                sc[WF_S_T] += 1;
-                atomicAdd(&s.stats[ST_STEPS], 1ull);
-                if (!sc[WF_S_RUNNING]) {
-                    atomicAdd(&s.stats[ST_EPISODES], 1ull);
-                    if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
-                }
-            }
-            const bool is_done = !sc[WF_S_RUNNING];
-            if (reward) reward[env] = rew;
-            if (done) done[env] = is_done ? 1 : 0;
-            sh_reset = (c.auto_reset && act && is_done) ? 1 : 0;
+            rew = c.default_reward;
+        }
+        sc[WF_S_T] += 1;
+        atomicAdd(&s.stats[ST_STEPS], 1ull);
+        if (!sc[WF_S_RUNNING]) {
+            atomicAdd(&s.stats[ST_EPISODES], 1ull);
+            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
         }
     }
-    __syncthreads();
-    if (sh_reset) reset_block<FB>(s, c, t, init, env);
+    const bool is_done = !sc[WF_S_RUNNING];
+    if (reward) reward[env] = rew;
+    if (done) done[env] = is_done ? 1 : 0;
+    if (c.auto_reset && act && is_done) t.reset_list[atomicAdd(&t.counters[1], 1)] = env;
+}
+
+// wf_reset: the reset list is the mask.
+__global__ void mask_to_list_kernel(TileState t, const uint8_t* mask, int n) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < n && (mask == nullptr || mask[env])) t.reset_list[atomicAdd(&t.counters[1], 1)] = env;
+}
+__global__ void zero_counter_kernel(TileState t, int which) { t.counters[which] = 0; }
+
+// Persistent CTAs drain the reset list: World.reset (environment.py:186-212), one CTA per env at a time.
+template <int FB>
+__global__ void __launch_bounds__(1024) reset_list_kernel(DevState s, StepCfg c, TileState t, const wf_init* init) {
+    const int n = t.counters[1];
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        reset_block<FB>(s, c, t, init, t.reset_list[k]);
+        __syncthreads();
+    }
 }
 
 // S := B & (fuel >= 2), R re-flooded, n_burning recounted (after wf_set_state / wf_set_fire_to)
@@ -589,6 +683,10 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     cudaError_t e;
     if ((e = cudaMalloc(&t->acc, (size_t)s.N * 4 * sizeof(int32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&t->need_flood, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->flood_list, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->reset_list, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t->counters, 2 * sizeof(int32_t))) != cudaSuccess) return e;
+    cudaMemset(t->counters, 0, 2 * sizeof(int32_t));
     cudaMemset(t->acc, 0, (size_t)s.N * 4 * sizeof(int32_t));
     cudaMemset(t->need_flood, 0, (size_t)s.N * sizeof(int32_t));
     *out = t;
@@ -597,27 +695,43 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
 
 void tile_destroy(TileState* t) {
     if (!t) return;
-    cudaFree(t->acc); cudaFree(t->need_flood);
+    cudaFree(t->acc); cudaFree(t->need_flood); cudaFree(t->flood_list); cudaFree(t->reset_list); cudaFree(t->counters);
     delete t;
 }
 
 static int cta_threads(const DevState& s) { return s.W * s.HW >= 8192 ? 1024 : 256; }
+static int list_grid(const DevState& s) { return s.N < 296 ? s.N : 296; }  // 2 persistent CTAs per SM
 
 template <int FB>
 static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st,
                               int64_t* launches) {
     const int nwords = s.W * s.HW;
     const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
-    const int ct = cta_threads(s);
+    const int eb = (s.N + 127) / 128;
     if (io.reset_mode) {
-        post_kernel<FB><<<s.N, ct, 0, st>>>(s, c, *t, nullptr, nullptr, 0, 1, io.mask, io.init);
-        *launches += 1;
-    } else {
-        pre_kernel<<<s.N, ct, 0, st>>>(s, c, *t, io.actions, io.do_tick);
-        tile_tick_kernel<FB><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.do_tick);
-        if (io.do_tick) t->cur ^= 1;
-        post_kernel<FB><<<s.N, ct, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick, 0, nullptr, nullptr);
+        zero_counter_kernel<<<1, 1, 0, st>>>(*t, 1);
+        mask_to_list_kernel<<<eb, 128, 0, st>>>(*t, io.mask, s.N);
+        reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, io.init);
         *launches += 3;
+    } else {
+        agent_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick);
+        flood_list_kernel<<<list_grid(s), 1024, 0, st>>>(s, *t);
+        int hw_shift = -1;
+        for (int k = 0; k < 16; ++k)
+            if ((1 << k) == s.HW) hw_shift = k;
+        if (s.HW % 4 == 0) {
+            const dim3 g4((nwords / 4 + kTileThreads - 1) / kTileThreads, s.N);
+            tile_tick_kernel<FB, 4><<<g4, kTileThreads, 0, st>>>(s, c, *t, io.do_tick, hw_shift);
+        } else {
+            tile_tick_kernel<FB, 1><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.do_tick, hw_shift);
+        }
+        if (io.do_tick) t->cur ^= 1;
+        finish_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick);
+        *launches += 4;
+        if (c.auto_reset) {
+            reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, nullptr);
+            *launches += 1;
+        }
     }
     if (io.obs) {
         obs_kernel<<<grid, kTileThreads, 0, st>>>(s, io.obs, io.obs_dtype);
