@@ -187,16 +187,21 @@ class BatchedForestFire:
         """
         if self._host is None:
             N, W, H = self.n_envs, self.width, self.height
-            self._host = dict(
-                actions=torch.empty((N,), dtype=torch.int32).pin_memory(),
-                obs=torch.empty((N, W, H, 3), dtype=self.obs_dtype).pin_memory(),
-                reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
-                done=torch.empty((N,), dtype=torch.uint8).pin_memory())
+            t = dict(actions=torch.empty((N,), dtype=torch.int32).pin_memory(),
+                     obs=torch.empty((N, W, H, 3), dtype=self.obs_dtype).pin_memory(),
+                     reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
+                     done=torch.empty((N,), dtype=torch.uint8).pin_memory())
+            self._host = dict(tensors=t, np_actions=t["actions"].numpy(), np_obs=t["obs"].numpy(),
+                              np_reward=t["reward"].numpy(), np_done=t["done"].numpy().view(np.bool_),
+                              ptrs=tuple(t[k].data_ptr() for k in ("actions", "obs", "reward", "done")),
+                              fn=_lib.lib().wf_step_host)
         hb = self._host
-        hb["actions"].numpy()[:] = actions
-        _lib.check(_lib.lib().wf_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), self._obs_code,
-                                           _ptr(hb["reward"]), _ptr(hb["done"])))
-        return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), {}
+        hb["np_actions"][:] = actions
+        pa, po, pr, pd = hb["ptrs"]
+        rc = hb["fn"](self._h, pa, po, self._obs_code, pr, pd)
+        if rc:
+            _lib.check(rc)
+        return hb["np_obs"], hb["np_reward"], hb["np_done"], {}
 
     def observe(self) -> torch.Tensor:
         """``World.get_state()`` (environment.py:399-402) without stepping."""

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -38,6 +39,7 @@ struct wf_env {
     TileState* tstate;
     // wf_step_host staging
     cudaStream_t hstream;
+    bool host_direct, host_obs_direct;
     int32_t* h_actions;
     void* h_obs;
     size_t h_obs_bytes;
@@ -385,6 +387,17 @@ int wf_step(wf_env* e, const int32_t* actions_dev, void* obs_dev, int32_t obs_dt
     return wf_rollout(e, 1, actions_dev, obs_dev, obs_dtype, reward_dev, done_dev, stream);
 }
 
+// Device-visible alias of a page-locked, mapped host buffer (nullptr if the memory is pageable).
+static void* mapped_alias(const void* host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
                  uint8_t* done_host) {
     if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
@@ -392,7 +405,50 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
     WF_CUDA(cudaSetDevice(e->device));
     const DevState& s = e->st;
     const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
-    if (!e->hstream) WF_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+    if (!e->hstream) {
+        WF_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+        // WF_HOST_MODE: "hybrid" (default) = actions/reward/done zero-copy, obs staged + one DMA copy;
+        //               "direct" = everything zero-copy; "copy" = everything staged.
+        const char* m = getenv("WF_HOST_MODE");
+        const std::string mode = m ? m : "hybrid";
+        e->host_direct = mode != "copy";
+        e->host_obs_direct = mode == "direct";
+    }
+    // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
+    // obs/reward/done stores stream over PCIe while the step is still computing and there is no
+    // separate copy to launch.  Pageable buffers fall back to staged cudaMemcpyAsync.
+    void* a_d = e->host_direct ? mapped_alias(actions_host) : nullptr;
+    void* o_d = e->host_direct ? mapped_alias(obs_host) : nullptr;
+    void* r_d = e->host_direct ? mapped_alias(reward_host) : nullptr;
+    void* d_d = e->host_direct ? mapped_alias(done_host) : nullptr;
+    const bool small_direct = a_d && (r_d || !reward_host) && (d_d || !done_host);
+    if (small_direct) {
+        // The SMs' stores over PCIe reach ~39 GB/s, a DMA copy ~48 GB/s (measured, tools/e2e_modes.py):
+        // the 16-36 KB of actions/reward/done go zero-copy (no per-copy latency), the observation block
+        // is written to HBM and moved by ONE cudaMemcpyAsync unless WF_HOST_MODE=direct.
+        const bool obs_direct = e->host_obs_direct && o_d && (reinterpret_cast<uintptr_t>(o_d) & 15u) == 0;
+        void* obs_target = nullptr;
+        if (obs_host) {
+            if (obs_direct) {
+                obs_target = o_d;
+            } else {
+                if (e->h_obs_bytes < obs_bytes) {
+                    cudaFree(e->h_obs);
+                    e->h_obs = nullptr;
+                    WF_CUDA(cudaMalloc(&e->h_obs, obs_bytes));
+                    e->h_obs_bytes = obs_bytes;
+                }
+                obs_target = e->h_obs;
+            }
+        }
+        int rc = wf_step(e, static_cast<const int32_t*>(a_d), obs_target, obs_dtype, static_cast<double*>(r_d),
+                         static_cast<uint8_t*>(d_d), e->hstream);
+        if (rc != WF_OK) return rc;
+        if (obs_host && !obs_direct)
+            WF_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, obs_bytes, cudaMemcpyDeviceToHost, e->hstream));
+        WF_CUDA(cudaStreamSynchronize(e->hstream));
+        return WF_OK;
+    }
     if (!e->h_actions) {
         WF_CUDA(cudaMalloc(&e->h_actions, (size_t)s.N * sizeof(int32_t)));
         WF_CUDA(cudaMalloc(&e->h_reward, (size_t)s.N * sizeof(double)));
