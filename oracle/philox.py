@@ -14,7 +14,7 @@ replace those draws by this stream:
     counter    = (env_id, episode, index, stream)
     stream 0   = RESET   sequential draws of one World.reset():  draw k is word
                  (k & 3) of the block with index = k >> 2
-    stream 1   = ACTION  index = step number t inside the episode, word 0
+    stream 1   = ACTION  step t of the episode uses word (t & 3) of the block with index = t >> 2
     stream 2   = IGNITE  index = k-th extra ignition, words 0/1 -> (x, y)
     a draw u picks ``seq[u % len(seq)]``;  randint(a, b) -> a + u % (b - a + 1)
 """
@@ -53,7 +53,7 @@ def draw(seed: int, env_id: int, episode: int, stream: int, k: int) -> int:
 
 
 def action_draw(seed: int, env_id: int, episode: int, t: int) -> int:
-    return philox4x32_10((env_id, episode, t, STREAM_ACTION), seed_key(seed))[0]
+    return philox4x32_10((env_id, episode, t >> 2, STREAM_ACTION), seed_key(seed))[t & 3]
 
 
 def ignite_draw(seed: int, env_id: int, episode: int, k: int):

@@ -453,8 +453,8 @@ int wfo_step(wfo_env* e, int action, uint8_t* obs, double* reward, int* done) {
 
 int wfo_stream_action(const wfo_env* e) {
     uint32_t w[4];
-    stream_block(e, e->t, 1u, w);
-    return (int)(w[0] % (uint32_t)e->cfg.n_actions);
+    stream_block(e, e->t >> 2, 1u, w); /* ACTION stream: step t = word (t & 3) of block t >> 2 */
+    return (int)(w[e->t & 3u] % (uint32_t)e->cfg.n_actions);
 }
 
 void wfo_get_planes(const wfo_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf,

@@ -6,7 +6,7 @@
 // Stream contract (identical on all sides):
 //   key = (seed & 0xffffffff, seed >> 32);  counter = (env_id, episode, index, stream)
 //   stream 0 RESET : sequential draws of one World.reset(); draw k = word (k & 3) of block k >> 2
-//   stream 1 ACTION: index = step t of the episode; action = word0 % n_actions
+//   stream 1 ACTION: step t of the episode = word (t & 3) of block t >> 2; action = word % n_actions
 //   stream 2 IGNITE: index = k-th extra ignition; cell = (word0 % W, word1 % H)
 #pragma once
 #include <stdint.h>

@@ -183,9 +183,9 @@ __global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* 
         action = actions[env];
     } else {
         uint32_t w[4];
-        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], (uint32_t)sc[WF_S_T], kStreamAction,
-                      c.key0, c.key1, w);
-        action = (int)(w[0] % (uint32_t)c.n_actions);
+        const uint32_t tt = (uint32_t)sc[WF_S_T];
+        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], tt >> 2, kStreamAction, c.key0, c.key1, w);
+        action = (int)(w[tt & 3u] % (uint32_t)c.n_actions);
     }
     int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
     if (!sc[WF_S_ALIVE]) return;

@@ -37,7 +37,10 @@ struct Agent {
     __device__ __forceinline__ void refresh_wind(const WindTable* wt) { kmin = wt->uniform[wid] ? wt->kmin[wid] : -1; }
 };
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef WF_WARPS_PER_BLOCK
+#define WF_WARPS_PER_BLOCK 4
+#endif
+constexpr int kWarpsPerBlock = WF_WARPS_PER_BLOCK;  // small CTAs balance 2048 warps over 148 SMs better
 
 template <int FB>
 __device__ __forceinline__ void dig(Rows<FB>& r, int x, int ax, int ay) {  // Agent.dig, environment.py:123-133
@@ -142,17 +145,18 @@ __device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepC
 constexpr int kStreamWords = 100;  // 3*32*32/32 = 96 words + spill-over of the last row's funnel shift
 
 template <int L>
-__device__ __forceinline__ void emit_obs(void* obs_env, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
-                                         uint32_t* stream_warp, const uint32_t* spread3, int sub, int x, int W, int H,
-                                         bool valid_env) {
-    constexpr int EPW = 32 / L;
-    uint32_t* stream = stream_warp + sub * (kStreamWords / EPW);
+__device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
+                                         uint32_t* stream, const uint32_t* spread3, int lane, int sub, int x, int W,
+                                         int H, int env0, int n_valid) {
+    // obs_step: start of this step's [N][W][H][3] block; env0: first env of the warp; n_valid: how many
+    // of the warp's envs exist.  The warp's envs are adjacent in memory, so they share ONE bit stream.
     const int nbits = W * H * 3;
-    const int nw = (nbits + 31) >> 5;
+    const int tbits = n_valid * nbits;
+    const int nw = (tbits + 31) >> 5;
     __syncwarp();
-    for (int w = x; w < nw + 4 && w < kStreamWords / EPW; w += L) stream[w] = 0u;
+    for (int w = lane; w < nw + 4 && w < kStreamWords; w += 32) stream[w] = 0u;
     __syncwarp();
-    if (x < W) {
+    if (x < W && sub < n_valid) {
         auto piece = [&](int p) -> uint32_t {  // cells 8p..8p+7 of this row -> 24 interleaved bits
             return spread3[(arow >> (8 * p)) & 255u] | (spread3[(frow >> (8 * p)) & 255u] << 1) |
                    (spread3[(freerow >> (8 * p)) & 255u] << 2);
@@ -164,7 +168,7 @@ __device__ __forceinline__ void emit_obs(void* obs_env, int dtype, uint32_t arow
             r1 |= p2 << 16;
             r2 = (p2 >> 16) | (p3 << 8);
         }
-        const int start = 3 * H * x, w0 = start >> 5, sh = start & 31;
+        const int start = sub * nbits + 3 * H * x, w0 = start >> 5, sh = start & 31;
         const uint32_t c0 = r0 << sh, c1 = __funnelshift_l(r0, r1, sh), c2 = __funnelshift_l(r1, r2, sh),
                        c3 = __funnelshift_l(r2, 0u, sh);
         if (c0) atomicOr(&stream[w0], c0);
@@ -173,21 +177,27 @@ __device__ __forceinline__ void emit_obs(void* obs_env, int dtype, uint32_t arow
         if (c3) atomicOr(&stream[w0 + 3], c3);
     }
     __syncwarp();
-    if (!valid_env) return;
+    if (n_valid <= 0) return;
     if (dtype == WF_OBS_U8) {
-        uint8_t* o8 = static_cast<uint8_t*>(obs_env);
-        if ((nbits & 3) == 0) {
+        uint8_t* o8 = static_cast<uint8_t*>(obs_step) + (size_t)env0 * nbits;
+        if ((tbits & 7) == 0 && (reinterpret_cast<uintptr_t>(o8) & 7u) == 0) {
+            uint2* o64 = reinterpret_cast<uint2*>(o8);  // output bytes 8j..8j+7 = stream bits 8j..8j+7
+            for (int j = lane; j < (tbits >> 3); j += 32) {
+                const uint32_t b8 = (stream[j >> 2] >> ((j & 3) * 8)) & 255u;
+                o64[j] = make_uint2(((b8 & 15u) * 0x00204081u) & 0x01010101u, ((b8 >> 4) * 0x00204081u) & 0x01010101u);
+            }
+        } else if ((tbits & 3) == 0 && (reinterpret_cast<uintptr_t>(o8) & 3u) == 0) {
             uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
-            for (int j = x; j < (nbits >> 2); j += L) {  // output word j = stream bits 4j..4j+3, one per byte
+            for (int j = lane; j < (tbits >> 2); j += 32) {
                 const uint32_t nib = (stream[j >> 3] >> ((j & 7) * 4)) & 15u;
                 o32[j] = (nib * 0x00204081u) & 0x01010101u;
             }
         } else {
-            for (int b = x; b < nbits; b += L) o8[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
+            for (int b = lane; b < tbits; b += 32) o8[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
         }
     } else {
-        float* of = static_cast<float*>(obs_env);
-        for (int b = x; b < nbits; b += L) of[b] = ((stream[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+        float* of = static_cast<float*>(obs_step) + (size_t)env0 * nbits;
+        for (int b = lane; b < tbits; b += 32) of[b] = ((stream[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
     }
 }
 
@@ -208,8 +218,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / L, x = lane % L;
-    const int env = (blockIdx.x * kWarpsPerBlock + warp) * EPW + sub;
+    const int env0 = (blockIdx.x * kWarpsPerBlock + warp) * EPW;  // first env of this warp
+    const int env = env0 + sub;
     const bool valid_env = env < s.N;
+    const int n_valid = min(EPW, s.N - env0);
     const int W = s.W, H = s.H;
     const uint32_t colmask = (H == 32) ? 0xffffffffu : ((1u << H) - 1u);
     const uint32_t validmask = (valid_env && x < W) ? colmask : 0u;
@@ -249,23 +261,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
         }
         __syncwarp();
         if (io.obs != nullptr) {
-            const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
-            emit_obs<L>(static_cast<char*>(io.obs) + (size_t)(valid_env ? env : 0) * esz, io.obs_dtype,
-                        (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, sub, x,
-                        W, H, valid_env);
+            emit_obs<L>(io.obs, io.obs_dtype, (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask,
+                        stream_warp, spread3, lane, sub, x, W, H, env0, n_valid);
         }
     } else {
         // ---------------- K x ForestFire.step(action) ----------------
         int it = io.a_iter0;
+        uint32_t ablk[4] = {0u, 0u, 0u, 0u}, ablk_ep = 0xffffffffu, ablk_idx = 0xffffffffu;  // cached ACTION block
         for (int k = 0; k < io.K; ++k) {
             const bool act = valid_env && a.running;  // finished envs are frozen (reward 0, done 1)
             int action;
             if (io.actions != nullptr) {
                 action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else {
-                uint32_t w[4];
-                philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, a.t, kStreamAction, c.key0, c.key1, w);
-                action = (int)(w[0] % (uint32_t)c.n_actions);
+                // one Philox block serves 4 consecutive steps of an episode
+                if ((a.t & 3u) == 0u || ablk_ep != a.episode || ablk_idx != (a.t >> 2)) {
+                    philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, a.t >> 2, kStreamAction, c.key0, c.key1, ablk);
+                    ablk_ep = a.episode;
+                    ablk_idx = a.t >> 2;
+                }
+                const uint32_t aw = (a.t & 3u) == 0u ? ablk[0] : (a.t & 3u) == 1u ? ablk[1] : (a.t & 3u) == 2u ? ablk[2] : ablk[3];
+                action = (int)(aw % (uint32_t)c.n_actions);
             }
             // ---- action: Agent.move :141-155 / toggle_digging :136-138 (agents[0] exists while alive)
             {
@@ -421,10 +437,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             }
             __syncwarp();
             if (io.obs != nullptr) {
-                const size_t esz = (size_t)W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
-                emit_obs<L>(static_cast<char*>(io.obs) + ((size_t)k * s.N + (valid_env ? env : 0)) * esz, io.obs_dtype,
-                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, sub,
-                            x, W, H, valid_env);
+                const size_t step_bytes = (size_t)s.N * W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
+                emit_obs<L>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
+                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, lane,
+                            sub, x, W, H, env0, n_valid);
             }
         }
     }
