@@ -36,10 +36,10 @@ WORKLOADS = {
     "c2": dict(n_envs=4096, meta=dict(width=14, height=14), chunk=64,
                desc="14x14 Logs/14-sized constants, 4096 envs/GPU, ACTION-stream random actions, auto-reset"),
     # configs[3]: 256x256, 1024 envs, wind enabled, multi-ignition stress of the stencil
-    "c4": dict(n_envs=1024, meta=dict(width=256, height=256, wind=[0.85, (1, 0)], extra_ignitions=32), chunk=1,
+    "c4": dict(n_envs=1024, meta=dict(width=256, height=256, wind=[0.85, (1, 0)], extra_ignitions=32), chunk=16,
                desc="256x256, wind [0.85,(1,0)], 32 extra ignitions, 1024 envs/GPU, random actions, auto-reset"),
     # configs[4]: 1024x1024 grid, 64 envs per GPU
-    "c5": dict(n_envs=64, meta=dict(width=1024, height=1024, extra_ignitions=256), chunk=1,
+    "c5": dict(n_envs=64, meta=dict(width=1024, height=1024, extra_ignitions=256), chunk=16,
                desc="1024x1024, no wind, 256 extra ignitions, 64 envs/GPU, random actions, auto-reset"),
 }
 BYTES_PER_CELL_UPDATE = 15  # 6 B state read + 6 B state write + 3 B uint8 observation

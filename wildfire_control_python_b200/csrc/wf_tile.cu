@@ -224,75 +224,90 @@ __global__ void __launch_bounds__(1024) flood_list_kernel(DevState s, TileState 
 // ---------------------------------------------------------------------------------------------
 // The stencil.
 // Active word (it burns or is heated): reduce_fuel :297-307, burn-out, apply_heat_from_to :278-294,
-// set_fire_to :233-246.  Returns the word's heat sources for the next tick.
+// set_fire_to :233-246.  Returns the word's heat sources for the next tick.  Planes this thread does
+// not hold in registers are patched with fire-and-forget reductions (RED), so nothing waits on them.
 template <int FB>
 __device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride, uint32_t& G, uint32_t& B, uint32_t h0,
                                                      uint32_t h1, uint32_t h2, uint32_t h3, const DevState& s,
                                                      const StepCfg& c, uint32_t* hrow, int wid, int kmin,
                                                      uint32_t edge, int& my_edge) {
+    uint32_t m = h0 | h1 | h2 | h3;
+    // issue the loads of this word together: fuel planes (only if it burns) and the first heated cells
     uint32_t FU[FB];
-#pragma unroll
-    for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
-    uint32_t borrow = B;
-#pragma unroll
-    for (int q = 0; q < FB; ++q) {
-        const uint32_t f = FU[q];
-        FU[q] = f ^ borrow;
-        borrow &= ~f;
-    }
-    uint32_t nz = 0u;
-#pragma unroll
-    for (int q = 0; q < FB; ++q) {
-        FU[q] &= ~borrow;
-        nz |= FU[q];
-    }
-    const uint32_t out = B & ~nz;
     if (B) {
 #pragma unroll
-        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
+        for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
     }
-    uint32_t F = 0u;
-    if (out) {  // type := burnt whatever it was (a dug-while-burning cell is dirt, Q7)
-        F = P[P_F * pstride];
-        P[P_BT * pstride] |= out;
-        P[P_D * pstride] &= ~out;
-        P[P_WT * pstride] &= ~out;
-        F &= ~out; G &= ~out; B &= ~out;
-    }
-    // Heated cells: hit counters are read-modify-written; up to 4 cells per round so that their loads
-    // are in flight together (a front usually heats 1-4 cells of a word).
-    uint32_t ign = 0u, m = h0 | h1 | h2 | h3;
-    while (m) {
-        int y[4];
-        uint32_t v[4];
+    int y[4];
+    uint32_t v[4];
+    uint32_t mm = m;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            y[j] = m ? __ffs(m) - 1 : -1;
-            m &= m - 1u;  // (0 & anything) stays 0
+    for (int j = 0; j < 4; ++j) {
+        y[j] = mm ? __ffs(mm) - 1 : -1;
+        mm &= mm - 1u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = y[j] >= 0 ? hrow[y[j]] : 0u;
+
+    uint32_t out = 0u, ge2 = 0u;
+    const bool burning_word = B != 0u;
+    if (B) {
+        uint32_t borrow = B;
+#pragma unroll
+        for (int q = 0; q < FB; ++q) {
+            const uint32_t f = FU[q];
+            FU[q] = f ^ borrow;
+            borrow &= ~f;
         }
+        uint32_t nz = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = y[j] >= 0 ? hrow[y[j]] : 0u;
+        for (int q = 0; q < FB; ++q) {
+            FU[q] &= ~borrow;
+            nz |= FU[q];
+        }
+        out = B & ~nz;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (y[j] < 0) continue;
-            const int yy = y[j];
-            const uint32_t nv = v[j] + (((h0 >> yy) & 1u) | (((h1 >> yy) & 1u) << 8) | (((h2 >> yy) & 1u) << 16) |
-                                        (((h3 >> yy) & 1u) << 24));
-            hrow[yy] = nv;
-            const bool ig = kmin >= 0 ? (int)__dp4a(nv, 0x01010101u, 0u) >= kmin : ignites(nv, s.wind, wid, c.threshold);
-            if (ig) ign |= 1u << yy;
+        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
+#pragma unroll
+        for (int q = 1; q < FB; ++q) ge2 |= FU[q];  // fuel >= 2, for every cell of the word
+    }
+    uint32_t ign = 0u;
+    auto heat_cell = [&](int yy, uint32_t old) {
+        const uint32_t nv = old + (((h0 >> yy) & 1u) | (((h1 >> yy) & 1u) << 8) | (((h2 >> yy) & 1u) << 16) |
+                                   (((h3 >> yy) & 1u) << 24));
+        hrow[yy] = nv;
+        const bool ig = kmin >= 0 ? (int)__dp4a(nv, 0x01010101u, 0u) >= kmin : ignites(nv, s.wind, wid, c.threshold);
+        if (ig) ign |= 1u << yy;
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (y[j] >= 0) heat_cell(y[j], v[j]);
+    while (mm) {  // more than 4 heated cells in one word: rare
+        const int yy = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        heat_cell(yy, hrow[yy]);
+    }
+    if (out) {  // type := burnt whatever it was (a dug-while-burning cell is dirt, Q7)
+        atomicOr(&P[P_BT * pstride], out);
+        atomicAnd(&P[P_D * pstride], ~out);
+        atomicAnd(&P[P_WT * pstride], ~out);
+        atomicAnd(&P[P_F * pstride], ~out);
+        G &= ~out; B &= ~out;
+    }
+    if (ign) {
+        atomicOr(&P[P_F * pstride], ign);
+        G &= ~ign; B |= ign;
+        if (!burning_word) {  // heated-only word that ignites (rare): now its fuel planes are needed
+#pragma unroll
+            for (int q = 1; q < FB; ++q) ge2 |= P[(P_FU0 + q) * pstride];
         }
     }
     if (ign | out) {
-        if (!out) F = P[P_F * pstride];
-        G &= ~ign; F |= ign; B |= ign;
-        P[P_G * pstride] = G; P[P_F * pstride] = F; P[P_B * pstride] = B;
+        P[P_G * pstride] = G;
+        P[P_B * pstride] = B;
     }
     if (ign & edge) my_edge = 1;
-    uint32_t ge2 = 0u;  // sources of the next tick: burning with fuel >= 2 (new fires hold the reset fuel)
-#pragma unroll
-    for (int q = 1; q < FB; ++q) ge2 |= FU[q];
-    return B & ge2;
+    return B & ge2;  // sources of the next tick: burning with fuel >= 2
 }
 
 // does a burning cell of this word sit in, or next to, the border-connected region R?
@@ -306,25 +321,35 @@ __device__ __forceinline__ bool touches_reach(const uint32_t* R, uint32_t B, int
     return (B & near) != 0u;
 }
 
-// VW = words per thread along y: 4 (128-bit loads; needs HW % 4 == 0) or 1.
+// VW = words per thread along y in the streaming phase: 4 (128-bit loads; needs HW % 4 == 0) or 1.
+// Phase 1 streams G, B and the source mask of every word and queues the ACTIVE words (burning or
+// heated) of the CTA in shared memory; phase 2 hands one queued word to each thread, so the
+// dependent loads of the active path (fuel planes, hit counters) run at full occupancy instead of
+// serially inside the few threads that happen to own a fire front.
 template <int FB, int VW>
 __global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, StepCfg c, TileState t, int do_tick,
                                                                  int hw_shift) {
+    constexpr int QCAP = kTileThreads * VW;
     __shared__ int red[4];
+    __shared__ int q_n;
+    __shared__ uint32_t q_idx[QCAP], q_G[QCAP], q_B[QCAP], q_h[4][QCAP];
     const int env = blockIdx.y;
     if (threadIdx.x < 4) red[threadIdx.x] = 0;
+    if (threadIdx.x == 0) q_n = 0;
     __syncthreads();
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VW;  // first word of this thread
     const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
     const bool act = sc[WF_S_RESERVED] != 0;
     const bool want_touch = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED];
+    const size_t pstride = (size_t)s.N * s.RS * s.HW;
+    uint32_t* const P0 = s.planes + word_index(s, 0, env, 0, 0);
+    const int scur = t.cur ? t.P_S1 : t.P_S0, snxt = t.cur ? t.P_S0 : t.P_S1;
     int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
     if (i < nwords) {
         const int x = hw_shift >= 0 ? (i >> hw_shift) : (i / HW);
         const int w0 = i - x * HW;
-        const size_t pstride = (size_t)s.N * s.RS * s.HW;
-        uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + i;
+        uint32_t* P = P0 + i;
         uint32_t G[VW], B[VW];
         if (VW == 4) {
             const uint4 g4 = *reinterpret_cast<const uint4*>(P + P_G * pstride);
@@ -336,9 +361,9 @@ __global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, Ste
             B[0] = P[P_B * pstride];
         }
         if (act && do_tick) {
-            const uint32_t* Sc = P + (size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride;
-            uint32_t* Sn = P + (size_t)(t.cur ? t.P_S0 : t.P_S1) * pstride;
-            uint32_t S[VW + 2], Sup[VW], Sdn[VW], Snew[VW];
+            const uint32_t* Sc = P + (size_t)scur * pstride;
+            uint32_t* Sn = P + (size_t)snxt * pstride;
+            uint32_t S[VW + 2], Sup[VW], Sdn[VW];
             if (VW == 4) {
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                 const uint4 s4 = *reinterpret_cast<const uint4*>(Sc);
@@ -354,30 +379,52 @@ __global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, Ste
             }
             S[0] = w0 > 0 ? Sc[-1] : 0u;
             S[VW + 1] = w0 + VW < HW ? Sc[VW] : 0u;
-            const int wid = sc[WF_S_WIND_ID];
-            const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
 #pragma unroll
             for (int k = 0; k < VW; ++k) {
                 const uint32_t h0 = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
                 const uint32_t h1 = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
                 const uint32_t h2 = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
                 const uint32_t h3 = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
-                uint32_t sn = 0u;
                 if (B[k] | h0 | h1 | h2 | h3) {
-                    sn = tick_active_word<FB>(P + k, pstride, G[k], B[k], h0, h1, h2, h3, s, c,
-                                              s.hits + ((size_t)env * W + x) * H + 32 * (w0 + k), wid, kmin,
-                                              edge_word(W, H, x, w0 + k), my_edge);
+                    const int pos = atomicAdd(&q_n, 1);
+                    q_idx[pos] = (uint32_t)(i + k);
+                    q_G[pos] = G[k]; q_B[pos] = B[k];
+                    q_h[0][pos] = h0; q_h[1][pos] = h1; q_h[2][pos] = h2; q_h[3][pos] = h3;
+                } else {
+                    my_ng += __popc(G[k]);  // inactive words cannot burn: B == 0
                 }
-                Snew[k] = sn;
             }
-            if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(Snew[0], Snew[VW > 1 ? 1 : 0], Snew[VW > 2 ? 2 : 0], Snew[VW > 3 ? 3 : 0]);
-            else Sn[0] = Snew[0];
-        }
+            // inactive words have no sources next tick; queued words overwrite their slot in phase 2
+            if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(0u, 0u, 0u, 0u);
+            else Sn[0] = 0u;
+        } else {
 #pragma unroll
-        for (int k = 0; k < VW; ++k) {
-            my_nb += __popc(B[k]);
-            my_ng += __popc(G[k]);
-            if (B[k] && want_touch && touches_reach(P + k + (size_t)t.P_R * pstride, B[k], x, w0 + k, W, HW)) my_touch = 1;
+            for (int k = 0; k < VW; ++k) {
+                my_nb += __popc(B[k]);
+                my_ng += __popc(G[k]);
+                if (B[k] && want_touch && touches_reach(P + k + (size_t)t.P_R * pstride, B[k], x, w0 + k, W, HW)) my_touch = 1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one queued active word per thread
+    const int nq = q_n;
+    if (nq) {
+        const int wid = sc[WF_S_WIND_ID];
+        const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
+        for (int it = threadIdx.x; it < nq; it += blockDim.x) {
+            const int wi = (int)q_idx[it];
+            const int x = hw_shift >= 0 ? (wi >> hw_shift) : (wi / HW);
+            const int w = wi - x * HW;
+            uint32_t G = q_G[it], B = q_B[it];
+            uint32_t* P = P0 + wi;
+            const uint32_t sn = tick_active_word<FB>(P, pstride, G, B, q_h[0][it], q_h[1][it], q_h[2][it], q_h[3][it], s, c,
+                                                     s.hits + ((size_t)env * W + x) * H + 32 * w, wid, kmin,
+                                                     edge_word(W, H, x, w), my_edge);
+            P[(size_t)snxt * pstride] = sn;
+            my_nb += __popc(B);
+            my_ng += __popc(G);
+            if (B && want_touch && touches_reach(P + (size_t)t.P_R * pstride, B, x, w, W, HW)) my_touch = 1;
         }
     }
     // ---- per-env reductions: warp redux -> shared -> one atomic per block and quantity
