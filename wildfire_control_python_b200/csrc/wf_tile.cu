@@ -520,32 +520,45 @@ __global__ void __launch_bounds__(kTileThreads) obs_kernel(DevState s, void* obs
 }
 
 // ---------------------------------------------------------------------------------------------
-// World.reset (environment.py:186-212) of one env by one CTA.
+// World.reset part 1 (reset_map, environment.py:59-67): every plane and the temp layer back to their
+// defaults.  Grid = (slices, persistent CTAs over the reset list): a big env is initialised by several CTAs.
+template <int FB>
+__global__ void __launch_bounds__(1024) reset_init_kernel(DevState s, StepCfg c, TileState t) {
+    const int n = t.counters[1];
+    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
+    const size_t pstride = (size_t)s.N * s.RS * s.HW;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int k = blockIdx.y; k < n; k += gridDim.y) {
+        const int env = t.reset_list[k];
+        uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
+        for (int i = tid; i < nwords; i += nthr) {
+            const int x = i / HW, w = i - x * HW;
+            const uint32_t valid = valid_word(H, w);
+            uint32_t* P = P0 + i;
+            P[P_G * pstride] = valid;
+            P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
+            P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
+#pragma unroll
+            for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
+            P[(size_t)t.P_S0 * pstride] = 0u;
+            P[(size_t)t.P_S1 * pstride] = 0u;
+            P[(size_t)t.P_R * pstride] = valid;  // open field: every cell reaches the border (re-flooded if rivers)
+        }
+        uint32_t* hits = s.hits + (size_t)env * W * H;  // temp layer := 0
+        if (((size_t)env * W * H) % 4 == 0 && (W * H) % 4 == 0) {
+            uint4* h4 = reinterpret_cast<uint4*>(hits);
+            for (int i = tid; i < (W * H) / 4; i += nthr) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (int i = tid; i < W * H; i += nthr) hits[i] = 0u;
+        }
+    }
+}
+
+// World.reset part 2 (environment.py:186-212) of one env by one CTA: wind, river, fire, agent, ignitions.
 template <int FB>
 __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState& t, const wf_init* init, int env) {
     __shared__ int sh_fab, sh_nb;
     const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {  // reset_map :59-67
-        const int x = i / HW, w = i - x * HW;
-        const uint32_t valid = valid_word(H, w);
-        uint32_t* P = P0 + i;
-        P[P_G * pstride] = valid;
-        P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
-        P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
-#pragma unroll
-        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
-        P[(size_t)t.P_S0 * pstride] = 0u;
-        P[(size_t)t.P_S1 * pstride] = 0u;
-    }
-    uint32_t* hits = s.hits + (size_t)env * W * H;  // temp layer := 0
-    if (((size_t)env * W * H) % 4 == 0 && (W * H) % 4 == 0) {
-        uint4* h4 = reinterpret_cast<uint4*>(hits);
-        for (int i = threadIdx.x; i < (W * H) / 4; i += blockDim.x) h4[i] = make_uint4(0u, 0u, 0u, 0u);
-    } else {
-        for (int i = threadIdx.x; i < W * H; i += blockDim.x) hits[i] = 0u;
-    }
     if (threadIdx.x == 0) { sh_fab = 0; sh_nb = 0; }
     __syncthreads();
     int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
@@ -596,6 +609,7 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
             plane_word(s, P_G, env, ax, w) &= ~bit; plane_word(s, P_F, env, ax, w) &= ~bit;
             plane_word(s, P_BT, env, ax, w) &= ~bit; plane_word(s, P_WT, env, ax, w) &= ~bit;
             plane_word(s, P_D, env, ax, w) |= bit; plane_word(s, P_I, env, ax, w) |= bit;
+            plane_word(s, t.P_R, env, ax, w) &= ~bit;
         }
         sc[WF_S_ALIVE] = 1; sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_DEAD] = 0; sc[WF_S_DIGGING] = 1;
         sc[WF_S_VISIBLE] = 1; sc[WF_S_RUNNING] = 1; sc[WF_S_LATCHED] = 0;
@@ -622,7 +636,10 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
         if (x == 0 || x == W - 1 || y == 0 || y == H - 1) sh_fab = 1;
     }
     __syncthreads();
-    flood_block(s, t, env);
+    // Without rivers the only blocked cell is the agent's start cell, and one cell cannot cut a
+    // >= 10x10 grid: R = every free cell (set by reset_init_kernel).  With rivers: flood.
+    if (c.make_rivers) flood_block(s, t, env);
+    else if (threadIdx.x == 0) t.need_flood[env] = 0;
     int n = 0;
     const uint32_t* B = &plane_word(s, P_B, env, 0, 0);
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) n += __popc(B[i]);
@@ -748,6 +765,10 @@ void tile_destroy(TileState* t) {
 
 static int cta_threads(const DevState& s) { return s.W * s.HW >= 8192 ? 1024 : 256; }
 static int list_grid(const DevState& s) { return s.N < 296 ? s.N : 296; }  // 2 persistent CTAs per SM
+static int init_slices(const DevState& s) {  // CTAs that share one env's plane initialisation
+    const int per = (s.W * s.H + 65535) / 65536;  // ~64K cells (256 KB of hit counters) per CTA
+    return per < 1 ? 1 : (per > 16 ? 16 : per);
+}
 
 template <int FB>
 static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st,
@@ -758,8 +779,9 @@ static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c,
     if (io.reset_mode) {
         zero_counter_kernel<<<1, 1, 0, st>>>(*t, 1);
         mask_to_list_kernel<<<eb, 128, 0, st>>>(*t, io.mask, s.N);
+        reset_init_kernel<FB><<<dim3(init_slices(s), list_grid(s)), 1024, 0, st>>>(s, c, *t);
         reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, io.init);
-        *launches += 3;
+        *launches += 4;
     } else {
         agent_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick);
         flood_list_kernel<<<list_grid(s), 1024, 0, st>>>(s, *t);
@@ -776,8 +798,9 @@ static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c,
         finish_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick);
         *launches += 4;
         if (c.auto_reset) {
+            reset_init_kernel<FB><<<dim3(init_slices(s), list_grid(s)), 1024, 0, st>>>(s, c, *t);
             reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, nullptr);
-            *launches += 1;
+            *launches += 2;
         }
     }
     if (io.obs) {
