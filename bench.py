@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the batched fire-spread step on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is ONE ForestFire.step over the whole batch of the workload (default c2 = BASELINE.json
@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE.json configs[1]: 14x14 (Logs/14-sized constants) batched 4096 envs, random actions
     "c2": dict(n_envs=4096, meta=dict(width=14, height=14), chunk=64,
                desc="14x14 Logs/14-sized constants, 4096 envs/GPU, ACTION-stream random actions, auto-reset"),
+    # configs[2]: 14x14 batched 65536 envs (8192 per GPU on 8 GPUs) with a DQN-policy rollout via torch:
+    # Flatten -> Dense(50, sigmoid) -> Dense(4) (DQN.py:209-233), fixed-seed weights, epsilon-greedy 0.1
+    "c3": dict(n_envs=8192, meta=dict(width=14, height=14), chunk=1, policy=True,
+               desc="14x14 Logs/14-sized constants, 8192 envs/GPU, torch MLP policy 588-50-4 in the loop (eps 0.1), auto-reset"),
     # configs[3]: 256x256, 1024 envs, wind enabled, multi-ignition stress of the stencil
     "c4": dict(n_envs=1024, meta=dict(width=256, height=256, wind=[0.85, (1, 0)], extra_ignitions=32), chunk=16,
                desc="256x256, wind [0.85,(1,0)], 32 extra ignitions, 1024 envs/GPU, ACTION-stream actions, auto-reset"),
@@ -301,6 +305,63 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, no_graph: bool,
     return res
 
 
+def measure_policy(D: Dist, name: str, K: int, Wm: int):
+    """configs[2]: the reference's DQN network picks the actions (DQN.py:188-233), one wf_step per step.
+    The whole step (obs -> float -> MLP -> epsilon-greedy -> wf_step) is captured in a CUDA graph."""
+    torch = D.torch
+    from wildfire_control_python_b200 import BatchedForestFire
+    wl = WORKLOADS[name]
+    dev, rank, world = D.dev, D.rank, D.world
+    N, W, H = wl["n_envs"], wl["meta"]["width"], wl["meta"]["height"]
+    env = BatchedForestFire(N, device=dev, auto_reset=True, seed=0, env_id_base=rank * N, **wl["meta"])
+    obs = env.reset()
+    g = torch.Generator(device=dev).manual_seed(1234)  # same weights on every rank
+    w1 = torch.randn(W * H * 3, 50, device=dev, generator=g) * 0.05
+    b1 = torch.zeros(50, device=dev)
+    w2 = torch.randn(50, env.n_actions, device=dev, generator=g) * 0.05
+    b2 = torch.zeros(env.n_actions, device=dev)
+    actions = torch.zeros(N, dtype=torch.int32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+
+    def one_step():
+        q = torch.sigmoid(obs.view(N, -1).float() @ w1 + b1) @ w2 + b2
+        greedy = q.argmax(1).to(torch.int32)
+        explore = torch.rand(N, device=dev) < 0.1
+        rnd = torch.randint(0, env.n_actions, (N,), device=dev, dtype=torch.int32)
+        actions.copy_(torch.where(explore, rnd, greedy))
+        env.step(actions)  # writes the handle's persistent obs buffer, which `obs` aliases
+
+    for _ in range(3):
+        one_step()
+    G_STEPS = 16
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        one_step()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(G_STEPS):
+                one_step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    reps_w, reps = max(1, Wm // G_STEPS), max(1, K // G_STEPS)
+    for _ in range(reps_w):
+        graph.replay()
+    D.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        graph.replay()
+    ev1.record()
+    D.barrier()
+    ms = D.max_over_ranks(ev0.elapsed_time(ev1))
+    Kt = reps * G_STEPS
+    res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": Kt, "chunk": 1, "fused": True, "graph": True, "ms": ms,
+           "launches": Kt, "value": world * N * Kt / (ms * 1e-3), "obs_mb": obs.numel() / 1e6, "family": env.kernel_family,
+           "stats": env.stats(), "policy": "torch MLP 588-50(sigmoid)-4, eps-greedy 0.1, inside a 16-step CUDA graph"}
+    env.close()
+    return res
+
+
 def roofline_of(res, world):
     peak, peak_src = load_peaks()
     N, W, H, fused = res["N"], res["W"], res["H"], res["fused"]
@@ -330,7 +391,10 @@ def roofline_of(res, world):
 def run_ours(args, wl):
     D = Dist(args.gpus)
     with ClockSampler(D.local) as clk:
-        res = measure(D, args.workload, args.steps, args.warmup, args.chunk, args.no_graph, True, True)
+        if wl.get("policy"):
+            res = measure_policy(D, args.workload, args.steps, args.warmup)
+        else:
+            res = measure(D, args.workload, args.steps, args.warmup, args.chunk, args.no_graph, True, True)
         sec = None
         if args.workload == "c2" and not args.no_secondary:
             sec = measure(D, "c4", 160, 32, 0, args.no_graph, False, False)
@@ -369,6 +433,9 @@ def run_ours(args, wl):
         "clocks": clocks,
         "stats": res["stats"],
     }
+    if "policy" in res:
+        line["config"]["policy"] = res["policy"]
+        line["steps"] = res["K"]
     if sec is not None:
         line["secondary"] = {"c4": {
             "workload": WORKLOADS["c4"]["desc"], "value": sec["value"], "unit": "env-steps/s", "steps": sec["K"],
