@@ -120,6 +120,17 @@ int wf_step(wf_env* env, const int32_t* actions_dev, void* obs_dev, int32_t obs_
 int wf_rollout(wf_env* env, int32_t k_steps, const int32_t* actions_dev, void* obs_dev,
                int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream);
 
+/* Action sources of wf_rollout_policy. */
+enum {
+    WF_POLICY_STREAM = 0, /* uniform random action from the ACTION stream (same as wf_rollout with NULL actions) */
+    WF_POLICY_WALK = 1    /* the reference's heuristic "walk round the fire" demonstration / Baseline policy:
+                             DQN.choose_randomwalk_action, DQN.py:353-389 (draws from the POLICY stream) */
+};
+/* wf_rollout with the actions chosen on the device by a built-in policy (DQN.collect_memories' inner loop,
+ * DQN.py:303-308: choose_randomwalk_action -> sim.step).  actions_out_dev: [K][N] int32 or NULL. */
+int wf_rollout_policy(wf_env* env, int32_t k_steps, int32_t policy, int32_t* actions_out_dev, void* obs_dev,
+                      int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream);
+
 /* Host-buffer variant of wf_step (what a CPU-side caller of the reference would bind):
  * copies actions H2D, steps, copies obs/reward/done D2H and synchronises.  Buffers should
  * be page-locked for full PCIe rate; pageable memory works but is slower. */

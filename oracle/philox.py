@@ -16,6 +16,8 @@ replace those draws by this stream:
                  (k & 3) of the block with index = k >> 2
     stream 1   = ACTION  step t of the episode uses word (t & 3) of the block with index = t >> 2
     stream 2   = IGNITE  index = k-th extra ignition, words 0/1 -> (x, y)
+    stream 3   = POLICY  draws of the heuristic walk policy (DQN.py:353-389) at step t:
+                 draw j (j < 12) is word (j & 3) of the block with index = 3 * t + (j >> 2)
     a draw u picks ``seq[u % len(seq)]``;  randint(a, b) -> a + u % (b - a + 1)
 """
 from __future__ import annotations
@@ -29,6 +31,7 @@ MASK = 0xFFFFFFFF
 STREAM_RESET = 0
 STREAM_ACTION = 1
 STREAM_IGNITE = 2
+STREAM_POLICY = 3
 
 
 def philox4x32_10(ctr, key):
@@ -54,6 +57,10 @@ def draw(seed: int, env_id: int, episode: int, stream: int, k: int) -> int:
 
 def action_draw(seed: int, env_id: int, episode: int, t: int) -> int:
     return philox4x32_10((env_id, episode, t >> 2, STREAM_ACTION), seed_key(seed))[t & 3]
+
+
+def policy_draw(seed: int, env_id: int, episode: int, t: int, j: int) -> int:
+    return philox4x32_10((env_id, episode, 3 * t + (j >> 2), STREAM_POLICY), seed_key(seed))[j & 3]
 
 
 def ignite_draw(seed: int, env_id: int, episode: int, k: int):

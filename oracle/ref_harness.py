@@ -99,6 +99,44 @@ def philox_rng(stream: philox.ResetStream):
         pyrandom.randint = old_randint
 
 
+_WALK_FN = None
+
+
+def reference_walk_policy():
+    """``DQN.choose_randomwalk_action`` (DQN.py:353-389) as a plain function of ``self``.
+
+    DQN.py imports Keras at module level, which the image lacks, so the method's source is taken
+    from the reference file with ``ast`` and compiled on its own; nothing is copied into the repo."""
+    global _WALK_FN
+    if _WALK_FN is None:
+        import ast
+        src = open(os.path.join(REF_ROOT, "DQN.py")).read()
+        tree = ast.parse(src)
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "choose_randomwalk_action")
+        mod = ast.Module(body=[fn], type_ignores=[])
+        ns = {"np": np}
+        exec(compile(mod, os.path.join(REF_ROOT, "DQN.py"), "exec"), ns)
+        _WALK_FN = ns["choose_randomwalk_action"]
+    return _WALK_FN
+
+
+class _PolicyStream:
+    """np.random.choice stand-in reading the POLICY stream of one (env, episode, step)."""
+
+    def __init__(self, seed, env_id, episode, t):
+        self.a = (seed, env_id, episode, t)
+        self.j = 0
+
+    def choice(self, seq):
+        seq = list(seq)
+        u = philox.policy_draw(*self.a, self.j)
+        self.j += 1
+        return seq[u % len(seq)]
+
+    def randint(self, a, b):
+        raise AssertionError("the walk policy only uses np.random.choice")
+
+
 DEFAULT_META = dict(
     death_penalty=-1000, contained_bonus=1000, default_reward=-1,
     wind=[0.54, (0, 0)], n_actions=4, a_speed=1, make_rivers=False,
@@ -159,6 +197,13 @@ class RefEnv:
 
     def random_action(self) -> int:
         return philox.action_draw(self.seed, self.env_id, self.episode, self.t) % int(self.cfg["n_actions"])
+
+    def walk_action(self) -> int:
+        """The reference's own heuristic policy code, fed from the shared POLICY stream."""
+        self._apply_meta()
+        fake_self = types.SimpleNamespace(sim=self.sim)
+        with philox_rng(_PolicyStream(self.seed, self.env_id, self.episode, self.t)):
+            return int(reference_walk_policy()(fake_self))
 
     def step(self, action):
         self._apply_meta()  # METADATA is a process-wide global in the reference

@@ -39,6 +39,10 @@ SCENARIOS = [
     dict(name="ring3_20_rivers", width=20, height=20, seed=23, policy="ring3", make_rivers=True),
     dict(name="ring2_12_toggle", width=12, height=12, seed=24, policy="ring2", allow_dig_toggle=True, n_actions=6),
     dict(name="ring4_16_aspeed2", width=16, height=16, seed=25, policy="ring4", a_speed=2),
+    # the reference's heuristic walk policy (DQN.choose_randomwalk_action), its own code vs the C restatement
+    dict(name="walk_10", width=10, height=10, seed=40, policy="walk"),
+    dict(name="walk_14", width=14, height=14, seed=41, policy="walk"),
+    dict(name="walk_20_rivers_wind", width=20, height=20, seed=42, policy="walk", make_rivers=True, wind="random"),
 ]
 
 
@@ -82,6 +86,9 @@ def run(sc, steps):
         assert a == orc.random_action()
         if ref.t < len(plan):
             a = plan[ref.t]
+        if policy == "walk":
+            a = ref.walk_action()
+            assert a == orc.walk_action(), f"{sc['name']} ep{ref.episode} t{ref.t}: walk action"
         o_r, r_r, d_r, _ = ref.step(a)
         o_o, r_o, d_o, _ = orc.step(a)
         tag = f"{sc['name']} ep{ref.episode} t{ref.t} a{a}"

@@ -457,6 +457,32 @@ int wfo_stream_action(const wfo_env* e) {
     return (int)(w[e->t & 3u] % (uint32_t)e->cfg.n_actions);
 }
 
+/* DQN.choose_randomwalk_action(avoid_fire=True) -- DQN.py:353-389: walk clockwise round the fire
+ * origin, re-drawing (at most 11 times) while the chosen move would step onto a burning cell.
+ * np.random.choice(possible_actions) is draw j of the POLICY stream (stream 3) of step t. */
+int wfo_policy_action(const wfo_env* e) {
+    if (!e->alive) return 0; /* :356-357 */
+    static const int DX[4] = {0, 0, 1, -1}, DY[4] = {-1, 1, 0, 0}; /* N S E W */
+    const int mid_x = e->W / 2, mid_y = e->H / 2, ax = e->ax, ay = e->ay;
+    int count = 0, action = 0, j = 0;
+    for (;;) {
+        int a0 = 0, a1 = 0; /* possible_actions, :369-376 */
+        if (ax >= mid_x && ay > mid_y) { a0 = 1; a1 = 3; }  /* ["S", "W"] */
+        if (ax > mid_x && ay <= mid_y) { a0 = 1; a1 = 2; }  /* ["S", "E"] */
+        if (ax <= mid_x && ay < mid_y) { a0 = 0; a1 = 2; }  /* ["N", "E"] */
+        if (ax < mid_x && ay >= mid_y) { a0 = 0; a1 = 3; }  /* ["N", "W"] */
+        uint32_t w[4];
+        stream_block(e, 3u * e->t + (uint32_t)(j >> 2), 3u, w);
+        action = (w[j & 3] % 2u) ? a1 : a0; /* :379 */
+        j++;
+        int nx = ax + DX[action], ny = ay + DY[action];
+        int fire_at_loc = inbounds(e, nx, ny) && is_burning(e, nx, ny); /* Agent.fire_in_direction environment.py:158-160 */
+        if (!fire_at_loc || count > 10) break; /* :385-387 */
+        count++;
+    }
+    return action;
+}
+
 void wfo_get_planes(const wfo_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf,
                     int32_t* fuel, double* temp, uint8_t* apos) {
     size_t n = (size_t)e->W * e->H;

@@ -51,6 +51,8 @@ void wfo_reset_at(wfo_env* e, int ax, int ay);
 int wfo_step(wfo_env* e, int action, uint8_t* obs_u8, double* reward, int* done);
 /* The action the shared ACTION stream prescribes for the env's current (episode, t). */
 int wfo_stream_action(const wfo_env* e);
+/* The reference's heuristic walk policy (DQN.choose_randomwalk_action, DQN.py:353-389), POLICY stream. */
+int wfo_policy_action(const wfo_env* e);
 void wfo_get_obs(const wfo_env* e, uint8_t* obs_u8);
 
 /* Canonical planes, each W*H, index x*H+y.  Any pointer may be NULL. */

@@ -53,6 +53,8 @@ def lib():
         L.wfo_step.argtypes = [p, C.c_int, u8p, f64p, C.POINTER(C.c_int)]
         L.wfo_stream_action.restype = C.c_int
         L.wfo_stream_action.argtypes = [p]
+        L.wfo_policy_action.restype = C.c_int
+        L.wfo_policy_action.argtypes = [p]
         L.wfo_get_obs.argtypes = [p, u8p]
         L.wfo_get_planes.argtypes = [p, u8p, u8p, u8p, i32p, f64p, u8p]
         L.wfo_get_scalars.argtypes = [p, i32p]
@@ -131,6 +133,10 @@ class OracleEnv:
 
     def random_action(self) -> int:
         return lib().wfo_stream_action(self.h)
+
+    def walk_action(self) -> int:
+        """DQN.choose_randomwalk_action (DQN.py:353-389) with POLICY-stream draws."""
+        return lib().wfo_policy_action(self.h)
 
     def step(self, action: int):
         o = np.empty((self.W, self.H, 3), np.uint8)

@@ -159,15 +159,19 @@ class BatchedForestFire:
             _lib.check(rc)
         return self._obs, self._reward, self._done_bool, {}
 
-    def rollout(self, k_steps: int, actions=None, obs: bool = True, out=None):
+    def rollout(self, k_steps: int, actions=None, obs: bool = True, out=None, policy: str = "stream",
+                return_actions: bool = False):
         """``k_steps`` consecutive ``step`` calls in one launch (state stays on chip in between).
 
-        ``actions``: ``[K, N]`` ints or ``None`` = draw from the shared ACTION stream.
+        ``actions``: ``[K, N]`` ints, or ``None`` = chosen on the device by ``policy``:
+        ``"stream"`` (uniform random, ACTION stream) or ``"walk"`` (the reference's heuristic
+        demonstration / Baseline policy ``DQN.choose_randomwalk_action``, DQN.py:353-389).
         ``out``: optional ``(obs_or_None, reward, done_u8)`` buffers to write into.
-        Returns ``(obs [K,N,W,H,3] or None, reward [K,N], done [K,N])``.
+        Returns ``(obs [K,N,W,H,3] or None, reward [K,N], done [K,N])`` (+ ``actions [K,N]`` if asked).
         """
         K, N = int(k_steps), self.n_envs
         a = None if actions is None else self._as_i32(actions, (K, N))
+        pol = {"stream": _lib.WF_POLICY_STREAM, "walk": _lib.WF_POLICY_WALK}[policy]
         with torch.cuda.device(self.device):
             if out is not None:
                 o, r, d = out
@@ -176,8 +180,16 @@ class BatchedForestFire:
                      if obs else None)
                 r = torch.empty((K, N), dtype=torch.float64, device=self.device)
                 d = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-            _lib.check(_lib.lib().wf_rollout(self._h, K, _ptr(a), _ptr(o), self._obs_code, _ptr(r), _ptr(d),
-                                             self._stream()))
+            L = _lib.lib()
+            if a is not None:
+                _lib.check(L.wf_rollout(self._h, K, _ptr(a), _ptr(o), self._obs_code, _ptr(r), _ptr(d), self._stream()))
+                chosen = a
+            else:
+                chosen = torch.empty((K, N), dtype=torch.int32, device=self.device) if return_actions else None
+                _lib.check(L.wf_rollout_policy(self._h, K, pol, _ptr(chosen), _ptr(o), self._obs_code, _ptr(r), _ptr(d),
+                                               self._stream()))
+        if return_actions:
+            return o, r, d.view(torch.bool), chosen
         return o, r, d.view(torch.bool)
 
     def step_host(self, actions):

@@ -330,10 +330,10 @@ int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* 
     WF_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->tile) {
-        TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, 1};
+        TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, 1, 0, nullptr};
         WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
     } else {
-        WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H)};
+        WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H), 0, nullptr};
         WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
         e->launches += 1;
     }
@@ -349,10 +349,11 @@ static int advance_a_iter(wf_env* e, int k_steps) {
     return it;
 }
 
-int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype,
-               double* reward_dev, uint8_t* done_dev, void* stream) {
+static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, int32_t policy, int32_t* actions_out,
+                        void* obs_dev, int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     if (k_steps < 1) return fail(WF_ERR_INVALID, "k_steps must be >= 1");
+    if (policy != WF_POLICY_STREAM && policy != WF_POLICY_WALK) return fail(WF_ERR_INVALID, "unknown policy");
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -367,18 +368,29 @@ int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs
                       obs_dev ? static_cast<char*>(obs_dev) + (size_t)k * s.N * esz : nullptr,
                       reward_dev ? reward_dev + (size_t)k * s.N : nullptr,
                       done_dev ? done_dev + (size_t)k * s.N : nullptr,
-                      nullptr, nullptr, obs_dtype, do_tick, 0};
+                      nullptr, nullptr, obs_dtype, do_tick, 0, policy,
+                      actions_out ? actions_out + (size_t)k * s.N : nullptr};
             WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
             e->a_iter = it;
         }
         return WF_OK;
     }
     WarpIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0,
-              magic_for(e->st.H)};
+              magic_for(e->st.H), policy, actions_out};
     WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
     e->launches += 1;
     e->a_iter = advance_a_iter(e, k_steps);
     return WF_OK;
+}
+
+int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype,
+               double* reward_dev, uint8_t* done_dev, void* stream) {
+    return rollout_impl(e, k_steps, actions_dev, WF_POLICY_STREAM, nullptr, obs_dev, obs_dtype, reward_dev, done_dev, stream);
+}
+
+int wf_rollout_policy(wf_env* e, int32_t k_steps, int32_t policy, int32_t* actions_out_dev, void* obs_dev,
+                      int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream) {
+    return rollout_impl(e, k_steps, nullptr, policy, actions_out_dev, obs_dev, obs_dtype, reward_dev, done_dev, stream);
 }
 
 int wf_step(wf_env* e, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype, double* reward_dev,

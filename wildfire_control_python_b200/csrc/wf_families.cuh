@@ -13,6 +13,8 @@ struct WarpIO {
     const wf_init* init;     // reset mode: [N] or nullptr
     int32_t obs_dtype, K, a_iter0, reset_mode;
     uint32_t magicH;         // ceil(2^32 / H)
+    int32_t policy;          // actions == nullptr: WF_POLICY_STREAM or WF_POLICY_WALK
+    int32_t* actions_out;    // [K][N] or nullptr: the actions the policy chose
 };
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 
@@ -24,6 +26,8 @@ struct TileIO {
     const uint8_t* mask;     // reset mode
     const wf_init* init;     // reset mode
     int32_t obs_dtype, do_tick, reset_mode;
+    int32_t policy;          // actions == nullptr: WF_POLICY_STREAM or WF_POLICY_WALK
+    int32_t* actions_out;    // [N] or nullptr
 };
 struct TileState;
 int tile_extra_planes();

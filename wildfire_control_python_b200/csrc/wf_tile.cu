@@ -169,7 +169,8 @@ __device__ void flood_block(const DevState& s, const TileState& t, int env) {
 
 // ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
 // steps, Agent.is_dead (:116-120).  One thread per env.
-__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick) {
+__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick, int policy,
+                             int32_t* actions_out) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env == 0) t.counters[1] = 0;  // the reset list was drained by the previous step
     if (env >= s.N) return;
@@ -181,12 +182,35 @@ __global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* 
     int action;
     if (actions != nullptr) {
         action = actions[env];
+    } else if (policy == WF_POLICY_WALK) {  // DQN.choose_randomwalk_action, DQN.py:353-389
+        action = 0;
+        if (sc[WF_S_ALIVE]) {
+            const int mx = s.W / 2, my = s.H / 2, px = sc[WF_S_AX], py = sc[WF_S_AY];
+            int a0 = 0, a1 = 0;
+            if (px >= mx && py > my) { a0 = 1; a1 = 3; }
+            if (px > mx && py <= my) { a0 = 1; a1 = 2; }
+            if (px <= mx && py < my) { a0 = 0; a1 = 2; }
+            if (px < mx && py >= my) { a0 = 0; a1 = 3; }
+            uint32_t pw[4];
+            for (int j = 0, count = 0;; ++j) {
+                if ((j & 3) == 0)
+                    philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE],
+                                  3u * (uint32_t)sc[WF_S_T] + (uint32_t)(j >> 2), kStreamPolicy, c.key0, c.key1, pw);
+                action = (pw[j & 3] & 1u) ? a1 : a0;
+                const int nx = px + (action == 2 ? 1 : action == 3 ? -1 : 0);
+                const int ny = py + (action == 1 ? 1 : action == 0 ? -1 : 0);
+                const bool fire_at_loc = nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && get_bit(s, P_F, env, nx, ny);
+                if (!fire_at_loc || count > 10) break;
+                count++;
+            }
+        }
     } else {
         uint32_t w[4];
         const uint32_t tt = (uint32_t)sc[WF_S_T];
         philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], tt >> 2, kStreamAction, c.key0, c.key1, w);
         action = (int)(w[tt & 3u] % (uint32_t)c.n_actions);
     }
+    if (actions_out != nullptr) actions_out[env] = action;
     int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
     if (!sc[WF_S_ALIVE]) return;
     if (action >= 0 && action < 4) {
@@ -783,7 +807,7 @@ static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c,
         reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, io.init);
         *launches += 4;
     } else {
-        agent_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick);
+        agent_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick, io.policy, io.actions_out);
         flood_list_kernel<<<list_grid(s), 1024, 0, st>>>(s, *t);
         int hw_shift = -1;
         for (int k = 0; k < 16; ++k)

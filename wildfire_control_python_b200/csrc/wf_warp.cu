@@ -273,6 +273,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             int action;
             if (io.actions != nullptr) {
                 action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
+            } else if (io.policy == WF_POLICY_WALK) {
+                // DQN.choose_randomwalk_action (DQN.py:353-389): walk clockwise round the fire origin,
+                // re-draw (at most 11 times) while the move would step onto a burning cell.
+                const int mx = W / 2, my = H / 2;
+                int a0 = 0, a1 = 0;
+                if (a.ax >= mx && a.ay > my) { a0 = 1; a1 = 3; }  // ["S", "W"]
+                if (a.ax > mx && a.ay <= my) { a0 = 1; a1 = 2; }  // ["S", "E"]
+                if (a.ax <= mx && a.ay < my) { a0 = 0; a1 = 2; }  // ["N", "E"]
+                if (a.ax < mx && a.ay >= my) { a0 = 0; a1 = 3; }  // ["N", "W"]
+                bool chosen = !(act && a.alive);  // `if not self.sim.W.agents: return 0`
+                int count = 0;
+                action = 0;
+                uint32_t pw[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 12; ++j) {
+                    if ((j & 3) == 0)
+                        philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, 3u * a.t + (uint32_t)(j >> 2), kStreamPolicy,
+                                      c.key0, c.key1, pw);
+                    const uint32_t u = (j & 3) == 0 ? pw[0] : (j & 3) == 1 ? pw[1] : (j & 3) == 2 ? pw[2] : pw[3];
+                    const int cand = (u & 1u) ? a1 : a0;
+                    const int nx = a.ax + (cand == 2 ? 1 : cand == 3 ? -1 : 0);
+                    const int ny = a.ay + (cand == 1 ? 1 : cand == 0 ? -1 : 0);
+                    const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
+                    const uint32_t frow = __shfl_sync(FULL, r.F, sub * L + (inb ? nx : 0));
+                    if (!chosen) {
+                        action = cand;
+                        const bool fire_at_loc = inb && ((frow >> ny) & 1u);  // Agent.fire_in_direction :158-160
+                        if (!fire_at_loc || count > 10) chosen = true;
+                        else count++;
+                    }
+                    if (__all_sync(FULL, chosen)) break;
+                }
             } else {
                 // one Philox block serves 4 consecutive steps of an episode
                 if ((a.t & 3u) == 0u || ablk_ep != a.episode || ablk_idx != (a.t >> 2)) {
@@ -283,6 +314,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                 const uint32_t aw = (a.t & 3u) == 0u ? ablk[0] : (a.t & 3u) == 1u ? ablk[1] : (a.t & 3u) == 2u ? ablk[2] : ablk[3];
                 action = (int)(aw % (uint32_t)c.n_actions);
             }
+            if (io.actions_out != nullptr && valid_env && x == 0) io.actions_out[(size_t)k * s.N + env] = action;
             // ---- action: Agent.move :141-155 / toggle_digging :136-138 (agents[0] exists while alive)
             {
                 const bool mv = act && a.alive && action >= 0 && action < 4;
