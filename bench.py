@@ -191,28 +191,13 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, no_graph: bool,
     chunk = max(1, min(chunk_arg or wl["chunk"], K))
     env = BatchedForestFire(N, device=dev, auto_reset=True, seed=0, env_id_base=rank * N, **wl["meta"])
     env.reset()
-    fused = env.kernel_family == "warp"
+    fused = True  # warp family: state in registers across the launch; tile family: one cluster per env, K steps per launch
     obs_buf = torch.empty((chunk, N, W, H, 3), dtype=torch.uint8, device=dev)
     rew_buf = torch.empty((chunk, N), dtype=torch.float64, device=dev)
     done_buf = torch.empty((chunk, N), dtype=torch.uint8, device=dev)
     out = (obs_buf, rew_buf, done_buf)
 
-    graph, launches_per_chunk = None, 0
-    if not fused and K >= chunk and chunk % 2 == 0 and not no_graph:
-        # Tile family: one step is 5-7 dependent launches.  Capture a `chunk`-step rollout (ACTION-stream
-        # actions: no action tensor is baked in) into a CUDA graph and replay it; an even number of ticks
-        # per replay keeps the library's source-mask ping-pong parity consistent across replays.
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            env.rollout(chunk, actions=None, out=out)
-            l0 = env.launch_count
-            env.rollout(chunk, actions=None, out=out)
-            launches_per_chunk = env.launch_count - l0
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                env.rollout(chunk, actions=None, out=out)
-        torch.cuda.current_stream(dev).wait_stream(side)
+    graph, launches_per_chunk = None, 0  # both families run `chunk` steps per launch: nothing to capture
     replays = [0]
 
     def run_steps(n_steps):
@@ -367,15 +352,16 @@ def roofline_of(res, world):
     N, W, H, fused = res["N"], res["W"], res["H"], res["fused"]
     per_gpu_steps = res["value"] / world
     achieved = per_gpu_steps * W * H * BYTES_PER_CELL_UPDATE / 1e9
-    if fused:  # state stays in registers across a launch: only outputs (+ state once per launch) touch HBM
+    if res["family"] == "warp":  # state stays in registers across a launch: only outputs (+ state once per launch) touch HBM
         own = W * H * 3 + 8 + 1 + 2 * 1616 / res["chunk"]
         kernel = "wf::warp_kernel"
         note = ("c2 state (4096 envs x 1.6 KB) lives in registers/L2: this kernel is issue/latency-bound "
                 "(ncu: DRAM 7 %, issue slots 52 %); the HBM roofline is reported because the contract asks for it")
-    else:  # dense pass: 3 plane words read (G, B, S) + S_next per 32 cells in the tick, 2 words + 96 B out in obs
+    else:  # dense pass per step: G, B, S read + S_next written (tick), F, I read + 96 B written (observation) per 32 cells
         own = W * H * (3 * 4 / 32 + 4 / 32 + 2 * 4 / 32 + 3)
-        kernel = "wf::tile_tick_kernel + wf::obs_kernel"
-        note = "HBM-bound pair; fuel planes / hit counters are touched only where the fire front is"
+        kernel = "wf::tile_rollout_kernel"
+        note = ("HBM-bound: one cluster per env streams 6 plane words + 96 B of observation per 32 cells and step; "
+                "fuel planes / hit counters are touched only where the fire front is")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
@@ -423,7 +409,7 @@ def run_ours(args, wl):
                    "steps_per_launch": res["chunk"] if res["fused"] else None,
                    "steps_per_graph_replay": res["chunk"] if res["graph"] else None, "kernel_family": res["family"],
                    "l2": f"outputs of one launch/replay ({res['obs_mb']:.0f} MB obs) exceed the 126 MB L2; "
-                         + ("state is register/L2 resident by design" if res["fused"] else "state (385 MB) exceeds L2 too")},
+                         + ("state is register/L2 resident by design" if res["family"] == "warp" else "state (385 MB) exceeds L2 too")},
         "cell_updates_per_sec": res["value"] * W * H,
         "cell_updates_per_sec_per_gpu": res["value"] * W * H / world,
         "e2e": res.get("e2e"), "per_step_launch": res.get("per_step"),

@@ -298,3 +298,35 @@ def test_trajectories_do_not_depend_on_sharding():
     assert torch.equal(dw[:, :16], dl) and torch.equal(dw[:, 16:], dh)
     a, b, c = whole.stats(), lo.stats(), hi.stats()
     assert all(a[k] == b[k] + c[k] for k in a)
+
+
+@pytest.mark.parametrize("T,CS", [(128, 1), (128, 2), (256, 4), (128, 8), (512, 2)])
+@pytest.mark.parametrize("cfg", [dict(width=64, height=64, seed=701, make_rivers=True, wind="random", extra_ignitions=3),
+                                 dict(width=100, height=70, seed=702, wind=[0.85, (1, 0)], extra_ignitions=6, a_speed=2),
+                                 dict(width=128, height=128, seed=703, allow_dig_toggle=True, n_actions=6, extra_ignitions=4)],
+                         ids=["64_rivers", "100x70_aspeed2", "128_toggle"])
+def test_tile_cluster_geometries_match_oracle(monkeypatch, T, CS, cfg):
+    """The tile family splits one env over a thread-block cluster of CS CTAs x T threads (chosen from
+    the batch size in production): every split must give the oracle's trajectory -- walk-policy
+    rollout with auto-reset (containments, re-floods of the reach plane, in-kernel resets)."""
+    monkeypatch.setenv("WF_TILE_T", str(T))
+    monkeypatch.setenv("WF_TILE_CS", str(CS))
+    N, K = 5, 150
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    obs0 = gpu.reset()
+    for e in orc:
+        e.reset()
+    compare_states("reset", gpu, orc, obs=obs0)
+    for policy in ("walk", "stream"):
+        obs, rew, done, acts = gpu.rollout(K, policy=policy, return_actions=True)
+        obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+        for i, e in enumerate(orc):
+            for k in range(K):
+                a = e.walk_action() if policy == "walk" else e.random_action()
+                assert acts[k, i] == a, f"{policy} env {i} step {k}: action"
+                o, r, d, _ = e.step(a)
+                assert rew[k, i] == r and bool(done[k, i]) == d, f"{policy} env {i} step {k}: reward/done {rew[k, i]} {r}"
+                if d:
+                    o = e.reset()
+                assert np.array_equal(obs[k, i], o), f"{policy} env {i} step {k}: obs"
+        compare_states(f"after {policy} rollout", gpu, orc)

@@ -330,7 +330,7 @@ int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* 
     WF_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (e->tile) {
-        TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, 1, 0, nullptr};
+        TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, e->a_iter, 1, 0, nullptr};
         WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
     } else {
         WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H), 0, nullptr};
@@ -357,22 +357,11 @@ static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, 
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (e->tile) {
-        const DevState& s = e->st;
-        const size_t esz = (size_t)s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
-        for (int k = 0; k < k_steps; ++k) {  // tile family: one tick per launch group
-            int it = e->a_iter - 1;
-            const int do_tick = (it == 0);
-            if (do_tick) it = e->cfg.a_speed;
-            TileIO io{actions_dev ? actions_dev + (size_t)k * s.N : nullptr,
-                      obs_dev ? static_cast<char*>(obs_dev) + (size_t)k * s.N * esz : nullptr,
-                      reward_dev ? reward_dev + (size_t)k * s.N : nullptr,
-                      done_dev ? done_dev + (size_t)k * s.N : nullptr,
-                      nullptr, nullptr, obs_dtype, do_tick, 0, policy,
-                      actions_out ? actions_out + (size_t)k * s.N : nullptr};
-            WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
-            e->a_iter = it;
-        }
+    if (e->tile) {  // one thread-block cluster per env runs all K steps in one launch
+        TileIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0, policy,
+                  actions_out};
+        WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
+        e->a_iter = advance_a_iter(e, k_steps);
         return WF_OK;
     }
     WarpIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0,

@@ -19,15 +19,15 @@ struct WarpIO {
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 
 struct TileIO {
-    const int32_t* actions;  // [N]
-    void* obs;               // [N][W][H][3] or nullptr
-    double* reward;          // [N] or nullptr
-    uint8_t* done;           // [N] or nullptr
-    const uint8_t* mask;     // reset mode
-    const wf_init* init;     // reset mode
-    int32_t obs_dtype, do_tick, reset_mode;
+    const int32_t* actions;  // [K][N] or nullptr (ACTION stream / policy)
+    void* obs;               // [K][N][W][H][3] or nullptr
+    double* reward;          // [K][N] or nullptr
+    uint8_t* done;           // [K][N] or nullptr
+    const uint8_t* mask;     // reset mode: [N] or nullptr
+    const wf_init* init;     // reset mode: [N] or nullptr
+    int32_t obs_dtype, K, a_iter0, reset_mode;
     int32_t policy;          // actions == nullptr: WF_POLICY_STREAM or WF_POLICY_WALK
-    int32_t* actions_out;    // [N] or nullptr
+    int32_t* actions_out;    // [K][N] or nullptr
 };
 struct TileState;
 int tile_extra_planes();

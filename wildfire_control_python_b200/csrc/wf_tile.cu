@@ -1,46 +1,101 @@
 // wf_tile.cu -- "tile" kernel family: grids wider or taller than 32 cells (256x256, 1024x1024 ...).
 //
 // Same bit-plane state as the warp family (wf_common.cuh) but resident in HBM: a row x of H cells is
-// HW = ceil(H/32) words, one thread owns one word (32 cells) per tick.  Per tick a word reads
-//   * the heat-source mask S (1 bit/cell: burning and fuel >= 2) of itself and its 4 neighbours,
-//   * its grass / fire / burning / fm_inf words,
-// and ONLY IF it burns or receives heat the fuel planes and the hit counters of the heated cells.
-// It writes the next source mask (ping-pong), whatever changed, and 96 bytes of observation.
-// The per-burning-cell Python loop (forest_fire.py:85-106) is boolean algebra on words; the A*
-// containment search (environment.py:342-377) is a persistent "reach" plane R (cells with a finite
-// 4-connected path to a finite border point) that is re-flooded only when a dig may disconnect it.
+// HW = ceil(H/32) words.  ONE thread-block cluster (1..8 CTAs, chosen so that all envs together fill
+// the 148 SMs) owns one environment for a whole K-step rollout; CTA r of the cluster owns the r-th
+// contiguous slice of the env's words.  Everything the reference does in ForestFire.step happens in
+// this one kernel, per step:
 //
-// One step = agent_kernel (1 thread/env: move/dig/reap + local articulation test; envs whose reach
-//                          plane may have been disconnected by the dig are appended to a work list)
-//          -> flood_list_kernel (persistent CTAs drain the list: re-flood R; usually the list is empty)
-//          -> tile_tick_kernel (the stencil: fuel, heat, ignition, per-env reductions)
-//          -> finish_kernel (1 thread/env: reward/done/latch; finished envs go to the reset list)
-//          -> reset_list_kernel (persistent CTAs drain the list: World.reset; usually empty)
-//          -> obs_kernel  (World.get_state of every env: 2 bits/cell in, 3 bytes/cell out)
+//   agent phase   thread 0 of every CTA (redundantly, from identical inputs): action, Agent.move /
+//                 toggle_digging / is_dead (environment.py:116-171), local articulation test for the
+//                 reach plane.  Reads only; the dig is applied by the thread that owns the word.
+//   barrier X     (cluster)  nobody writes a plane before everybody has read the agent's surroundings
+//   tick          stream G, B and the heat-source mask S (1 bit/cell: burning and fuel >= 2) of the
+//                 slice; words that burn or are heated are queued in shared memory and handed one per
+//                 thread to the active path (fuel planes, hit counters, ignition, burn-out --
+//                 forest_fire.py:85-106, environment.py:278-307); S is ping-ponged so the in-place
+//                 update of every other plane is race-free across CTAs.
+//   barrier Y     (cluster)  per-env reductions exchanged through distributed shared memory
+//   finish        RUNNING, World.get_reward (environment.py:342-390: containment = no burning cell in
+//                 or next to the border-connected reach plane R), done, statistics; auto-reset
+//   observation   World.get_state (environment.py:399-402): 2 plane words in, 96 bytes out per word
+//
+// The A* containment search (pyastar/astar.cpp) is the persistent reach plane R (cells with a finite
+// 4-connected path to a finite border point), re-flooded by the cluster only when a dig may disconnect it.
+#include <cstdlib>
+
 #include "wf_families.cuh"
 
 namespace wf {
 
-constexpr int kTileThreads = 256;
-
 struct TileState {
-    int32_t* acc;         // [N][4]: burning cells, grass cells, ignition-on-edge flag, burning-touches-reach flag
-    int32_t* need_flood;  // [N] flag: R of this env must be re-flooded
-    int32_t* flood_list;  // [N] env ids appended by agent_kernel, + counter
-    int32_t* reset_list;  // [N] env ids appended by finish_kernel / mask_to_list_kernel, + counter
-    int32_t* counters;    // [0] = flood_list length, [1] = reset_list length
-    int32_t cur;          // which of the two S planes holds the sources of the NEXT tick
     int32_t P_S0, P_S1, P_R;
-    int32_t flood_smem_ok;
+    int32_t T, CS;  // threads per CTA, CTAs per cluster (one cluster per env)
+};
+
+struct TilePar {  // launch constants, precomputed on the host so the kernel re-reads them from the constant bank
+    int32_t P_S0, P_S1, P_R, hw_shift;
+    uint32_t hw_magic;   // ceil(2^32 / HW): row = umulhi(word, hw_magic) when HW is not a power of two
+    int32_t wpc;         // words of an env owned by one CTA (multiple of 32)
+    int32_t T;           // threads per CTA
+    int32_t nwords;      // W * HW
+    int32_t cells;       // W * H
+    size_t pstride;      // words between consecutive planes (N * RS * HW)
+    size_t env_words;    // words between consecutive envs within a plane (RS * HW)
+    size_t step_bytes;   // bytes of one step's observation block [N][W][H][3]
+};
+
+// Block-wide scratch of the env a CTA is working on (every CTA of the cluster holds the same values).
+struct StepShared {
+    int32_t act;          // env was running at step start (finished envs are frozen)
+    int32_t dig_word;     // word index of the cell dug this step, or -1
+    uint32_t dig_bit;
+    int32_t dig_clear_R;  // the dug cell leaves the reach plane
+    int32_t need_flood;   // ... and may disconnect it: re-flood before the tick
+    int32_t tot[4];       // cluster totals: burning cells, grass cells, ignition on edge, burning touches reach
+    int32_t reset_now;
+    int32_t obs_vis, obs_ax, obs_ay;  // agent_pos layer of the observation being emitted
 };
 
 int tile_extra_planes() { return 3; }
 
+// ---------------------------------------------------------------------------------------------
+// cluster primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {  // release/acquire at cluster scope (also orders global memory)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_cluster(int* local_ptr, uint32_t peer, int v) {  // DSMEM store
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(peer));
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+template <bool CL>
+__device__ __forceinline__ void sync_env() {
+    if (CL) cluster_barrier();
+    else __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t valid_word(int H, int w) {
     const int rem = H - 32 * w;
     return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 }
-
 // Literal border_points (environment.py:215-222): (x,0) (x,H-1) for all x; (0,y) (H-1,y) for all y.
 __device__ __forceinline__ uint32_t seed_word(int W, int H, int x, int w) {
     const uint32_t v = valid_word(H, w);
@@ -59,95 +114,64 @@ __device__ __forceinline__ uint32_t edge_word(int W, int H, int x, int w) {
     return m & v;
 }
 
-__device__ __forceinline__ uint32_t& plane_word(const DevState& s, int p, int env, int x, int w) {
-    return s.planes[word_index(s, p, env, x, w)];
-}
-__device__ __forceinline__ bool get_bit(const DevState& s, int p, int env, int x, int y) {
-    return (s.planes[word_index(s, p, env, x, y >> 5)] >> (y & 31)) & 1u;
-}
+// Everything a device function needs to address the env this CTA works on.
+struct Env {
+    uint32_t* P0;    // word 0 of plane 0 of this env
+    size_t pstride;  // words between consecutive planes
+    uint32_t* hits;  // hit counters of this env
+    int env, W, H, HW, nwords, hw_shift;
+    uint32_t hw_magic;
+    int lo, hi;      // this CTA's slice of the env's words
+    int rank, CS, tid, T;
+    __device__ __forceinline__ uint32_t* plane(int p) const { return P0 + (size_t)p * pstride; }
+    __device__ __forceinline__ int row_of(int i) const {
+        return hw_shift >= 0 ? (i >> hw_shift) : (int)__umulhi((uint32_t)i, hw_magic);
+    }
+    __device__ __forceinline__ bool bit(int p, int x, int y) const {
+        return (plane(p)[x * HW + (y >> 5)] >> (y & 31)) & 1u;
+    }
+};
 
-// Agent.dig (environment.py:123-133) on planes in HBM + incremental maintenance of the reach plane.
-__device__ void tile_dig(const DevState& s, const TileState& t, int env, int x, int y, const int32_t* sc) {
-    const int w = y >> 5;
-    const uint32_t bit = 1u << (y & 31);
-    uint32_t& D = plane_word(s, P_D, env, x, w);
-    if (D & bit) return;
-    plane_word(s, P_G, env, x, w) &= ~bit;
-    plane_word(s, P_F, env, x, w) &= ~bit;
-    plane_word(s, P_BT, env, x, w) &= ~bit;
-    plane_word(s, P_WT, env, x, w) &= ~bit;
-    D |= bit;
-    uint32_t& I = plane_word(s, P_I, env, x, w);
-    const bool was_free = !(I & bit);
-    I |= bit;
-    if (!was_free) return;
-    // get_reward only searches for a path while `not fire_at_border and len(border_points)`
-    // (environment.py:345): once either latch is set R is never read again in this episode
-    // (World.reset re-floods it), so it is not maintained.
-    if (sc[WF_S_FIRE_AT_BORDER] || sc[WF_S_LATCHED]) return;
-    uint32_t& R = plane_word(s, t.P_R, env, x, w);
-    if (!(R & bit)) return;  // the cell had no path to the border: nobody reached the border through it
-    R &= ~bit;
-    // Does removing this cell possibly disconnect its neighbours from the border?  Its free 4-neighbours
-    // were all in R.  If they stay connected to each other through the ring of 8 surrounding cells,
-    // every path through the dug cell can be re-routed and R is unchanged elsewhere ("simple point").
-    const int W = s.W, H = s.H;
-    const bool on_seed = (x == 0 || x == H - 1 || y == 0 || y == H - 1);
-    bool f[8];  // N, NE, E, SE, S, SW, W, NW  (screen coordinates: N = y-1, E = x+1)
-    const int dx[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int nx = x + dx[k], ny = y + dy[k];
-        f[k] = (nx >= 0 && nx < W && ny >= 0 && ny < H) && !get_bit(s, P_I, env, nx, ny);
+// Sum the CTAs' partial reductions red[0..3] over the cluster into ss.tot[0..3] (and clear red).
+// Call with red[] complete (after a __syncthreads); returns with ss.tot visible to the whole CTA.
+template <bool CL>
+__device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[8][4], int& par, StepShared& ss) {
+    if (CL) {
+        if (e.tid < 4 * e.CS) st_shared_cluster(&xch[par][e.rank][e.tid & 3], (uint32_t)(e.tid >> 2), red[e.tid & 3]);
+        cluster_barrier();
+        if (e.tid < 4) {
+            int v = 0;
+            for (int r = 0; r < e.CS; ++r) v += xch[par][r][e.tid];
+            ss.tot[e.tid] = v;
+            red[e.tid] = 0;
+        }
+        par ^= 1;
+    } else {
+        if (e.tid < 4) {
+            ss.tot[e.tid] = red[e.tid];
+            red[e.tid] = 0;
+        }
     }
-    int n4 = 0, groups = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-        if (!f[k]) continue;
-        n4++;
-        // this 4-neighbour starts a new group unless it is ring-connected to the previous 4-neighbour
-        const int pk = (k + 6) & 7, pd = (k + 7) & 7;
-        if (!(f[pk] && f[pd])) groups++;
-    }
-    if (n4 == 4 && groups == 0) groups = 1;  // full ring
-    if ((on_seed ? n4 > 0 : groups > 1) && !t.need_flood[env]) {
-        t.need_flood[env] = 1;
-        t.flood_list[atomicAdd(&t.counters[0], 1)] = env;
-    }
-}
-
-// World.set_fire_to (environment.py:233-246) on planes in HBM (keeps the source mask consistent).
-__device__ void tile_set_fire(const DevState& s, const TileState& t, int env, int x, int y, int32_t* sc) {
-    const int w = y >> 5;
-    const uint32_t bit = 1u << (y & 31);
-    plane_word(s, P_G, env, x, w) &= ~bit;
-    plane_word(s, P_BT, env, x, w) &= ~bit;
-    plane_word(s, P_D, env, x, w) &= ~bit;
-    plane_word(s, P_WT, env, x, w) &= ~bit;
-    plane_word(s, P_F, env, x, w) |= bit;
-    plane_word(s, P_B, env, x, w) |= bit;
-    uint32_t ge2 = 0u;
-    for (int q = 1; q < s.FB; ++q) ge2 |= plane_word(s, P_FU0 + q, env, x, w);
-    if (ge2 & bit) plane_word(s, t.cur ? t.P_S1 : t.P_S0, env, x, w) |= bit;
-    if (x == 0 || x == s.W - 1 || y == 0 || y == s.H - 1) sc[WF_S_FIRE_AT_BORDER] = 1;
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
 // Reach plane: R = finite cells 4-connected to a finite border point (flood from the border over
-// ~fm_inf).  Whole CTA; in-place monotone relaxation until a full sweep changes nothing.
-__device__ void flood_block(const DevState& s, const TileState& t, int env) {
-    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    uint32_t* R = &plane_word(s, t.P_R, env, 0, 0);
-    const uint32_t* I = &plane_word(s, P_I, env, 0, 0);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-        const int x = i / HW, w = i - x * HW;
+// ~fm_inf).  Whole cluster; in-place monotone relaxation until a full sweep changes nothing anywhere.
+template <bool CL>
+__device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[8][4], int& par, StepShared& ss) {
+    const int W = e.W, H = e.H, HW = e.HW;
+    uint32_t* R = e.plane(t.P_R);
+    const uint32_t* I = e.plane(P_I);
+    for (int i = e.lo + e.tid; i < e.hi; i += e.T) {
+        const int x = e.row_of(i), w = i - x * HW;
         R[i] = seed_word(W, H, x, w) & ~I[i];
     }
-    __syncthreads();
+    sync_env<CL>();
     for (;;) {
         int changed = 0;
-        for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-            const int x = i / HW, w = i - x * HW;
+        for (int i = e.lo + e.tid; i < e.hi; i += e.T) {
+            const int x = e.row_of(i), w = i - x * HW;
             const uint32_t free_ = ~I[i] & valid_word(H, w);
             if (!free_) continue;
             const uint32_t old = R[i];
@@ -162,30 +186,87 @@ __device__ void flood_block(const DevState& s, const TileState& t, int env) {
                 changed = 1;
             }
         }
-        if (!__syncthreads_or(changed)) break;
+        if (changed) red[0] = 1;
+        __syncthreads();
+        exchange<CL>(e, red, xch, par, ss);
+        if (!ss.tot[0]) break;
     }
-    if (threadIdx.x == 0) t.need_flood[env] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Agent.dig (environment.py:123-133), planning half: what the dig changes and whether the reach plane
+// survives it.  Thread 0 only, reads only.  Returns true iff the cell becomes dirt now.
+__device__ bool plan_dig(const Env& e, const TilePar& t, const int32_t* sc, StepShared& ss, int x, int y) {
+    const int W = e.W, H = e.H;
+    const int wi = x * e.HW + (y >> 5);
+    const uint32_t bit = 1u << (y & 31);
+    const uint32_t Dw = e.plane(P_D)[wi], Iw = e.plane(P_I)[wi], Rw = e.plane(t.P_R)[wi];
+    bool f[8];  // free neighbours N, NE, E, SE, S, SW, W, NW  (screen coordinates: N = y-1, E = x+1)
+    const int dx[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int nx = x + dx[k], ny = y + dy[k];
+        const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
+        f[k] = inb && !e.bit(P_I, inb ? nx : x, inb ? ny : y);
+    }
+    if (Dw & bit) return false;
+    ss.dig_word = wi;
+    ss.dig_bit = bit;
+    if (Iw & bit) return true;  // the cell already had infinite fire mobility (water is never entered; kept for safety)
+    // get_reward only searches for a path while `not fire_at_border and len(border_points)`
+    // (environment.py:345): once either latch is set R is never read again in this episode
+    // (World.reset re-floods it), so it is not maintained.
+    if (sc[WF_S_FIRE_AT_BORDER] || sc[WF_S_LATCHED]) return true;
+    if (!(Rw & bit)) return true;  // the cell had no path to the border: nobody reached the border through it
+    ss.dig_clear_R = 1;
+    // Does removing this cell possibly disconnect its neighbours from the border?  Its free 4-neighbours
+    // were all in R.  If they stay connected to each other through the ring of 8 surrounding cells,
+    // every path through the dug cell can be re-routed and R is unchanged elsewhere ("simple point").
+    const bool on_seed = (x == 0 || x == H - 1 || y == 0 || y == H - 1);
+    int n4 = 0, groups = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        if (!f[k]) continue;
+        n4++;
+        // this 4-neighbour starts a new group unless it is ring-connected to the previous 4-neighbour
+        const int pk = (k + 6) & 7, pd = (k + 7) & 7;
+        if (!(f[pk] && f[pd])) groups++;
+    }
+    if (n4 == 4 && groups == 0) groups = 1;  // full ring
+    if (on_seed ? n4 > 0 : groups > 1) ss.need_flood = 1;
+    return true;
+}
+
+// The planned dig, applied to the planes in HBM (by the one thread that owns the word).
+__device__ __forceinline__ void apply_dig(const Env& e, const TilePar& t, int wi, uint32_t bit, int clear_R) {
+    atomicAnd(&e.plane(P_G)[wi], ~bit);
+    atomicAnd(&e.plane(P_F)[wi], ~bit);
+    atomicAnd(&e.plane(P_BT)[wi], ~bit);
+    atomicAnd(&e.plane(P_WT)[wi], ~bit);
+    atomicOr(&e.plane(P_D)[wi], bit);
+    atomicOr(&e.plane(P_I)[wi], bit);
+    if (clear_R) atomicAnd(&e.plane(t.P_R)[wi], ~bit);
 }
 
 // ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
-// steps, Agent.is_dead (:116-120).  One thread per env.
-__global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* actions, int do_tick, int policy,
-                             int32_t* actions_out) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env == 0) t.counters[1] = 0;  // the reset list was drained by the previous step
-    if (env >= s.N) return;
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    int32_t* acc = t.acc + 4 * env;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0;
-    sc[WF_S_RESERVED] = sc[WF_S_RUNNING];  // "act": was running at step start (finished envs are frozen)
+// steps, Agent.is_dead (:116-120).  Thread 0 of every CTA computes the same thing; only `writer`
+// (cluster rank 0) touches global memory.
+__device__ void agent_phase(const Env& e, const StepCfg& c, const TilePar& t, const TileIO& io, const DevState& s, int k,
+                            int do_tick, int32_t* sc, StepShared& ss, bool writer) {
+    ss.act = sc[WF_S_RUNNING];
+    ss.dig_word = -1;
+    ss.dig_bit = 0u;
+    ss.dig_clear_R = 0;
+    ss.need_flood = 0;
     if (!sc[WF_S_RUNNING]) return;
+    const int W = e.W, H = e.H;
     int action;
-    if (actions != nullptr) {
-        action = actions[env];
-    } else if (policy == WF_POLICY_WALK) {  // DQN.choose_randomwalk_action, DQN.py:353-389
+    if (io.actions != nullptr) {
+        action = io.actions[(size_t)k * s.N + e.env];
+    } else if (io.policy == WF_POLICY_WALK) {  // DQN.choose_randomwalk_action, DQN.py:353-389
         action = 0;
         if (sc[WF_S_ALIVE]) {
-            const int mx = s.W / 2, my = s.H / 2, px = sc[WF_S_AX], py = sc[WF_S_AY];
+            const int mx = W / 2, my = H / 2, px = sc[WF_S_AX], py = sc[WF_S_AY];
             int a0 = 0, a1 = 0;
             if (px >= mx && py > my) { a0 = 1; a1 = 3; }
             if (px > mx && py <= my) { a0 = 1; a1 = 2; }
@@ -194,12 +275,12 @@ __global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* 
             uint32_t pw[4];
             for (int j = 0, count = 0;; ++j) {
                 if ((j & 3) == 0)
-                    philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE],
+                    philox4x32_10((uint32_t)(c.env_id_base + e.env), (uint32_t)sc[WF_S_EPISODE],
                                   3u * (uint32_t)sc[WF_S_T] + (uint32_t)(j >> 2), kStreamPolicy, c.key0, c.key1, pw);
                 action = (pw[j & 3] & 1u) ? a1 : a0;
                 const int nx = px + (action == 2 ? 1 : action == 3 ? -1 : 0);
                 const int ny = py + (action == 1 ? 1 : action == 0 ? -1 : 0);
-                const bool fire_at_loc = nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && get_bit(s, P_F, env, nx, ny);
+                const bool fire_at_loc = nx >= 0 && nx < W && ny >= 0 && ny < H && e.bit(P_F, nx, ny);
                 if (!fire_at_loc || count > 10) break;
                 count++;
             }
@@ -207,41 +288,35 @@ __global__ void agent_kernel(DevState s, StepCfg c, TileState t, const int32_t* 
     } else {
         uint32_t w[4];
         const uint32_t tt = (uint32_t)sc[WF_S_T];
-        philox4x32_10((uint32_t)(c.env_id_base + env), (uint32_t)sc[WF_S_EPISODE], tt >> 2, kStreamAction, c.key0, c.key1, w);
+        philox4x32_10((uint32_t)(c.env_id_base + e.env), (uint32_t)sc[WF_S_EPISODE], tt >> 2, kStreamAction, c.key0, c.key1, w);
         action = (int)(w[tt & 3u] % (uint32_t)c.n_actions);
     }
-    if (actions_out != nullptr) actions_out[env] = action;
-    int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
+    if (writer && io.actions_out != nullptr) io.actions_out[(size_t)k * s.N + e.env] = action;
     if (!sc[WF_S_ALIVE]) return;
+    int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
+    bool on_fire_now = e.bit(P_F, ax, ay);  // type == fire under the agent (pre-move cell)
     if (action >= 0 && action < 4) {
         sc[WF_S_VISIBLE] = 0;  // Q1
         const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
         const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
-        if (nx >= 0 && nx < s.W && ny >= 0 && ny < s.H && !get_bit(s, P_WT, env, nx, ny)) {
+        const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
+        if (inb && !e.bit(P_WT, nx, ny)) {
             ax = nx; ay = ny;
             sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
-            const bool onfire = get_bit(s, P_F, env, nx, ny);
-            if (sc[WF_S_DIGGING] && !onfire) tile_dig(s, t, env, nx, ny, sc);
+            const bool onfire = e.bit(P_F, nx, ny);
+            on_fire_now = onfire;
+            if (sc[WF_S_DIGGING] && !onfire) plan_dig(e, t, sc, ss, nx, ny);
             if (onfire) sc[WF_S_DEAD] = 1;
         }
     }
     if (c.allow_dig_toggle && action == 4) {
         sc[WF_S_DIGGING] ^= 1;
-        if (sc[WF_S_DIGGING]) tile_dig(s, t, env, ax, ay, sc);
+        if (sc[WF_S_DIGGING] && plan_dig(e, t, sc, ss, ax, ay)) on_fire_now = false;  // dig makes the cell dirt (Q7)
     }
-    if (do_tick && (sc[WF_S_DEAD] || get_bit(s, P_F, env, ax, ay))) {
+    if (do_tick && (sc[WF_S_DEAD] || on_fire_now)) {
         sc[WF_S_VISIBLE] = 0;
         sc[WF_S_ALIVE] = 0;
-        atomicAdd(&s.stats[ST_DEATHS], 1ull);
-    }
-}
-
-// Persistent CTAs drain the flood list (empty on most steps).
-__global__ void __launch_bounds__(1024) flood_list_kernel(DevState s, TileState t) {
-    const int n = t.counters[0];
-    for (int k = blockIdx.x; k < n; k += gridDim.x) {
-        flood_block(s, t, t.flood_list[k]);
-        __syncthreads();
+        if (writer) atomicAdd(&s.stats[ST_DEATHS], 1ull);
     }
 }
 
@@ -334,279 +409,273 @@ __device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride
     return B & ge2;  // sources of the next tick: burning with fuel >= 2
 }
 
-// does a burning cell of this word sit in, or next to, the border-connected region R?
-__device__ __forceinline__ bool touches_reach(const uint32_t* R, uint32_t B, int x, int w, int W, int HW) {
-    uint32_t near = R[0];
+// Does a burning cell of word `wi` sit in, or next to, the border-connected region R?  Words of other
+// CTAs' slices may not show this step's dig yet: the dug cell is masked out here (digw, digclr).
+__device__ __forceinline__ bool touches_reach(const uint32_t* R, int wi, uint32_t B, int x, int w, int W, int HW, int digw,
+                                              uint32_t digclr) {
+    auto ld = [&](int j) -> uint32_t {
+        const uint32_t v = R[j];
+        return j == digw ? (v & ~digclr) : v;
+    };
+    uint32_t near = ld(wi);
     near |= (near << 1) | (near >> 1);
-    if (x > 0) near |= R[-HW];
-    if (x < W - 1) near |= R[HW];
-    if (w > 0) near |= R[-1] >> 31;
-    if (w < HW - 1) near |= R[1] << 31;
+    if (x > 0) near |= ld(wi - HW);
+    if (x < W - 1) near |= ld(wi + HW);
+    if (w > 0) near |= ld(wi - 1) >> 31;
+    if (w < HW - 1) near |= ld(wi + 1) << 31;
     return (B & near) != 0u;
 }
 
-// VW = words per thread along y in the streaming phase: 4 (128-bit loads; needs HW % 4 == 0) or 1.
-// Phase 1 streams G, B and the source mask of every word and queues the ACTIVE words (burning or
-// heated) of the CTA in shared memory; phase 2 hands one queued word to each thread, so the
-// dependent loads of the active path (fuel planes, hit counters) run at full occupancy instead of
-// serially inside the few threads that happen to own a fire front.
+// One tick (or, on non-tick steps, just the per-env counts) over this CTA's slice.  Leaves the CTA's
+// partial reductions in red[0..3]; the caller synchronises.
+// VW = words per thread and batch along y: 4 (128-bit loads; needs HW % 4 == 0) or 1.
 template <int FB, int VW>
-__global__ void __launch_bounds__(kTileThreads) tile_tick_kernel(DevState s, StepCfg c, TileState t, int do_tick,
-                                                                 int hw_shift) {
-    constexpr int QCAP = kTileThreads * VW;
-    __shared__ int red[4];
-    __shared__ int q_n;
-    __shared__ uint32_t q_idx[QCAP], q_G[QCAP], q_B[QCAP], q_h[4][QCAP];
-    const int env = blockIdx.y;
-    if (threadIdx.x < 4) red[threadIdx.x] = 0;
-    if (threadIdx.x == 0) q_n = 0;
-    __syncthreads();
-    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VW;  // first word of this thread
-    const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const bool act = sc[WF_S_RESERVED] != 0;
+__device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, const StepCfg& c, const TilePar& t,
+                                           const int32_t* sc, const StepShared& ss, bool ticking, int digw, int* red,
+                                           int* q_n, uint32_t* qmem) {
+    const int W = e.W, H = e.H, HW = e.HW, T = e.T, tid = e.tid;
+    const int QCAP = T * VW;
+    uint32_t* const q_idx = qmem;
+    uint32_t* const q_G = qmem + QCAP;
+    uint32_t* const q_B = qmem + 2 * QCAP;
+    uint32_t* const q_h = qmem + 3 * QCAP;  // [4][QCAP]
+    const size_t pstride = e.pstride;
     const bool want_touch = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED];
-    const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    uint32_t* const P0 = s.planes + word_index(s, 0, env, 0, 0);
-    const int scur = t.cur ? t.P_S1 : t.P_S0, snxt = t.cur ? t.P_S0 : t.P_S1;
+    const int cur = sc[WF_S_RESERVED] & 1;
+    const int scur = cur ? t.P_S1 : t.P_S0, snxt = cur ? t.P_S0 : t.P_S1;
+    const uint32_t digclr = ss.dig_clear_R ? ss.dig_bit : 0u;
+    const int digw_R = ss.dig_word;  // R is patched in registers even after a re-flood (harmless: the bit is clear)
+    const uint32_t* const Rp = e.plane(t.P_R);
+    const int wid = sc[WF_S_WIND_ID];
+    const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
     int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
-    if (i < nwords) {
-        const int x = hw_shift >= 0 ? (i >> hw_shift) : (i / HW);
-        const int w0 = i - x * HW;
-        uint32_t* P = P0 + i;
-        uint32_t G[VW], B[VW];
-        if (VW == 4) {
-            const uint4 g4 = *reinterpret_cast<const uint4*>(P + P_G * pstride);
-            const uint4 b4 = *reinterpret_cast<const uint4*>(P + P_B * pstride);
-            G[0] = g4.x; G[VW > 1 ? 1 : 0] = g4.y; G[VW > 2 ? 2 : 0] = g4.z; G[VW > 3 ? 3 : 0] = g4.w;
-            B[0] = b4.x; B[VW > 1 ? 1 : 0] = b4.y; B[VW > 2 ? 2 : 0] = b4.z; B[VW > 3 ? 3 : 0] = b4.w;
-        } else {
-            G[0] = P[P_G * pstride];
-            B[0] = P[P_B * pstride];
-        }
-        if (act && do_tick) {
-            const uint32_t* Sc = P + (size_t)scur * pstride;
-            uint32_t* Sn = P + (size_t)snxt * pstride;
-            uint32_t S[VW + 2], Sup[VW], Sdn[VW];
+    const int nu = (e.hi - e.lo + VW - 1) / VW;
+    for (int base = 0, b = 0; base < nu; base += T, ++b) {
+        const int u = base + tid;
+        if (u < nu) {
+            const int i = e.lo + u * VW;  // first word of this thread's unit
+            const int x = e.row_of(i), w0 = i - x * HW;
+            uint32_t* P = e.P0 + i;
+            uint32_t G[VW], B[VW];
             if (VW == 4) {
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                const uint4 s4 = *reinterpret_cast<const uint4*>(Sc);
-                const uint4 u4 = x > 0 ? *reinterpret_cast<const uint4*>(Sc - HW) : z;
-                const uint4 d4 = x < W - 1 ? *reinterpret_cast<const uint4*>(Sc + HW) : z;
-                S[1] = s4.x; S[VW > 1 ? 2 : 1] = s4.y; S[VW > 2 ? 3 : 1] = s4.z; S[VW > 3 ? 4 : 1] = s4.w;
-                Sup[0] = u4.x; Sup[VW > 1 ? 1 : 0] = u4.y; Sup[VW > 2 ? 2 : 0] = u4.z; Sup[VW > 3 ? 3 : 0] = u4.w;
-                Sdn[0] = d4.x; Sdn[VW > 1 ? 1 : 0] = d4.y; Sdn[VW > 2 ? 2 : 0] = d4.z; Sdn[VW > 3 ? 3 : 0] = d4.w;
+                const uint4 g4 = *reinterpret_cast<const uint4*>(P + P_G * pstride);
+                const uint4 b4 = *reinterpret_cast<const uint4*>(P + P_B * pstride);
+                G[0] = g4.x; G[VW > 1 ? 1 : 0] = g4.y; G[VW > 2 ? 2 : 0] = g4.z; G[VW > 3 ? 3 : 0] = g4.w;
+                B[0] = b4.x; B[VW > 1 ? 1 : 0] = b4.y; B[VW > 2 ? 2 : 0] = b4.z; B[VW > 3 ? 3 : 0] = b4.w;
             } else {
-                S[1] = Sc[0];
-                Sup[0] = x > 0 ? Sc[-HW] : 0u;
-                Sdn[0] = x < W - 1 ? Sc[HW] : 0u;
+                G[0] = P[P_G * pstride];
+                B[0] = P[P_B * pstride];
             }
-            S[0] = w0 > 0 ? Sc[-1] : 0u;
-            S[VW + 1] = w0 + VW < HW ? Sc[VW] : 0u;
+            if (digw >= i && digw < i + VW) {  // Agent.dig lands in this unit: this thread owns the word
 #pragma unroll
-            for (int k = 0; k < VW; ++k) {
-                const uint32_t h0 = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
-                const uint32_t h1 = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
-                const uint32_t h2 = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
-                const uint32_t h3 = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
-                if (B[k] | h0 | h1 | h2 | h3) {
-                    const int pos = atomicAdd(&q_n, 1);
-                    q_idx[pos] = (uint32_t)(i + k);
-                    q_G[pos] = G[k]; q_B[pos] = B[k];
-                    q_h[0][pos] = h0; q_h[1][pos] = h1; q_h[2][pos] = h2; q_h[3][pos] = h3;
+                for (int k = 0; k < VW; ++k)
+                    if (digw == i + k) G[k] &= ~ss.dig_bit;
+                apply_dig(e, t, digw, ss.dig_bit, ss.dig_clear_R);
+            }
+            if (ticking) {
+                const uint32_t* Sc = P + (size_t)scur * pstride;
+                uint32_t* Sn = P + (size_t)snxt * pstride;
+                uint32_t S[VW + 2], Sup[VW], Sdn[VW];
+                if (VW == 4) {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 s4 = *reinterpret_cast<const uint4*>(Sc);
+                    const uint4 u4 = x > 0 ? *reinterpret_cast<const uint4*>(Sc - HW) : z;
+                    const uint4 d4 = x < W - 1 ? *reinterpret_cast<const uint4*>(Sc + HW) : z;
+                    S[1] = s4.x; S[VW > 1 ? 2 : 1] = s4.y; S[VW > 2 ? 3 : 1] = s4.z; S[VW > 3 ? 4 : 1] = s4.w;
+                    Sup[0] = u4.x; Sup[VW > 1 ? 1 : 0] = u4.y; Sup[VW > 2 ? 2 : 0] = u4.z; Sup[VW > 3 ? 3 : 0] = u4.w;
+                    Sdn[0] = d4.x; Sdn[VW > 1 ? 1 : 0] = d4.y; Sdn[VW > 2 ? 2 : 0] = d4.z; Sdn[VW > 3 ? 3 : 0] = d4.w;
                 } else {
-                    my_ng += __popc(G[k]);  // inactive words cannot burn: B == 0
+                    S[1] = Sc[0];
+                    Sup[0] = x > 0 ? Sc[-HW] : 0u;
+                    Sdn[0] = x < W - 1 ? Sc[HW] : 0u;
+                }
+                S[0] = w0 > 0 ? Sc[-1] : 0u;
+                S[VW + 1] = w0 + VW < HW ? Sc[VW] : 0u;
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    const uint32_t h0 = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
+                    const uint32_t h1 = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
+                    const uint32_t h2 = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
+                    const uint32_t h3 = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
+                    if (B[k] | h0 | h1 | h2 | h3) {
+                        const int pos = atomicAdd(&q_n[b & 1], 1);
+                        q_idx[pos] = (uint32_t)(i + k);
+                        q_G[pos] = G[k]; q_B[pos] = B[k];
+                        q_h[pos] = h0; q_h[QCAP + pos] = h1; q_h[2 * QCAP + pos] = h2; q_h[3 * QCAP + pos] = h3;
+                    } else {
+                        my_ng += __popc(G[k]);  // inactive words cannot burn: B == 0
+                    }
+                }
+                // inactive words have no sources next tick; queued words overwrite their slot in phase 2
+                if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(0u, 0u, 0u, 0u);
+                else Sn[0] = 0u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    my_nb += __popc(B[k]);
+                    my_ng += __popc(G[k]);
+                    if (B[k] && want_touch && touches_reach(Rp, i + k, B[k], x, w0 + k, W, HW, digw_R, digclr)) my_touch = 1;
                 }
             }
-            // inactive words have no sources next tick; queued words overwrite their slot in phase 2
-            if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(0u, 0u, 0u, 0u);
-            else Sn[0] = 0u;
-        } else {
-#pragma unroll
-            for (int k = 0; k < VW; ++k) {
-                my_nb += __popc(B[k]);
-                my_ng += __popc(G[k]);
-                if (B[k] && want_touch && touches_reach(P + k + (size_t)t.P_R * pstride, B[k], x, w0 + k, W, HW)) my_touch = 1;
-            }
         }
-    }
-    __syncthreads();
-    // ---- phase 2: one queued active word per thread
-    const int nq = q_n;
-    if (nq) {
-        const int wid = sc[WF_S_WIND_ID];
-        const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
-        for (int it = threadIdx.x; it < nq; it += blockDim.x) {
+        if (!ticking) continue;
+        __syncthreads();
+        // ---- phase 2: one queued active word per thread
+        const int nq = q_n[b & 1];
+        if (tid == 0) q_n[(b + 1) & 1] = 0;
+        for (int it = tid; it < nq; it += T) {
             const int wi = (int)q_idx[it];
-            const int x = hw_shift >= 0 ? (wi >> hw_shift) : (wi / HW);
-            const int w = wi - x * HW;
+            const int x = e.row_of(wi), w = wi - x * HW;
             uint32_t G = q_G[it], B = q_B[it];
-            uint32_t* P = P0 + wi;
-            const uint32_t sn = tick_active_word<FB>(P, pstride, G, B, q_h[0][it], q_h[1][it], q_h[2][it], q_h[3][it], s, c,
-                                                     s.hits + ((size_t)env * W + x) * H + 32 * w, wid, kmin,
+            uint32_t* P = e.P0 + wi;
+            const uint32_t sn = tick_active_word<FB>(P, pstride, G, B, q_h[it], q_h[QCAP + it], q_h[2 * QCAP + it],
+                                                     q_h[3 * QCAP + it], s, c, e.hits + ((size_t)x * H + 32 * w), wid, kmin,
                                                      edge_word(W, H, x, w), my_edge);
             P[(size_t)snxt * pstride] = sn;
             my_nb += __popc(B);
             my_ng += __popc(G);
-            if (B && want_touch && touches_reach(P + (size_t)t.P_R * pstride, B, x, w, W, HW)) my_touch = 1;
+            if (B && want_touch && touches_reach(Rp, wi, B, x, w, W, HW, digw_R, digclr)) my_touch = 1;
         }
+        __syncthreads();
     }
-    // ---- per-env reductions: warp redux -> shared -> one atomic per block and quantity
+    // ---- partial reductions of this CTA: warp redux -> shared
     const unsigned FULL = 0xffffffffu;
     my_nb = __reduce_add_sync(FULL, my_nb);
     my_ng = __reduce_add_sync(FULL, my_ng);
     my_edge = __any_sync(FULL, my_edge);
     my_touch = __any_sync(FULL, my_touch);
-    if ((threadIdx.x & 31) == 0) {
+    if ((tid & 31) == 0) {
         if (my_nb) atomicAdd(&red[0], my_nb);
         if (my_ng) atomicAdd(&red[1], my_ng);
         if (my_edge) atomicOr(&red[2], 1);
         if (my_touch) atomicOr(&red[3], 1);
     }
-    __syncthreads();
-    if (threadIdx.x < 4 && red[threadIdx.x]) {
-        int32_t* acc = t.acc + 4 * env;
-        if (threadIdx.x < 2) atomicAdd(&acc[threadIdx.x], red[threadIdx.x]);
-        else atomicOr(&acc[threadIdx.x], 1);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// World.get_state :399-402 for every env: [agent_pos, type == fire, fire_mobility != inf].
-// One thread per word: 2 plane words in, 96 bytes (32 cells x 3 channels) out.
-__global__ void __launch_bounds__(kTileThreads) obs_kernel(DevState s, void* obs, int obs_dtype) {
-    __shared__ uint32_t spread3[256];
-    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
-        uint32_t o = 0u;
+// World.get_state :399-402 of this CTA's slice: [agent_pos, type == fire, fire_mobility != inf].
+// Output element (x*H + y)*3 + ch is ONE BIT, so a word's 32 cells are a 96-bit stream (its three masks
+// interleaved bit by bit, via a 256-entry "spread by 3" table).  A warp stages the streams of 32
+// consecutive words in shared memory (3 KB of output); then lane l expands the 16 stream bits of
+// 16-byte chunk it*32+l with two lookups in a byte -> 8 bytes table: every store instruction writes
+// 512 contiguous bytes.  2 plane words in, 96 bytes out per word.
+__device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int obs_dtype, const uint32_t* spread3,
+                                               const uint2* tab8, uint32_t* stage_all, int vis, int ax, int ay) {
+    const int W = e.W, H = e.H, HW = e.HW;
+    const int lane = e.tid & 31, warp = e.tid >> 5, nwarps = e.T >> 5;
+    const uint32_t* PF = e.plane(P_F);
+    const uint32_t* PI = e.plane(P_I);
+    const int aw = vis ? ax * HW + (ay >> 5) : -1;
+    uint32_t* stage = stage_all + warp * 96;  // 32 words x 96 bits
+    const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
+    const bool fast_ok = obs_dtype == WF_OBS_U8 && (H & 31) == 0;
+    for (int g = e.lo + warp * 32; g < e.hi; g += nwarps * 32) {
+        const int i = g + lane;
+        if (i < e.hi) {
+            const int x = e.row_of(i), w = i - x * HW;
+            const uint32_t F = PF[i];
+            const uint32_t freerow = ~PI[i] & valid_word(H, w);
+            uint32_t p[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
-        spread3[v] = o;
-    }
-    __syncthreads();
-    const int env = blockIdx.y;
-    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ic = min(i, nwords - 1);  // tail threads stay alive for the warp shuffles
-    const int x = ic / HW, w = ic - x * HW;
-    const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    const uint32_t* P = s.planes + word_index(s, 0, env, 0, 0) + ic;
-    const uint32_t F = P[P_F * pstride];
-    const uint32_t freerow = ~P[P_I * pstride] & valid_word(H, w);
-    const uint32_t arow = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && (sc[WF_S_AY] >> 5) == w) ? 1u << (sc[WF_S_AY] & 31) : 0u;
-    const int ncell = min(32, H - 32 * w);
-    const size_t e0 = (((size_t)env * W + x) * H + 32 * w) * 3;  // first output element of this word
-    uint32_t r[3];
-    {
-        uint32_t p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            p[k] = spread3[(arow >> (8 * k)) & 255u] | (spread3[(F >> (8 * k)) & 255u] << 1) |
-                   (spread3[(freerow >> (8 * k)) & 255u] << 2);
-        r[0] = p[0] | (p[1] << 24);
-        r[1] = (p[1] >> 8) | (p[2] << 16);
-        r[2] = (p[2] >> 16) | (p[3] << 8);
-    }
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // Fast path (warp-uniform): the warp's 32 words are 32 full words of ONE row-major run, so their
-    // 32 x 96 output bytes are contiguous.  Chunk c (16 bytes) of that run comes from word c/6: fetch its
-    // stream bits by shuffle so that every store instruction writes 512 contiguous bytes.
-    const int i0 = i - lane;
-    const bool fast = obs_dtype == WF_OBS_U8 && (H & 31) == 0 && i0 + 31 < nwords;
-    if (fast) {
-        uint8_t* base = static_cast<uint8_t*>(obs) + (((size_t)env * W) * H + (size_t)32 * i0) * 3;
-        uint4* o = reinterpret_cast<uint4*>(base);
-#pragma unroll
-        for (int it = 0; it < 6; ++it) {
-            const int cidx = it * 32 + lane;       // chunk index within the warp's 3072 bytes
-            const int src = cidx / 6, k = cidx - 6 * src;
-            const uint32_t a0 = __shfl_sync(FULL, r[0], src), a1 = __shfl_sync(FULL, r[1], src),
-                           a2 = __shfl_sync(FULL, r[2], src);
-            const uint32_t word = (k >> 1) == 0 ? a0 : (k >> 1) == 1 ? a1 : a2;
-            const uint32_t bits = (word >> ((k & 1) * 16)) & 0xffffu;
-            uint4 v;
-            v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-            v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-            o[cidx] = v;
+            for (int k = 0; k < 4; ++k)
+                p[k] = (spread3[(F >> (8 * k)) & 255u] << 1) | (spread3[(freerow >> (8 * k)) & 255u] << 2);
+            if (i == aw) p[(ay & 31) >> 3] |= 1u << (3 * (ay & 7));  // agent_pos layer: one cell per env
+            const uint32_t r0 = p[0] | (p[1] << 24), r1 = (p[1] >> 8) | (p[2] << 16), r2 = (p[2] >> 16) | (p[3] << 8);
+            if (fast_ok && g + 31 < e.hi) {
+                stage[3 * lane] = r0; stage[3 * lane + 1] = r1; stage[3 * lane + 2] = r2;
+            } else {  // ragged rows, the slice's tail, float observations: one word per thread
+                const int ncell = min(32, H - 32 * w);
+                const size_t e0 = (((size_t)e.env * W + x) * H + 32 * w) * 3;  // first output element of this word
+                const uint32_t r[3] = {r0, r1, r2};
+                if (obs_dtype == WF_OBS_U8) {
+                    uint8_t* o8 = static_cast<uint8_t*>(obs_step) + e0;
+                    for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
+                } else {
+                    float* of = static_cast<float*>(obs_step) + e0;
+                    for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+                }
+            }
         }
-    } else if (i < nwords) {
-        if (obs_dtype == WF_OBS_U8) {
-            uint8_t* o8 = static_cast<uint8_t*>(obs) + e0;
-            for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
-        } else {
-            float* of = static_cast<float*>(obs) + e0;
-            for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
+        if (fast_ok && g + 31 < e.hi) {  // warp-uniform
+            __syncwarp();
+            uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
+#pragma unroll
+            for (int it = 0; it < 6; ++it) {
+                const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 3072 bytes = 16 stream bits
+                const uint32_t bits = stage16[cidx];
+                const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
+                __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+            }
+            __syncwarp();
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// World.reset part 1 (reset_map, environment.py:59-67): every plane and the temp layer back to their
-// defaults.  Grid = (slices, persistent CTAs over the reset list): a big env is initialised by several CTAs.
-template <int FB>
-__global__ void __launch_bounds__(1024) reset_init_kernel(DevState s, StepCfg c, TileState t) {
-    const int n = t.counters[1];
-    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (int k = blockIdx.y; k < n; k += gridDim.y) {
-        const int env = t.reset_list[k];
-        uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
-        for (int i = tid; i < nwords; i += nthr) {
-            const int x = i / HW, w = i - x * HW;
-            const uint32_t valid = valid_word(H, w);
-            uint32_t* P = P0 + i;
-            P[P_G * pstride] = valid;
-            P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
-            P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
-#pragma unroll
-            for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
-            P[(size_t)t.P_S0 * pstride] = 0u;
-            P[(size_t)t.P_S1 * pstride] = 0u;
-            P[(size_t)t.P_R * pstride] = valid;  // open field: every cell reaches the border (re-flooded if rivers)
-        }
-        uint32_t* hits = s.hits + (size_t)env * W * H;  // temp layer := 0
-        if (((size_t)env * W * H) % 4 == 0 && (W * H) % 4 == 0) {
-            uint4* h4 = reinterpret_cast<uint4*>(hits);
-            for (int i = tid; i < (W * H) / 4; i += nthr) h4[i] = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-            for (int i = tid; i < W * H; i += nthr) hits[i] = 0u;
-        }
-    }
-}
-
-// World.reset part 2 (environment.py:186-212) of one env by one CTA: wind, river, fire, agent, ignitions.
-template <int FB>
-__device__ void reset_block(const DevState& s, const StepCfg& c, const TileState& t, const wf_init* init, int env) {
-    __shared__ int sh_fab, sh_nb;
-    const int W = s.W, H = s.H, HW = s.HW, nwords = W * HW;
-    if (threadIdx.x == 0) { sh_fab = 0; sh_nb = 0; }
-    __syncthreads();
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
+// World.reset (environment.py:186-212) of this cluster's env: reset_map (:59-95), fire at the centre,
+// Agent.__init__ (:100-113), extra ignitions, reach plane, burning count.  Whole cluster.
+template <int FB, bool CL>
+__device__ void reset_env(const Env& e, const DevState& s, const StepCfg& c, const TilePar& t, const wf_init* init,
+                          int32_t* sc, StepShared& ss, int* red, int (*xch)[8][4], int& par) {
+    const int W = e.W, H = e.H, HW = e.HW, tid = e.tid, T = e.T;
+    const size_t pstride = e.pstride;
     const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;  // every thread reads the old value ...
+    const int cur = sc[WF_S_RESERVED] & 1;
     __syncthreads();                                            // ... before thread 0 overwrites it
-    if (threadIdx.x == 0) {
-        ResetDraws dr((uint32_t)(c.env_id_base + env), episode, c.key0, c.key1);
+    // ---- reset_map :59-67: every plane and the temp layer of this slice back to their defaults
+    for (int i = e.lo + tid; i < e.hi; i += T) {
+        const int x = e.row_of(i), w = i - x * HW;
+        const uint32_t valid = valid_word(H, w);
+        uint32_t* P = e.P0 + i;
+        P[P_G * pstride] = valid;
+        P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
+        P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
+#pragma unroll
+        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
+        P[(size_t)t.P_S0 * pstride] = 0u;
+        P[(size_t)t.P_S1 * pstride] = 0u;
+        P[(size_t)t.P_R * pstride] = valid;  // open field: every cell reaches the border (re-flooded if rivers)
+    }
+    {   // hit counters (temp layer := 0) of the cells of words [lo, hi)
+        auto cell_of = [&](int i) -> int {
+            if (i >= e.nwords) return W * H;
+            const int x = e.row_of(i), w = i - x * HW;
+            return x * H + min(32 * w, H);
+        };
+        const int c0 = cell_of(e.lo), c1 = cell_of(e.hi);
+        uint32_t* hits = e.hits;
+        if ((((size_t)e.env * W * H) & 3) == 0 && (c0 & 3) == 0 && (c1 & 3) == 0) {
+            uint4* h4 = reinterpret_cast<uint4*>(hits);
+            for (int i = (c0 >> 2) + tid; i < (c1 >> 2); i += T) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (int i = c0 + tid; i < c1; i += T) hits[i] = 0u;
+        }
+    }
+    sync_env<CL>();
+    const bool writer = e.rank == 0;
+    const int cx = W / 2, cy = H / 2;  // get_fire_location, utility.py:61-64
+    const int scur = cur ? t.P_S1 : t.P_S0;
+    if (tid == 0) {  // the draws are replayed by every CTA (identical scalars); rank 0 writes the planes
+        ResetDraws dr((uint32_t)(c.env_id_base + e.env), episode, c.key0, c.key1);
         int wid = 0;
         if (c.wind_random) {  // :188-190
             const int si = dr.next() % 3u, wx = dr.next() % 3u, wy = dr.next() % 3u;
             wid = si * 9 + wx * 3 + wy;
         }
-        const int cx = W / 2, cy = H / 2;
         if (c.make_rivers) {  // reset_map :69-95
             int river_x = dr.next() % (uint32_t)W;
             int river_y = 1 + dr.next() % 3u;
             while (river_y < H - (1 + (int)(dr.next() % 3u))) {
-                const uint32_t bit = 1u << (river_y & 31);
-                plane_word(s, P_G, env, river_x, river_y >> 5) &= ~bit;
-                plane_word(s, P_WT, env, river_x, river_y >> 5) |= bit;
-                plane_word(s, P_I, env, river_x, river_y >> 5) |= bit;
+                if (writer) {
+                    const uint32_t bit = 1u << (river_y & 31);
+                    const int wi = river_x * HW + (river_y >> 5);
+                    e.plane(P_G)[wi] &= ~bit;
+                    e.plane(P_WT)[wi] |= bit;
+                    e.plane(P_I)[wi] |= bit;
+                }
                 const int new_y = river_y + 1;
                 int new_x = river_x + ((dr.next() % 2u) ? -1 : 1);
-                for (;;) {
+                for (;;) {  // `not a <= new_x < b and not (new_x, new_y) == fire`; the chain short-circuits b
                     const int lo = 1 + dr.next() % 3u;
                     bool chain = false;
                     if (lo <= new_x) chain = new_x < W - (1 + (int)(dr.next() % 3u));
@@ -617,23 +686,32 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
                 river_y = new_y;
             }
         }
-        tile_set_fire(s, t, env, cx, cy, sc);  // :203
         int ax, ay;
-        if (init != nullptr && init[env].ax >= 0) {
-            ax = init[env].ax; ay = init[env].ay;
+        if (init != nullptr && init[e.env].ax >= 0) {
+            ax = init[e.env].ax; ay = init[e.env].ay;
         } else {
-            const int rad = dr.next() % 3u;
+            const int rad = dr.next() % 3u;  // radius - 1, utility.py:70
             const int idx = dr.next() % (uint32_t)kCircleLen[rad];
             ax = cx + kCircle[rad][idx][0];
             ay = cy + kCircle[rad][idx][1];
         }
-        {  // Agent.__init__ digs its start cell (:112-113); R is re-flooded below
-            const uint32_t bit = 1u << (ay & 31);
-            const int w = ay >> 5;
-            plane_word(s, P_G, env, ax, w) &= ~bit; plane_word(s, P_F, env, ax, w) &= ~bit;
-            plane_word(s, P_BT, env, ax, w) &= ~bit; plane_word(s, P_WT, env, ax, w) &= ~bit;
-            plane_word(s, P_D, env, ax, w) |= bit; plane_word(s, P_I, env, ax, w) |= bit;
-            plane_word(s, t.P_R, env, ax, w) &= ~bit;
+        if (writer) {
+            {   // World.set_fire_to(centre), :203 / :233-246 (a river cell under the origin keeps fm_inf, Q5)
+                const uint32_t bit = 1u << (cy & 31);
+                const int wi = cx * HW + (cy >> 5);
+                e.plane(P_G)[wi] &= ~bit; e.plane(P_BT)[wi] &= ~bit; e.plane(P_D)[wi] &= ~bit; e.plane(P_WT)[wi] &= ~bit;
+                e.plane(P_F)[wi] |= bit; e.plane(P_B)[wi] |= bit;
+                if (c.fuel >= 2) e.plane(scur)[wi] |= bit;
+            }
+            {   // Agent.__init__ digs its start cell (:112-113)
+                const uint32_t bit = 1u << (ay & 31);
+                const int wi = ax * HW + (ay >> 5);
+                if (!(e.plane(P_D)[wi] & bit)) {
+                    e.plane(P_G)[wi] &= ~bit; e.plane(P_F)[wi] &= ~bit; e.plane(P_BT)[wi] &= ~bit; e.plane(P_WT)[wi] &= ~bit;
+                    e.plane(P_D)[wi] |= bit; e.plane(P_I)[wi] |= bit;
+                    e.plane(t.P_R)[wi] &= ~bit;
+                }
+            }
         }
         sc[WF_S_ALIVE] = 1; sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_DEAD] = 0; sc[WF_S_DIGGING] = 1;
         sc[WF_S_VISIBLE] = 1; sc[WF_S_RUNNING] = 1; sc[WF_S_LATCHED] = 0;
@@ -643,206 +721,316 @@ __device__ void reset_block(const DevState& s, const StepCfg& c, const TileState
     }
     __syncthreads();
     // extra ignitions: World.set_fire_to after reset() (IGNITE stream).  set_fire_to is idempotent and
-    // commutes with itself, so the k-th ignitions run in parallel with atomics.
-    const int scur = t.cur ? t.P_S1 : t.P_S0;
-    for (int k = threadIdx.x; k < c.extra_ignitions; k += blockDim.x) {
+    // commutes with itself, so the k-th ignitions run in parallel with atomics (rank 0); every CTA
+    // replays the draws for the fire_at_border flag.
+    int my_fab = 0;
+    for (int k = tid; k < c.extra_ignitions; k += T) {
         uint32_t wd[4];
-        philox4x32_10((uint32_t)(c.env_id_base + env), episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, wd);
-        const int x = (int)(wd[0] % (uint32_t)W), y = (int)(wd[1] % (uint32_t)H), w = y >> 5;
-        const uint32_t bit = 1u << (y & 31);
-        atomicAnd(&plane_word(s, P_G, env, x, w), ~bit);
-        atomicAnd(&plane_word(s, P_BT, env, x, w), ~bit);
-        atomicAnd(&plane_word(s, P_D, env, x, w), ~bit);
-        atomicAnd(&plane_word(s, P_WT, env, x, w), ~bit);
-        atomicOr(&plane_word(s, P_F, env, x, w), bit);
-        atomicOr(&plane_word(s, P_B, env, x, w), bit);
-        if (c.fuel >= 2) atomicOr(&plane_word(s, scur, env, x, w), bit);
-        if (x == 0 || x == W - 1 || y == 0 || y == H - 1) sh_fab = 1;
+        philox4x32_10((uint32_t)(c.env_id_base + e.env), episode, (uint32_t)k, kStreamIgnite, c.key0, c.key1, wd);
+        const int x = (int)(wd[0] % (uint32_t)W), y = (int)(wd[1] % (uint32_t)H);
+        if (writer) {
+            const int wi = x * HW + (y >> 5);
+            const uint32_t bit = 1u << (y & 31);
+            atomicAnd(&e.plane(P_G)[wi], ~bit);
+            atomicAnd(&e.plane(P_BT)[wi], ~bit);
+            atomicAnd(&e.plane(P_D)[wi], ~bit);
+            atomicAnd(&e.plane(P_WT)[wi], ~bit);
+            atomicOr(&e.plane(P_F)[wi], bit);
+            atomicOr(&e.plane(P_B)[wi], bit);
+            if (c.fuel >= 2) atomicOr(&e.plane(scur)[wi], bit);
+        }
+        if (x == 0 || x == W - 1 || y == 0 || y == H - 1) my_fab = 1;
     }
-    __syncthreads();
+    const int fab = __syncthreads_or(my_fab);
+    if (tid == 0 && fab) sc[WF_S_FIRE_AT_BORDER] = 1;
+    sync_env<CL>();
     // Without rivers the only blocked cell is the agent's start cell, and one cell cannot cut a
-    // >= 10x10 grid: R = every free cell (set by reset_init_kernel).  With rivers: flood.
-    if (c.make_rivers) flood_block(s, t, env);
-    else if (threadIdx.x == 0) t.need_flood[env] = 0;
+    // >= 10x10 grid: R = every free cell (set above).  With rivers: flood.
+    if (c.make_rivers) flood<CL>(e, t, red, xch, par, ss);
     int n = 0;
-    const uint32_t* B = &plane_word(s, P_B, env, 0, 0);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) n += __popc(B[i]);
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sh_nb, n);
+    const uint32_t* B = e.plane(P_B);
+    for (int i = e.lo + tid; i < e.hi; i += T) n += __popc(B[i]);
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((tid & 31) == 0 && n) atomicAdd(&red[0], n);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sc[WF_S_N_BURNING] = sh_nb;
-        if (sh_fab) sc[WF_S_FIRE_AT_BORDER] = 1;
+    exchange<CL>(e, red, xch, par, ss);
+    if (tid == 0) {
+        sc[WF_S_N_BURNING] = ss.tot[0];
+        ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
     }
-}
-
-// ForestFire.step part 3: RUNNING flag (forest_fire.py:105-106), World.get_reward
-// (environment.py:342-390).  One thread per env; finished envs are appended to the reset list.
-__global__ void finish_kernel(DevState s, StepCfg c, TileState t, double* reward, uint8_t* done, int do_tick) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env == 0) t.counters[0] = 0;  // the flood list was drained before the tick
-    if (env >= s.N) return;
-    int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
-    const int32_t* acc = t.acc + 4 * env;
-    const bool act = sc[WF_S_RESERVED] != 0;
-    double rew = 0.0;
-    if (act) {
-        const bool anyB = acc[0] > 0;
-        sc[WF_S_N_BURNING] = acc[0];
-        if (do_tick) {
-            if (acc[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
-            if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
-        }
-        const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
-        if (check && !acc[3]) {
-            sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
-            rew = c.contained_bonus;
-            atomicAdd(&s.stats[ST_CONTAINED], 1ull);
-        } else if (!sc[WF_S_ALIVE]) {
-            rew = c.death_penalty;
-        } else if (!anyB) {
-            rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)acc[1], (double)(s.W * s.H)));
-        } else {
-            rew = c.default_reward;
-        }
-        sc[WF_S_T] += 1;
-        atomicAdd(&s.stats[ST_STEPS], 1ull);
-        if (!sc[WF_S_RUNNING]) {
-            atomicAdd(&s.stats[ST_EPISODES], 1ull);
-            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
-        }
-    }
-    const bool is_done = !sc[WF_S_RUNNING];
-    if (reward) reward[env] = rew;
-    if (done) done[env] = is_done ? 1 : 0;
-    if (c.auto_reset && act && is_done) t.reset_list[atomicAdd(&t.counters[1], 1)] = env;
-}
-
-// wf_reset: the reset list is the mask.
-__global__ void mask_to_list_kernel(TileState t, const uint8_t* mask, int n) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env < n && (mask == nullptr || mask[env])) t.reset_list[atomicAdd(&t.counters[1], 1)] = env;
-}
-__global__ void zero_counter_kernel(TileState t, int which) { t.counters[which] = 0; }
-
-// Persistent CTAs drain the reset list: World.reset (environment.py:186-212), one CTA per env at a time.
-template <int FB>
-__global__ void __launch_bounds__(1024) reset_list_kernel(DevState s, StepCfg c, TileState t, const wf_init* init) {
-    const int n = t.counters[1];
-    for (int k = blockIdx.x; k < n; k += gridDim.x) {
-        reset_block<FB>(s, c, t, init, t.reset_list[k]);
-        __syncthreads();
-    }
-}
-
-// S := B & (fuel >= 2), R re-flooded, n_burning recounted (after wf_set_state / wf_set_fire_to)
-__global__ void rebuild_kernel(DevState s, TileState t) {
-    __shared__ int sh_nb;
-    const int env = blockIdx.x;
-    const int nwords = s.W * s.HW;
-    const size_t pstride = (size_t)s.N * s.RS * s.HW;
-    uint32_t* P0 = s.planes + word_index(s, 0, env, 0, 0);
-    if (threadIdx.x == 0) sh_nb = 0;
     __syncthreads();
-    int n = 0;
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-        uint32_t* P = P0 + i;
-        uint32_t ge2 = 0u;
-        for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * pstride];
-        const uint32_t B = P[P_B * pstride];
-        P[(size_t)(t.cur ? t.P_S1 : t.P_S0) * pstride] = B & ge2;
-        n += __popc(B);
-    }
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&sh_nb, n);
-    __syncthreads();
-    if (threadIdx.x == 0) s.scal[(size_t)env * WF_NSCALARS + WF_S_N_BURNING] = sh_nb;
-    flood_block(s, t, env);
 }
 
 // ---------------------------------------------------------------------------------------------
+// K x ForestFire.step (forest_fire.py:30-49) or ForestFire.reset of one env per cluster.
+template <int FB, int VW, bool CL>
+__global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCfg c, TilePar t, TileIO io) {
+    extern __shared__ uint32_t qmem[];  // active-word queue: 7 arrays of blockDim.x * VW words
+    __shared__ int32_t sc[WF_NSCALARS];
+    __shared__ int red[4];
+    __shared__ int xch[2][8][4];
+    __shared__ int q_n[2];
+    __shared__ StepShared ss;
+    __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
+    __shared__ uint2 tab8[256];        // bit i of the index -> byte i
+
+    Env e;
+    e.tid = threadIdx.x; e.T = t.T;
+    e.CS = CL ? (int)cluster_nctarank() : 1;
+    e.rank = CL ? (int)cluster_ctarank() : 0;
+    e.env = CL ? (int)cluster_id_x() : (int)blockIdx.x;
+    e.W = s.W; e.H = s.H; e.HW = s.HW; e.nwords = t.nwords; e.hw_shift = t.hw_shift; e.hw_magic = t.hw_magic;
+    e.lo = min(e.nwords, e.rank * t.wpc);
+    e.hi = min(e.nwords, e.lo + t.wpc);
+    e.pstride = t.pstride;
+    e.P0 = s.planes + (size_t)e.env * t.env_words;
+    e.hits = s.hits + (size_t)e.env * t.cells;
+    const int tid = e.tid;
+
+    for (int v = tid; v < 256; v += e.T) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
+        spread3[v] = o;
+        uint2 b8;
+        b8.x = ((v & 15u) * 0x00204081u) & 0x01010101u;
+        b8.y = (((v >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        tab8[v] = b8;
+    }
+    if (tid < WF_NSCALARS) sc[tid] = s.scal[(size_t)e.env * WF_NSCALARS + tid];
+    if (tid < 4) red[tid] = 0;
+    if (tid < 2) q_n[tid] = 0;
+    __syncthreads();
+    int par = 0;
+    const bool writer = e.rank == 0;
+    const size_t step_bytes = t.step_bytes;
+
+    if (io.reset_mode) {
+        // ---------------- ForestFire.reset() ----------------
+        if (io.mask == nullptr || io.mask[e.env] != 0) reset_env<FB, CL>(e, s, c, t, io.init, sc, ss, red, xch, par);
+        if (io.obs != nullptr) emit_obs_slice(e, io.obs, io.obs_dtype, spread3, tab8, qmem, sc[WF_S_VISIBLE], sc[WF_S_AX], sc[WF_S_AY]);
+    } else {
+        // ---------------- K x ForestFire.step(action) ----------------
+        int it = io.a_iter0;
+        for (int k = 0; k < io.K; ++k) {
+            it -= 1;
+            const int do_tick = (it == 0);  // the fire ticks once every a_speed steps (forest_fire.py:40-43)
+            if (do_tick) it = c.a_speed;
+            if (tid == 0) {
+                agent_phase(e, c, t, io, s, k, do_tick, sc, ss, writer);
+                q_n[0] = 0;  // the tick's first batch appends to queue 0
+            }
+            sync_env<CL>();  // barrier X
+            const bool act = ss.act != 0;
+            int digw = ss.dig_word;
+            if (ss.need_flood) {  // rare: the dig may cut the reach plane -> apply it now and re-flood R
+                if (tid == 0 && digw >= e.lo && digw < e.hi) apply_dig(e, t, digw, ss.dig_bit, ss.dig_clear_R);
+                digw = -1;
+                sync_env<CL>();
+                flood<CL>(e, t, red, xch, par, ss);
+            }
+            if (act) {
+                const bool ticking = do_tick != 0;
+                tick_slice<FB, VW>(e, s, c, t, sc, ss, ticking, digw, red, q_n, qmem);
+                __syncthreads();
+                const int cur = sc[WF_S_RESERVED];
+                exchange<CL>(e, red, xch, par, ss);  // barrier Y
+                if (tid == 0) {
+                    // ---- RUNNING (forest_fire.py:105-106), World.get_reward (environment.py:342-390)
+                    if (ticking) sc[WF_S_RESERVED] = cur ^ 1;  // the source mask just written becomes current
+                    const bool anyB = ss.tot[0] > 0;
+                    sc[WF_S_N_BURNING] = ss.tot[0];
+                    if (do_tick) {
+                        if (ss.tot[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
+                        if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
+                    }
+                    double rew;
+                    const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
+                    if (check && !ss.tot[3]) {
+                        sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
+                        rew = c.contained_bonus;
+                        if (writer) atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+                    } else if (!sc[WF_S_ALIVE]) {
+                        rew = c.death_penalty;
+                    } else if (!anyB) {
+                        rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)ss.tot[1], (double)(s.W * s.H)));
+                    } else {
+                        rew = c.default_reward;
+                    }
+                    sc[WF_S_T] += 1;
+                    const bool is_done = !sc[WF_S_RUNNING];
+                    if (writer) {
+                        atomicAdd(&s.stats[ST_STEPS], 1ull);
+                        if (is_done) {
+                            atomicAdd(&s.stats[ST_EPISODES], 1ull);
+                            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
+                        }
+                        if (io.reward) io.reward[(size_t)k * s.N + e.env] = rew;
+                        if (io.done) io.done[(size_t)k * s.N + e.env] = is_done ? 1 : 0;
+                    }
+                    ss.reset_now = c.auto_reset && is_done;
+                    ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
+                }
+            } else if (tid == 0) {  // frozen env: reward 0, done 1, nothing moves
+                if (writer) {
+                    if (io.reward) io.reward[(size_t)k * s.N + e.env] = 0.0;
+                    if (io.done) io.done[(size_t)k * s.N + e.env] = 1;
+                }
+                ss.reset_now = 0;
+                ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
+            }
+            __syncthreads();
+            if (ss.reset_now) reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
+            if (io.obs != nullptr)
+                emit_obs_slice(e, static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype, spread3, tab8, qmem,
+                               ss.obs_vis, ss.obs_ax, ss.obs_ay);
+        }
+    }
+    __syncthreads();
+    if (writer && tid < WF_NSCALARS) s.scal[(size_t)e.env * WF_NSCALARS + tid] = sc[tid];
+}
+
+// S := B & (fuel >= 2) in the env's current source plane, R re-flooded, n_burning recounted
+// (after wf_set_state / wf_set_fire_to).  One CTA per env.
+__global__ void rebuild_kernel(DevState s, TilePar t) {
+    __shared__ int red[4];
+    __shared__ int xch[2][8][4];
+    __shared__ StepShared ss;
+    Env e;
+    e.tid = threadIdx.x; e.T = blockDim.x; e.CS = 1; e.rank = 0; e.env = blockIdx.x;
+    e.W = s.W; e.H = s.H; e.HW = s.HW; e.nwords = t.nwords; e.hw_shift = t.hw_shift; e.hw_magic = t.hw_magic;
+    e.lo = 0; e.hi = e.nwords;
+    e.pstride = t.pstride;
+    e.P0 = s.planes + (size_t)e.env * t.env_words;
+    e.hits = s.hits + (size_t)e.env * t.cells;
+    int32_t* sc = s.scal + (size_t)e.env * WF_NSCALARS;
+    const int cur = sc[WF_S_RESERVED] & 1;
+    if (e.tid < 4) red[e.tid] = 0;
+    __syncthreads();
+    int n = 0;
+    for (int i = e.tid; i < e.nwords; i += e.T) {
+        uint32_t* P = e.P0 + i;
+        uint32_t ge2 = 0u;
+        for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * e.pstride];
+        const uint32_t B = P[P_B * e.pstride];
+        P[(size_t)(cur ? t.P_S1 : t.P_S0) * e.pstride] = B & ge2;
+        n += __popc(B);
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((e.tid & 31) == 0 && n) atomicAdd(&red[0], n);
+    __syncthreads();
+    if (e.tid == 0) {
+        sc[WF_S_N_BURNING] = red[0];
+        red[0] = 0;
+    }
+    __syncthreads();
+    int par = 0;
+    flood<false>(e, t, red, xch, par, ss);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Threads per env so that all N envs together fill the machine (148 SMs x 1024 threads at <= 64
+// registers), split into a CTA size T and a cluster size CS.
+static void choose_geometry(const DevState& s, int& T, int& CS) {
+    const int VW = (s.HW % 4 == 0) ? 4 : 1;
+    const long nunits = ((long)s.W * s.HW + VW - 1) / VW;
+    long tpe = 148L * 1024 / (s.N > 0 ? s.N : 1);
+    long p = 128;
+    while (p * 2 <= tpe && p < 4096) p *= 2;
+    while (p > 128 && p > nunits) p /= 2;
+    T = (int)(p < 512 ? p : 512);
+    CS = (int)(p / T);
+    if (p == 2048) { T = 256; CS = 8; }
+    const int t_env = env_int("WF_TILE_T", 0), cs_env = env_int("WF_TILE_CS", 0);
+    if (t_env == 128 || t_env == 256 || t_env == 512) T = t_env;
+    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) CS = cs_env;
+}
+
+template <int FB, int VW, bool CL>
+static cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(tile_rollout_kernel<FB, VW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 4 * 28);
+}
+
 cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     TileState* t = new TileState();
-    t->cur = 0;
     t->P_S0 = 7 + s.FB;
     t->P_S1 = 8 + s.FB;
     t->P_R = 9 + s.FB;
-    t->flood_smem_ok = 0;
+    choose_geometry(s, t->T, t->CS);
     cudaError_t e;
-    if ((e = cudaMalloc(&t->acc, (size_t)s.N * 4 * sizeof(int32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->need_flood, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->flood_list, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->reset_list, (size_t)s.N * sizeof(int32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t->counters, 2 * sizeof(int32_t))) != cudaSuccess) return e;
-    cudaMemset(t->counters, 0, 2 * sizeof(int32_t));
-    cudaMemset(t->acc, 0, (size_t)s.N * 4 * sizeof(int32_t));
-    cudaMemset(t->need_flood, 0, (size_t)s.N * sizeof(int32_t));
+    if ((e = set_smem_attr<5, 1, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<5, 4, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<8, 1, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<8, 4, false>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<5, 1, true>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<5, 4, true>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<8, 1, true>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<8, 4, true>()) != cudaSuccess) return e;
     *out = t;
     return cudaSuccess;
 }
 
-void tile_destroy(TileState* t) {
-    if (!t) return;
-    cudaFree(t->acc); cudaFree(t->need_flood); cudaFree(t->flood_list); cudaFree(t->reset_list); cudaFree(t->counters);
-    delete t;
-}
+void tile_destroy(TileState* t) { delete t; }
 
-static int cta_threads(const DevState& s) { return s.W * s.HW >= 8192 ? 1024 : 256; }
-static int list_grid(const DevState& s) { return s.N < 296 ? s.N : 296; }  // 2 persistent CTAs per SM
-static int init_slices(const DevState& s) {  // CTAs that share one env's plane initialisation
-    const int per = (s.W * s.H + 65535) / 65536;  // ~64K cells (256 KB of hit counters) per CTA
-    return per < 1 ? 1 : (per > 16 ? 16 : per);
-}
-
-template <int FB>
-static cudaError_t run_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st,
-                              int64_t* launches) {
+static TilePar make_par(const TileState* t, const DevState& s, int obs_dtype) {
+    TilePar p;
+    p.P_S0 = t->P_S0; p.P_S1 = t->P_S1; p.P_R = t->P_R;
+    p.hw_shift = -1;
+    for (int k = 0; k < 16; ++k)
+        if ((1 << k) == s.HW) p.hw_shift = k;
+    p.hw_magic = (uint32_t)((0x100000000ull + (uint64_t)s.HW - 1) / (uint64_t)s.HW);  // exact for word < 2^32 / HW
     const int nwords = s.W * s.HW;
-    const dim3 grid((nwords + kTileThreads - 1) / kTileThreads, s.N);
-    const int eb = (s.N + 127) / 128;
-    if (io.reset_mode) {
-        zero_counter_kernel<<<1, 1, 0, st>>>(*t, 1);
-        mask_to_list_kernel<<<eb, 128, 0, st>>>(*t, io.mask, s.N);
-        reset_init_kernel<FB><<<dim3(init_slices(s), list_grid(s)), 1024, 0, st>>>(s, c, *t);
-        reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, io.init);
-        *launches += 4;
-    } else {
-        agent_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.actions, io.do_tick, io.policy, io.actions_out);
-        flood_list_kernel<<<list_grid(s), 1024, 0, st>>>(s, *t);
-        int hw_shift = -1;
-        for (int k = 0; k < 16; ++k)
-            if ((1 << k) == s.HW) hw_shift = k;
-        if (s.HW % 4 == 0) {
-            const dim3 g4((nwords / 4 + kTileThreads - 1) / kTileThreads, s.N);
-            tile_tick_kernel<FB, 4><<<g4, kTileThreads, 0, st>>>(s, c, *t, io.do_tick, hw_shift);
-        } else {
-            tile_tick_kernel<FB, 1><<<grid, kTileThreads, 0, st>>>(s, c, *t, io.do_tick, hw_shift);
-        }
-        if (io.do_tick) t->cur ^= 1;
-        finish_kernel<<<eb, 128, 0, st>>>(s, c, *t, io.reward, io.done, io.do_tick);
-        *launches += 4;
-        if (c.auto_reset) {
-            reset_init_kernel<FB><<<dim3(init_slices(s), list_grid(s)), 1024, 0, st>>>(s, c, *t);
-            reset_list_kernel<FB><<<list_grid(s), 1024, 0, st>>>(s, c, *t, nullptr);
-            *launches += 2;
-        }
+    const int per = (nwords + t->CS - 1) / t->CS;
+    p.wpc = (per + 31) / 32 * 32;
+    p.T = t->T;
+    p.nwords = nwords;
+    p.cells = s.W * s.H;
+    p.pstride = (size_t)s.N * s.RS * s.HW;
+    p.env_words = (size_t)s.RS * s.HW;
+    p.step_bytes = (size_t)s.N * s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
+    return p;
+}
+
+template <int FB, int VW>
+static cudaError_t launch(const TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st) {
+    const TilePar p = make_par(t, s, io.obs_dtype);
+    const size_t smem = (size_t)t->T * VW * 28;
+    if (t->CS == 1) {
+        tile_rollout_kernel<FB, VW, false><<<s.N, t->T, smem, st>>>(s, c, p, io);
+        return cudaGetLastError();
     }
-    if (io.obs) {
-        obs_kernel<<<grid, kTileThreads, 0, st>>>(s, io.obs, io.obs_dtype);
-        *launches += 1;
-    }
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)s.N * t->CS);
+    cfg.blockDim = dim3(t->T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = t->CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tile_rollout_kernel<FB, VW, true>, s, c, p, io);
 }
 
 cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io,
                                cudaStream_t stream, int64_t* launches) {
-    if (s.FB == 5) return run_family<5>(t, s, c, io, stream, launches);
-    return run_family<8>(t, s, c, io, stream, launches);
+    *launches += 1;
+    const bool v4 = (s.HW % 4 == 0);
+    if (s.FB == 5) return v4 ? launch<5, 4>(t, s, c, io, stream) : launch<5, 1>(t, s, c, io, stream);
+    return v4 ? launch<8, 4>(t, s, c, io, stream) : launch<8, 1>(t, s, c, io, stream);
 }
 
 cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg&, cudaStream_t stream,
                                  int64_t* launches) {
-    rebuild_kernel<<<s.N, cta_threads(s), 0, stream>>>(s, *t);
+    rebuild_kernel<<<s.N, s.W * s.HW >= 8192 ? 1024 : 256, 0, stream>>>(s, make_par(t, s, WF_OBS_U8));
     *launches += 1;
     return cudaGetLastError();
 }
