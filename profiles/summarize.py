@@ -5,7 +5,7 @@ usage: python profiles/summarize.py r01
 Reads (whatever exists):
   gpurun_out/launches_c2.csv, launches_c4.csv     `ncu --metrics gpu__time_duration.sum ...` launch lists
   gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 64 steps/launch)
-  gpurun_out/prof_c4tick.ncu-rep, prof_c4obs.ncu-rep   captures of the tile family's two big kernels
+  gpurun_out/prof_c4.ncu-rep, prof_c5.ncu-rep     captures of wf::tile_rollout_kernel (c4 / c5, 16 steps/launch)
 Writes profiles/<round>_*.{csv,txt,json} and profiles/ncu_traffic.json (read by bench.py).
 """
 import collections
@@ -85,15 +85,15 @@ def main(rnd):
         ls = launch_summary(name, rnd)
         if ls:
             summary[f"{name}_launch_list"] = ls
-    for rep, tag, key in (("prof_c2.ncu-rep", "c2_warp_kernel", "c2_chunk64"), ("prof_c4tick.ncu-rep", "c4_tile_tick", "c4_tick"),
-                          ("prof_c4obs.ncu-rep", "c4_obs_kernel", "c4_obs"), ("prof_c4.ncu-rep", "c4_tile_step", None)):
+    for rep, tag, key in (("prof_c2.ncu-rep", "c2_warp_kernel", "c2_chunk64"), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4_chunk16"),
+                          ("prof_c5.ncu-rep", "c5_tile_rollout", "c5_chunk16")):
         ks = rep_summary(rep, rnd, tag)
         if ks:
             summary[tag] = ks
             if key and "dram__bytes_read.sum" in ks[0]:
                 traffic[key] = sum(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]) for k in ks) / len(ks)
-    if "c4_tick" in traffic and "c4_obs" in traffic:
-        traffic["c4_chunk1"] = traffic["c4_tick"] + traffic["c4_obs"]
+    for stale in ("c4_tick", "c4_obs", "c4_chunk1"):  # kernels of the earlier multi-launch tile pipeline
+        traffic.pop(stale, None)
     json.dump(summary, open(os.path.join(PR, f"{rnd}_summary.json"), "w"), indent=1)
     json.dump(traffic, open(tpath, "w"), indent=1)
     print(json.dumps(traffic, indent=1))

@@ -55,9 +55,26 @@ struct StepShared {
     int32_t tot[4];       // cluster totals: burning cells, grass cells, ignition on edge, burning touches reach
     int32_t reset_now;
     int32_t obs_vis, obs_ax, obs_ay;  // agent_pos layer of the observation being emitted
+    uint32_t stat[ST_N];  // this launch's contribution to the handle's statistics (flushed once, at the end)
 };
 
 int tile_extra_planes() { return 3; }
+
+// Phase timing of one probe CTA (debug builds only: -DWF_TILE_TIMING; read with wf_debug_tile_timing).
+#ifdef WF_TILE_TIMING
+__device__ unsigned long long g_tile_timing[16];
+#define WF_TSTAMP(slot)                                                      \
+    do {                                                                     \
+        if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) {               \
+            unsigned long long _t;                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));           \
+            g_tile_timing[slot] += _t - t_last;                              \
+            t_last = _t;                                                     \
+        }                                                                    \
+    } while (0)
+#else
+#define WF_TSTAMP(slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // cluster primitives
@@ -194,30 +211,54 @@ __device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[8][4]
 }
 
 // ---------------------------------------------------------------------------------------------
-// Agent.dig (environment.py:123-133), planning half: what the dig changes and whether the reach plane
-// survives it.  Thread 0 only, reads only.  Returns true iff the cell becomes dirt now.
-__device__ bool plan_dig(const Env& e, const TilePar& t, const int32_t* sc, StepShared& ss, int x, int y) {
-    const int W = e.W, H = e.H;
-    const int wi = x * e.HW + (y >> 5);
-    const uint32_t bit = 1u << (y & 31);
-    const uint32_t Dw = e.plane(P_D)[wi], Iw = e.plane(P_I)[wi], Rw = e.plane(t.P_R)[wi];
-    bool f[8];  // free neighbours N, NE, E, SE, S, SW, W, NW  (screen coordinates: N = y-1, E = x+1)
-    const int dx[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dy[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+// Everything the agent phase needs to know about a cell and its 8 neighbours, fetched with loads
+// that do not depend on each other (one memory round trip instead of one per question).
+struct Around {
+    uint32_t wt, f, d, i, r;  // bits of the cell itself: water, type == fire, dirt, fm_inf, reach
+    bool free8[8];            // free (in bounds and finite fire mobility) neighbours N, NE, E, SE, S, SW, W, NW
+};
+__device__ __forceinline__ Around load_around(const Env& e, const TilePar& t, int x, int y) {
+    const int W = e.W, H = e.H, HW = e.HW;
+    const int w = y >> 5, b = y & 31, wi = x * HW + w;
+    const uint32_t WTw = e.plane(P_WT)[wi], Fw = e.plane(P_F)[wi], Dw = e.plane(P_D)[wi], Rw = e.plane(t.P_R)[wi];
+    const uint32_t* I = e.plane(P_I);
+    uint32_t rows[3][3];  // fm_inf words [x-1, x, x+1][w-1, w, w+1]; out of bounds reads as blocked
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int nx = x + dx[k], ny = y + dy[k];
-        const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
-        f[k] = inb && !e.bit(P_I, inb ? nx : x, inb ? ny : y);
-    }
-    if (Dw & bit) return false;
-    ss.dig_word = wi;
-    ss.dig_bit = bit;
-    if (Iw & bit) return true;  // the cell already had infinite fire mobility (water is never entered; kept for safety)
+    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+        for (int dw = -1; dw <= 1; ++dw) {
+            const int xx = x + dx, ww = w + dw;
+            const bool ok = xx >= 0 && xx < W && ww >= 0 && ww < HW && (dw == 0 || (dw < 0 ? b == 0 : b == 31));
+            rows[dx + 1][dw + 1] = ok ? I[xx * HW + ww] : 0xffffffffu;
+        }
+    Around a;
+    a.wt = (WTw >> b) & 1u; a.f = (Fw >> b) & 1u; a.d = (Dw >> b) & 1u; a.r = (Rw >> b) & 1u;
+    a.i = (rows[1][1] >> b) & 1u;
+    auto blocked = [&](int dx, int dy) -> bool {  // fm_inf (or outside the grid) at (x + dx, y + dy)
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) return true;
+        const int dw = (yy >> 5) - w;
+        return (rows[dx + 1][dw + 1] >> (yy & 31)) & 1u;
+    };
+    const int dx8[8] = {0, 1, 1, 1, 0, -1, -1, -1}, dy8[8] = {-1, -1, 0, 1, 1, 1, 0, -1};  // screen: N = y-1, E = x+1
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.free8[k] = !blocked(dx8[k], dy8[k]);
+    return a;
+}
+
+// Agent.dig (environment.py:123-133), planning half: what the dig changes and whether the reach plane
+// survives it.  Thread 0 only, no memory access.  Returns true iff the cell becomes dirt now.
+__device__ __forceinline__ bool plan_dig(const Env& e, const Around& a, const int32_t* sc, StepShared& ss, int x, int y) {
+    const int H = e.H;
+    if (a.d) return false;
+    ss.dig_word = x * e.HW + (y >> 5);
+    ss.dig_bit = 1u << (y & 31);
+    if (a.i) return true;  // the cell already had infinite fire mobility (water is never entered; kept for safety)
     // get_reward only searches for a path while `not fire_at_border and len(border_points)`
     // (environment.py:345): once either latch is set R is never read again in this episode
     // (World.reset re-floods it), so it is not maintained.
     if (sc[WF_S_FIRE_AT_BORDER] || sc[WF_S_LATCHED]) return true;
-    if (!(Rw & bit)) return true;  // the cell had no path to the border: nobody reached the border through it
+    if (!a.r) return true;  // the cell had no path to the border: nobody reached the border through it
     ss.dig_clear_R = 1;
     // Does removing this cell possibly disconnect its neighbours from the border?  Its free 4-neighbours
     // were all in R.  If they stay connected to each other through the ring of 8 surrounding cells,
@@ -226,11 +267,11 @@ __device__ bool plan_dig(const Env& e, const TilePar& t, const int32_t* sc, Step
     int n4 = 0, groups = 0;
 #pragma unroll
     for (int k = 0; k < 8; k += 2) {
-        if (!f[k]) continue;
+        if (!a.free8[k]) continue;
         n4++;
         // this 4-neighbour starts a new group unless it is ring-connected to the previous 4-neighbour
         const int pk = (k + 6) & 7, pd = (k + 7) & 7;
-        if (!(f[pk] && f[pd])) groups++;
+        if (!(a.free8[pk] && a.free8[pd])) groups++;
     }
     if (n4 == 4 && groups == 0) groups = 1;  // full ring
     if (on_seed ? n4 > 0 : groups > 1) ss.need_flood = 1;
@@ -294,29 +335,32 @@ __device__ void agent_phase(const Env& e, const StepCfg& c, const TilePar& t, co
     if (writer && io.actions_out != nullptr) io.actions_out[(size_t)k * s.N + e.env] = action;
     if (!sc[WF_S_ALIVE]) return;
     int ax = sc[WF_S_AX], ay = sc[WF_S_AY];
-    bool on_fire_now = e.bit(P_F, ax, ay);  // type == fire under the agent (pre-move cell)
-    if (action >= 0 && action < 4) {
+    const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
+    const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
+    const bool is_move = action >= 0 && action < 4;
+    const bool inb = is_move && nx >= 0 && nx < W && ny >= 0 && ny < H;
+    // one round trip: the cell under the agent and everything about the target cell
+    bool on_fire_now = e.bit(P_F, ax, ay);  // type == fire under the agent
+    const Around tgt = load_around(e, t, inb ? nx : ax, inb ? ny : ay);
+    if (is_move) {
         sc[WF_S_VISIBLE] = 0;  // Q1
-        const int nx = ax + (action == 2 ? 1 : action == 3 ? -1 : 0);
-        const int ny = ay + (action == 1 ? 1 : action == 0 ? -1 : 0);
-        const bool inb = nx >= 0 && nx < W && ny >= 0 && ny < H;
-        if (inb && !e.bit(P_WT, nx, ny)) {
+        if (inb && !tgt.wt) {
             ax = nx; ay = ny;
             sc[WF_S_AX] = ax; sc[WF_S_AY] = ay; sc[WF_S_VISIBLE] = 1;
-            const bool onfire = e.bit(P_F, nx, ny);
+            const bool onfire = tgt.f != 0u;
             on_fire_now = onfire;
-            if (sc[WF_S_DIGGING] && !onfire) plan_dig(e, t, sc, ss, nx, ny);
+            if (sc[WF_S_DIGGING] && !onfire) plan_dig(e, tgt, sc, ss, nx, ny);
             if (onfire) sc[WF_S_DEAD] = 1;
         }
     }
-    if (c.allow_dig_toggle && action == 4) {
+    if (c.allow_dig_toggle && action == 4) {  // not a move: `tgt` describes the agent's own cell
         sc[WF_S_DIGGING] ^= 1;
-        if (sc[WF_S_DIGGING] && plan_dig(e, t, sc, ss, ax, ay)) on_fire_now = false;  // dig makes the cell dirt (Q7)
+        if (sc[WF_S_DIGGING] && plan_dig(e, tgt, sc, ss, ax, ay)) on_fire_now = false;  // dig makes the cell dirt (Q7)
     }
     if (do_tick && (sc[WF_S_DEAD] || on_fire_now)) {
         sc[WF_S_VISIBLE] = 0;
         sc[WF_S_ALIVE] = 0;
-        if (writer) atomicAdd(&s.stats[ST_DEATHS], 1ull);
+        ss.stat[ST_DEATHS] += 1u;
     }
 }
 
@@ -428,17 +472,27 @@ __device__ __forceinline__ bool touches_reach(const uint32_t* R, int wi, uint32_
 
 // One tick (or, on non-tick steps, just the per-env counts) over this CTA's slice.  Leaves the CTA's
 // partial reductions in red[0..3]; the caller synchronises.
-// VW = words per thread and batch along y: 4 (128-bit loads; needs HW % 4 == 0) or 1.
+// VW = words per thread and iteration along y: 4 (128-bit loads; needs HW % 4 == 0) or 1.
+// Every WARP works on its own: it streams 32 units, compacts the ACTIVE words (burning or heated)
+// into its private queue in shared memory (ballot + prefix count) and then hands one queued word to
+// each lane, so the dependent loads of the active path (fuel planes, hit counters) run in parallel
+// instead of serially inside the few lanes that own a fire front.  Nothing in the tick couples two
+// warps (S is ping-ponged, R is only read, every other plane word has one owner), so there is no
+// block-wide barrier here and a warp without fire never waits for one that has some.
 template <int FB, int VW>
 __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, const StepCfg& c, const TilePar& t,
                                            const int32_t* sc, const StepShared& ss, bool ticking, int digw, int* red,
-                                           int* q_n, uint32_t* qmem) {
-    const int W = e.W, H = e.H, HW = e.HW, T = e.T, tid = e.tid;
-    const int QCAP = T * VW;
-    uint32_t* const q_idx = qmem;
-    uint32_t* const q_G = qmem + QCAP;
-    uint32_t* const q_B = qmem + 2 * QCAP;
-    uint32_t* const q_h = qmem + 3 * QCAP;  // [4][QCAP]
+                                           uint32_t* qmem) {
+    const int W = e.W, H = e.H, HW = e.HW, tid = e.tid;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = e.T >> 5;
+    constexpr int QW = 32 * VW;  // queue capacity of one warp
+    constexpr int WSM = 7 * QW;  // shared words per warp: 7 queue arrays (the observation phase reuses them as staging)
+    uint32_t* const q_idx = qmem + warp * WSM;
+    uint32_t* const q_G = q_idx + QW;
+    uint32_t* const q_B = q_idx + 2 * QW;
+    uint32_t* const q_h = q_idx + 3 * QW;  // [4][QW]
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const size_t pstride = e.pstride;
     const bool want_touch = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED];
     const int cur = sc[WF_S_RESERVED] & 1;
@@ -450,13 +504,20 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
     const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
     int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
     const int nu = (e.hi - e.lo + VW - 1) / VW;
-    for (int base = 0, b = 0; base < nu; base += T, ++b) {
-        const int u = base + tid;
+    for (int ub = warp; ub * 32 < nu; ub += nwarps) {
+        const int u = ub * 32 + lane;
+        uint32_t G[VW], B[VW], h[4][VW];
+        bool active[VW];
+#pragma unroll
+        for (int k = 0; k < VW; ++k) {
+            G[k] = B[k] = 0u;
+            h[0][k] = h[1][k] = h[2][k] = h[3][k] = 0u;
+            active[k] = false;
+        }
+        const int i = e.lo + u * VW;  // first word of this lane's unit
         if (u < nu) {
-            const int i = e.lo + u * VW;  // first word of this thread's unit
             const int x = e.row_of(i), w0 = i - x * HW;
             uint32_t* P = e.P0 + i;
-            uint32_t G[VW], B[VW];
             if (VW == 4) {
                 const uint4 g4 = *reinterpret_cast<const uint4*>(P + P_G * pstride);
                 const uint4 b4 = *reinterpret_cast<const uint4*>(P + P_B * pstride);
@@ -493,18 +554,12 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
                 S[VW + 1] = w0 + VW < HW ? Sc[VW] : 0u;
 #pragma unroll
                 for (int k = 0; k < VW; ++k) {
-                    const uint32_t h0 = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
-                    const uint32_t h1 = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
-                    const uint32_t h2 = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
-                    const uint32_t h3 = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
-                    if (B[k] | h0 | h1 | h2 | h3) {
-                        const int pos = atomicAdd(&q_n[b & 1], 1);
-                        q_idx[pos] = (uint32_t)(i + k);
-                        q_G[pos] = G[k]; q_B[pos] = B[k];
-                        q_h[pos] = h0; q_h[QCAP + pos] = h1; q_h[2 * QCAP + pos] = h2; q_h[3 * QCAP + pos] = h3;
-                    } else {
-                        my_ng += __popc(G[k]);  // inactive words cannot burn: B == 0
-                    }
+                    h[0][k] = G[k] & ((S[k + 1] >> 1) | (S[k + 2] << 31));  // d = N (0,-1): source at y+1
+                    h[1][k] = G[k] & ((S[k + 1] << 1) | (S[k] >> 31));      // d = S (0,+1): source at y-1
+                    h[2][k] = G[k] & Sup[k];                                // d = E (+1,0): source at x-1
+                    h[3][k] = G[k] & Sdn[k];                                // d = W (-1,0): source at x+1
+                    active[k] = (B[k] | h[0][k] | h[1][k] | h[2][k] | h[3][k]) != 0u;
+                    if (!active[k]) my_ng += __popc(G[k]);  // inactive words cannot burn: B == 0
                 }
                 // inactive words have no sources next tick; queued words overwrite their slot in phase 2
                 if (VW == 4) *reinterpret_cast<uint4*>(Sn) = make_uint4(0u, 0u, 0u, 0u);
@@ -519,32 +574,43 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
             }
         }
         if (!ticking) continue;
-        __syncthreads();
-        // ---- phase 2: one queued active word per thread
-        const int nq = q_n[b & 1];
-        if (tid == 0) q_n[(b + 1) & 1] = 0;
-        for (int it = tid; it < nq; it += T) {
+        // ---- compact the warp's active words into its queue
+        int nq = 0;
+#pragma unroll
+        for (int k = 0; k < VW; ++k) {
+            const uint32_t m = __ballot_sync(FULL, active[k]);
+            if (active[k]) {
+                const int pos = nq + __popc(m & lt_mask);
+                q_idx[pos] = (uint32_t)(i + k);
+                q_G[pos] = G[k]; q_B[pos] = B[k];
+                q_h[pos] = h[0][k]; q_h[QW + pos] = h[1][k]; q_h[2 * QW + pos] = h[2][k]; q_h[3 * QW + pos] = h[3][k];
+            }
+            nq += __popc(m);
+        }
+        if (nq == 0) continue;  // warp-uniform
+        __syncwarp();
+        // ---- phase 2: one queued active word per lane
+        for (int it = lane; it < nq; it += 32) {
             const int wi = (int)q_idx[it];
             const int x = e.row_of(wi), w = wi - x * HW;
-            uint32_t G = q_G[it], B = q_B[it];
+            uint32_t Gq = q_G[it], Bq = q_B[it];
             uint32_t* P = e.P0 + wi;
-            const uint32_t sn = tick_active_word<FB>(P, pstride, G, B, q_h[it], q_h[QCAP + it], q_h[2 * QCAP + it],
-                                                     q_h[3 * QCAP + it], s, c, e.hits + ((size_t)x * H + 32 * w), wid, kmin,
+            const uint32_t sn = tick_active_word<FB>(P, pstride, Gq, Bq, q_h[it], q_h[QW + it], q_h[2 * QW + it],
+                                                     q_h[3 * QW + it], s, c, e.hits + ((size_t)x * H + 32 * w), wid, kmin,
                                                      edge_word(W, H, x, w), my_edge);
             P[(size_t)snxt * pstride] = sn;
-            my_nb += __popc(B);
-            my_ng += __popc(G);
-            if (B && want_touch && touches_reach(Rp, wi, B, x, w, W, HW, digw_R, digclr)) my_touch = 1;
+            my_nb += __popc(Bq);
+            my_ng += __popc(Gq);
+            if (Bq && want_touch && touches_reach(Rp, wi, Bq, x, w, W, HW, digw_R, digclr)) my_touch = 1;
         }
-        __syncthreads();
+        __syncwarp();
     }
     // ---- partial reductions of this CTA: warp redux -> shared
-    const unsigned FULL = 0xffffffffu;
     my_nb = __reduce_add_sync(FULL, my_nb);
     my_ng = __reduce_add_sync(FULL, my_ng);
     my_edge = __any_sync(FULL, my_edge);
     my_touch = __any_sync(FULL, my_touch);
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         if (my_nb) atomicAdd(&red[0], my_nb);
         if (my_ng) atomicAdd(&red[1], my_ng);
         if (my_edge) atomicOr(&red[2], 1);
@@ -568,8 +634,55 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
     const int aw = vis ? ax * HW + (ay >> 5) : -1;
     uint32_t* stage = stage_all + warp * 96;  // 32 words x 96 bits
     const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
+    int g_first = e.lo;
+    if (obs_dtype == WF_OBS_U8 && (H & 31) == 0 && (HW & 3) == 0) {
+        // Wide path: a warp takes 128 consecutive words (12 KB of output) per iteration with two 128-bit
+        // loads per lane, issued one iteration ahead so that the expansion never waits on HBM.
+        uint32_t* stage4 = stage_all + warp * 384;  // 128 words x 96 bits
+        const uint16_t* stage4_16 = reinterpret_cast<const uint16_t*>(stage4);
+        const int n128 = (e.hi - e.lo) >> 7;  // full 128-word groups of this slice
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 F4 = z4, I4 = z4;
+        if (warp < n128) {
+            F4 = *reinterpret_cast<const uint4*>(PF + e.lo + warp * 128 + 4 * lane);
+            I4 = *reinterpret_cast<const uint4*>(PI + e.lo + warp * 128 + 4 * lane);
+        }
+        for (int gi = warp; gi < n128; gi += nwarps) {
+            const int g = e.lo + gi * 128;
+            const uint4 Fc = F4, Ic = I4;
+            if (gi + nwarps < n128) {
+                F4 = *reinterpret_cast<const uint4*>(PF + g + nwarps * 128 + 4 * lane);
+                I4 = *reinterpret_cast<const uint4*>(PI + g + nwarps * 128 + 4 * lane);
+            }
+            const uint32_t Fw[4] = {Fc.x, Fc.y, Fc.z, Fc.w}, Iw[4] = {Ic.x, Ic.y, Ic.z, Ic.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t F = Fw[j], freerow = ~Iw[j];
+                uint32_t p[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    p[k] = (spread3[(F >> (8 * k)) & 255u] << 1) | (spread3[(freerow >> (8 * k)) & 255u] << 2);
+                if (g + 4 * lane + j == aw) p[(ay & 31) >> 3] |= 1u << (3 * (ay & 7));
+                uint32_t* st = stage4 + (4 * lane + j) * 3;
+                st[0] = p[0] | (p[1] << 24);
+                st[1] = (p[1] >> 8) | (p[2] << 16);
+                st[2] = (p[2] >> 16) | (p[3] << 8);
+            }
+            __syncwarp();
+            uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
+#pragma unroll 8
+            for (int it = 0; it < 24; ++it) {
+                const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 12288 bytes = 16 stream bits
+                const uint32_t bits = stage4_16[cidx];
+                const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
+                __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+            }
+            __syncwarp();
+        }
+        g_first = e.lo + n128 * 128;  // the slice's tail (< 128 words) takes the narrow path
+    }
     const bool fast_ok = obs_dtype == WF_OBS_U8 && (H & 31) == 0;
-    for (int g = e.lo + warp * 32; g < e.hi; g += nwarps * 32) {
+    for (int g = g_first + warp * 32; g < e.hi; g += nwarps * 32) {
         const int i = g + lane;
         if (i < e.hi) {
             const int x = e.row_of(i), w = i - x * HW;
@@ -764,12 +877,15 @@ __device__ void reset_env(const Env& e, const DevState& s, const StepCfg& c, con
 // ---------------------------------------------------------------------------------------------
 // K x ForestFire.step (forest_fire.py:30-49) or ForestFire.reset of one env per cluster.
 template <int FB, int VW, bool CL>
-__global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCfg c, TilePar t, TileIO io) {
-    extern __shared__ uint32_t qmem[];  // active-word queue: 7 arrays of blockDim.x * VW words
+#ifndef WF_TILE_MAXT
+#define WF_TILE_MAXT 512
+#define WF_TILE_MINB 2
+#endif
+__global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kernel(DevState s, StepCfg c, TilePar t, TileIO io) {
+    extern __shared__ uint32_t qmem[];  // per-warp active-word queues (7 x 32 * VW words each); observation staging
     __shared__ int32_t sc[WF_NSCALARS];
     __shared__ int red[4];
     __shared__ int xch[2][8][4];
-    __shared__ int q_n[2];
     __shared__ StepShared ss;
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
@@ -799,12 +915,16 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
     }
     if (tid < WF_NSCALARS) sc[tid] = s.scal[(size_t)e.env * WF_NSCALARS + tid];
     if (tid < 4) red[tid] = 0;
-    if (tid < 2) q_n[tid] = 0;
+    if (tid < ST_N) ss.stat[tid] = 0u;
     __syncthreads();
     int par = 0;
     const bool writer = e.rank == 0;
     const size_t step_bytes = t.step_bytes;
 
+#ifdef WF_TILE_TIMING
+    unsigned long long t_last;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+#endif
     if (io.reset_mode) {
         // ---------------- ForestFire.reset() ----------------
         if (io.mask == nullptr || io.mask[e.env] != 0) reset_env<FB, CL>(e, s, c, t, io.init, sc, ss, red, xch, par);
@@ -816,11 +936,10 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
             it -= 1;
             const int do_tick = (it == 0);  // the fire ticks once every a_speed steps (forest_fire.py:40-43)
             if (do_tick) it = c.a_speed;
-            if (tid == 0) {
-                agent_phase(e, c, t, io, s, k, do_tick, sc, ss, writer);
-                q_n[0] = 0;  // the tick's first batch appends to queue 0
-            }
+            if (tid == 0) agent_phase(e, c, t, io, s, k, do_tick, sc, ss, writer);
+            WF_TSTAMP(0);
             sync_env<CL>();  // barrier X
+            WF_TSTAMP(1);
             const bool act = ss.act != 0;
             int digw = ss.dig_word;
             if (ss.need_flood) {  // rare: the dig may cut the reach plane -> apply it now and re-flood R
@@ -831,10 +950,13 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
             }
             if (act) {
                 const bool ticking = do_tick != 0;
-                tick_slice<FB, VW>(e, s, c, t, sc, ss, ticking, digw, red, q_n, qmem);
+                tick_slice<FB, VW>(e, s, c, t, sc, ss, ticking, digw, red, qmem);
+                WF_TSTAMP(2);
                 __syncthreads();
+                WF_TSTAMP(3);
                 const int cur = sc[WF_S_RESERVED];
                 exchange<CL>(e, red, xch, par, ss);  // barrier Y
+                WF_TSTAMP(4);
                 if (tid == 0) {
                     // ---- RUNNING (forest_fire.py:105-106), World.get_reward (environment.py:342-390)
                     if (ticking) sc[WF_S_RESERVED] = cur ^ 1;  // the source mask just written becomes current
@@ -849,7 +971,7 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
                     if (check && !ss.tot[3]) {
                         sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
                         rew = c.contained_bonus;
-                        if (writer) atomicAdd(&s.stats[ST_CONTAINED], 1ull);
+                        ss.stat[ST_CONTAINED] += 1u;
                     } else if (!sc[WF_S_ALIVE]) {
                         rew = c.death_penalty;
                     } else if (!anyB) {
@@ -859,12 +981,12 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
                     }
                     sc[WF_S_T] += 1;
                     const bool is_done = !sc[WF_S_RUNNING];
+                    ss.stat[ST_STEPS] += 1u;
+                    if (is_done) {
+                        ss.stat[ST_EPISODES] += 1u;
+                        if (sc[WF_S_ALIVE]) ss.stat[ST_BURNOUTS] += 1u;
+                    }
                     if (writer) {
-                        atomicAdd(&s.stats[ST_STEPS], 1ull);
-                        if (is_done) {
-                            atomicAdd(&s.stats[ST_EPISODES], 1ull);
-                            if (sc[WF_S_ALIVE]) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
-                        }
                         if (io.reward) io.reward[(size_t)k * s.N + e.env] = rew;
                         if (io.done) io.done[(size_t)k * s.N + e.env] = is_done ? 1 : 0;
                     }
@@ -879,15 +1001,20 @@ __global__ void __launch_bounds__(512, 2) tile_rollout_kernel(DevState s, StepCf
                 ss.reset_now = 0;
                 ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
             }
+            WF_TSTAMP(5);
             __syncthreads();
+            WF_TSTAMP(6);
             if (ss.reset_now) reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
+            WF_TSTAMP(7);
             if (io.obs != nullptr)
                 emit_obs_slice(e, static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype, spread3, tab8, qmem,
                                ss.obs_vis, ss.obs_ax, ss.obs_ay);
+            WF_TSTAMP(8);
         }
     }
     __syncthreads();
     if (writer && tid < WF_NSCALARS) s.scal[(size_t)e.env * WF_NSCALARS + tid] = sc[tid];
+    if (writer && tid < ST_N && ss.stat[tid]) atomicAdd(&s.stats[tid], (unsigned long long)ss.stat[tid]);
 }
 
 // S := B & (fuel >= 2) in the env's current source plane, R re-flooded, n_burning recounted
@@ -936,12 +1063,13 @@ static int env_int(const char* name, int dflt) {
 }
 
 // Threads per env so that all N envs together fill the machine (148 SMs x 1024 threads at <= 64
-// registers), split into a CTA size T and a cluster size CS.
+// registers), split into a CTA size T and a cluster size CS.  Measured on B200 (tools/geom_sweep.sh):
+// 256 threads per env beat 128 even when that means two waves of CTAs (c4: 51 vs 61 us/step).
 static void choose_geometry(const DevState& s, int& T, int& CS) {
     const int VW = (s.HW % 4 == 0) ? 4 : 1;
     const long nunits = ((long)s.W * s.HW + VW - 1) / VW;
     long tpe = 148L * 1024 / (s.N > 0 ? s.N : 1);
-    long p = 128;
+    long p = 256;
     while (p * 2 <= tpe && p < 4096) p *= 2;
     while (p > 128 && p > nunits) p /= 2;
     T = (int)(p < 512 ? p : 512);
@@ -1000,7 +1128,7 @@ static TilePar make_par(const TileState* t, const DevState& s, int obs_dtype) {
 template <int FB, int VW>
 static cudaError_t launch(const TileState* t, const DevState& s, const StepCfg& c, const TileIO& io, cudaStream_t st) {
     const TilePar p = make_par(t, s, io.obs_dtype);
-    const size_t smem = (size_t)t->T * VW * 28;
+    const size_t smem = (size_t)t->T * VW * 28;  // per warp: 7 queue arrays of 32 * VW words (reused as observation staging)
     if (t->CS == 1) {
         tile_rollout_kernel<FB, VW, false><<<s.N, t->T, smem, st>>>(s, c, p, io);
         return cudaGetLastError();
@@ -1027,6 +1155,18 @@ cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c
     if (s.FB == 5) return v4 ? launch<5, 4>(t, s, c, io, stream) : launch<5, 1>(t, s, c, io, stream);
     return v4 ? launch<8, 4>(t, s, c, io, stream) : launch<8, 1>(t, s, c, io, stream);
 }
+
+#ifdef WF_TILE_TIMING
+extern "C" int wf_debug_tile_timing(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_tile_timing, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_tile_timing, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg&, cudaStream_t stream,
                                  int64_t* launches) {
