@@ -64,7 +64,16 @@ __global__ void get_state_kernel(DevState s, uint8_t* type, uint8_t* burning, ui
             for (int q = 0; q < s.FB; ++q) f |= bit(P_FU0 + q) << q;
             fuel[i] = (uint8_t)f;
         }
-        if (hits) reinterpret_cast<uint32_t*>(hits)[i] = s.hits[i];
+        if (hits) {
+            uint32_t hv;
+            if (s.HB) {  // bit-sliced total (direction-independent quanta): reported in the N byte
+                hv = 0u;
+                for (int q = 0; q < s.HB; ++q) hv |= bit(P_FU0 + s.FB + q) << q;
+            } else {
+                hv = s.hits[i];
+            }
+            reinterpret_cast<uint32_t*>(hits)[i] = hv;
+        }
         if (apos) {
             const int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
             apos[i] = (sc[WF_S_VISIBLE] && sc[WF_S_AX] == x && sc[WF_S_AY] == y) ? 1 : 0;
@@ -108,8 +117,19 @@ __global__ void set_state_kernel(DevState s, const uint8_t* type, const uint8_t*
                 s.planes[word_index(s, P_FU0 + q, env, x, w)] = m;
             }
         }
-        if (hits)
+        if (hits && s.HB) {
+            for (int q = 0; q < s.HB; ++q) {
+                uint32_t m = 0;
+                for (int b = 0; b < ny; ++b) {
+                    const uint32_t hv = reinterpret_cast<const uint32_t*>(hits)[cell0 + b];
+                    const uint32_t tot = (hv & 255u) + ((hv >> 8) & 255u) + ((hv >> 16) & 255u) + (hv >> 24);
+                    m |= ((tot >> q) & 1u) << b;
+                }
+                s.planes[word_index(s, P_FU0 + s.FB + q, env, x, w)] = m;
+            }
+        } else if (hits) {
             for (int b = 0; b < ny; ++b) s.hits[cell0 + b] = reinterpret_cast<const uint32_t*>(hits)[cell0 + b];
+        }
     }
 }
 
@@ -253,7 +273,7 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
     s.HW = (c.height + 31) / 32;
     s.RS = e->tile ? c.width : (c.width <= 16 ? 16 : 32);
     s.FB = c.fuel <= 31 ? 5 : 8;
-    s.NP = 7 + s.FB + (e->tile ? tile_extra_planes() : 0);
+    s.HB = 0;
     StepCfg& sc = e->sc;
     sc.n_actions = c.n_actions; sc.a_speed = c.a_speed; sc.allow_dig_toggle = c.allow_dig_toggle;
     sc.make_rivers = c.make_rivers; sc.wind_random = c.wind_random; sc.fuel = c.fuel;
@@ -263,6 +283,14 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
     sc.key0 = (uint32_t)(c.seed & 0xffffffffu); sc.key1 = (uint32_t)(c.seed >> 32);
     sc.env_id_base = c.env_id_base;
     build_wind_table(c, e->wind_host, e->n_wind);
+    {   // Direction-independent heat quanta for every wind this handle can meet (e.g. the Logs/ constants:
+        // wind [0.54, (0, 0)]): only the TOTAL hit count of a cell matters, and the warp family keeps it
+        // bit-sliced in registers (7 planes cover 4 neighbours x (fuel - 1) <= 120 hits).
+        bool all_uniform = true;
+        for (int i = 0; i < e->n_wind; ++i) all_uniform = all_uniform && e->wind_host.uniform[i];
+        if (!e->tile && all_uniform && s.FB == 5 && !getenv("WF_WARP_NO_BITSLICED_HITS")) s.HB = 7;
+    }
+    s.NP = 7 + s.FB + s.HB + (e->tile ? tile_extra_planes() : 0);
 
     const size_t plane_words = (size_t)s.NP * s.N * s.RS * s.HW;
     const size_t cells = (size_t)s.N * s.W * s.H;
@@ -312,7 +340,7 @@ int64_t wf_launch_count(const wf_env* e) { return e ? e->launches : 0; }
 int64_t wf_state_bytes_per_env(const wf_env* e) {
     if (!e) return 0;
     const DevState& s = e->st;
-    return (int64_t)s.NP * s.RS * s.HW * 4 + (int64_t)s.W * s.H * 4 + WF_NSCALARS * 4;
+    return (int64_t)s.NP * s.RS * s.HW * 4 + (s.HB ? 0 : (int64_t)s.W * s.H * 4) + WF_NSCALARS * 4;
 }
 
 static int check_obs(const void* obs, int32_t dtype) {

@@ -9,6 +9,7 @@
 // tile family: W).  Planes (one-hot cell type + the two flags type cannot express, Q7):
 //     G grass  F fire(type==1)  BT burnt  D dirt  WT water  B burning_cells  I fire_mobility==inf
 //     FU0.. fuel, bit-sliced (FB planes)     S0/S1 heat-source mask, ping-pong (tile family)
+//     HC0.. total hits per cell, bit-sliced (HB planes; warp family with direction-independent quanta only)
 // The `temp` layer is kept as exact per-direction hit counters, one uint32 per cell:
 //     hits[(env * W + x) * H + y] = n_N | n_S << 8 | n_E << 16 | n_W << 24
 // (temp = sum_d n_d * coef[d], environment.py:286-290), touched only where heat arrives.
@@ -45,6 +46,8 @@ struct DevState {
     const WindTable* wind;
     unsigned long long* stats;  // [ST_N]
     int32_t N, W, H, RS, HW, FB, NP;
+    int32_t HB;         // warp family, every wind of the handle uniform: total hit count per cell kept as HB bit planes
+                        // (planes P_FU0 + FB ...) instead of the `hits` array; 0 otherwise
 };
 
 struct StepCfg {

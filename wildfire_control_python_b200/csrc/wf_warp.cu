@@ -12,20 +12,25 @@
 namespace wf {
 
 // Row x of every plane, one register each (constant indices only, so it never leaves the RF).
+constexpr int kHitBits = 7;  // bit-sliced total hit count per cell (<= 4 neighbours x (31 - 1) hits)
+
 template <int FB>
 struct Rows {
     uint32_t G, F, BT, D, WT, B, I;
     uint32_t FU[FB];
+    uint32_t HC[kHitBits];  // only live in the UNI instantiations (dead registers otherwise)
     __device__ __forceinline__ uint32_t get(int p) const {
         switch (p) {
             case P_G: return G; case P_F: return F; case P_BT: return BT; case P_D: return D;
-            case P_WT: return WT; case P_B: return B; case P_I: return I; default: return FU[p - P_FU0];
+            case P_WT: return WT; case P_B: return B; case P_I: return I;
+            default: return p < P_FU0 + FB ? FU[p - P_FU0] : HC[p - P_FU0 - FB];
         }
     }
     __device__ __forceinline__ void set(int p, uint32_t v) {
         switch (p) {
             case P_G: G = v; break; case P_F: F = v; break; case P_BT: BT = v; break; case P_D: D = v; break;
-            case P_WT: WT = v; break; case P_B: B = v; break; case P_I: I = v; break; default: FU[p - P_FU0] = v;
+            case P_WT: WT = v; break; case P_B: B = v; break; case P_I: I = v; break;
+            default: if (p < P_FU0 + FB) FU[p - P_FU0] = v; else HC[p - P_FU0 - FB] = v;
         }
     }
 };
@@ -66,7 +71,7 @@ __device__ __forceinline__ void set_fire(Rows<FB>& r, int x, int fx, int fy) {  
 
 // World.reset -- environment.py:186-212 (+ reset_map :59-95, Agent.__init__ :100-113,
 // get_agent_location utility.py:66-78).  Runs per env group; no warp collectives inside.
-template <int L, int FB>
+template <int L, int FB, bool UNI>
 __device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepCfg& c, const wf_init* init,
                            int env, int x, uint32_t validmask) {
     const int W = s.W, H = s.H;
@@ -83,8 +88,13 @@ __device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepC
     r.F = r.BT = r.D = r.WT = r.B = r.I = 0u;
 #pragma unroll
     for (int k = 0; k < FB; ++k) r.FU[k] = ((c.fuel >> k) & 1) ? validmask : 0u;
-    uint32_t* hits = s.hits + (size_t)env * W * H;
-    for (int i = x; i < W * H; i += L) hits[i] = 0u;  // temp layer := 0
+    if (UNI) {  // temp layer := 0
+#pragma unroll
+        for (int q = 0; q < kHitBits; ++q) r.HC[q] = 0u;
+    } else {
+        uint32_t* hits = s.hits + (size_t)env * W * H;
+        for (int i = x; i < W * H; i += L) hits[i] = 0u;
+    }
 
     const int cx = W / 2, cy = H / 2;  // get_fire_location, utility.py:61-64
     if (c.make_rivers) {               // reset_map :69-95; every lane replays the same draws
@@ -201,7 +211,11 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
     }
 }
 
-template <int L, int FB>
+// UNI: every wind of the handle has direction-independent heat quanta (e.g. wind vector (0, 0)): a cell
+// ignites when its TOTAL hit count reaches kmin, so `temp` is a 7-bit counter per cell, bit-sliced in
+// registers (planes HC0..HC6); heat transfer + ignition test are ~40 word-parallel logic instructions
+// per tick instead of a data-dependent loop over hit counters in memory.
+template <int L, int FB, bool UNI>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, StepCfg c, WarpIO io) {
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     Agent a;
     {
 #pragma unroll
-        for (int p = 0; p < 7 + FB; ++p) r.set(p, valid_env ? s.planes[word_index(s, p, env, x, 0)] : 0u);
+        for (int p = 0; p < 7 + FB + (UNI ? kHitBits : 0); ++p) r.set(p, valid_env ? s.planes[word_index(s, p, env, x, 0)] : 0u);
         int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
         if (valid_env) {
             const int4* sp = reinterpret_cast<const int4*>(s.scal + (size_t)env * WF_NSCALARS);
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
         // ---------------- ForestFire.reset() ----------------
         const bool doit = valid_env && (io.mask == nullptr || io.mask[env] != 0);
         if (doit) {
-            reset_rows<L, FB>(r, a, s, c, io.init, env, x, validmask);
+            reset_rows<L, FB, UNI>(r, a, s, c, io.init, env, x, validmask);
             a.refresh_wind(s.wind);
         }
         __syncwarp();
@@ -381,6 +395,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                 const uint32_t h2 = r.G & up;          // d = E (+1,0): source at x-1
                 const uint32_t h3 = r.G & dn;          // d = W (-1,0): source at x+1
                 uint32_t m = h0 | h1 | h2 | h3, ign = 0u;
+                if (UNI) {
+                    // hits this tick, per cell: h0 + h1 + h2 + h3 as a 3-bit number (s2 s1 s0) ...
+                    const uint32_t x01 = h0 ^ h1, s0 = x01 ^ h2 ^ h3;
+                    const uint32_t c01 = h0 & h1, c23 = h2 & h3, cx = x01 & (h2 ^ h3);
+                    const uint32_t s1 = c01 ^ c23 ^ cx, s2 = c01 & c23;
+                    // ... added to the 7-bit counter (ripple carry) ...
+                    uint32_t k = r.HC[0] & s0;
+                    r.HC[0] ^= s0;
+                    uint32_t t1 = r.HC[1];
+                    r.HC[1] = t1 ^ s1 ^ k;
+                    k = (t1 & s1) | (k & (t1 ^ s1));
+                    t1 = r.HC[2];
+                    r.HC[2] = t1 ^ s2 ^ k;
+                    k = (t1 & s2) | (k & (t1 ^ s2));
+#pragma unroll
+                    for (int q = 3; q < kHitBits; ++q) {
+                        t1 = r.HC[q];
+                        r.HC[q] = t1 ^ k;
+                        k &= t1;
+                    }
+                    // ... and compared with kmin, most significant bit first: ge = (count >= kmin)
+                    const uint32_t km = (uint32_t)min(a.kmin, (1 << kHitBits) - 1);
+                    uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+                    for (int q = kHitBits - 1; q >= 0; --q) {
+                        const uint32_t kb = ((km >> q) & 1u) ? 0xffffffffu : 0u;
+                        gt |= eq & r.HC[q] & ~kb;
+                        eq &= ~(r.HC[q] ^ kb);
+                    }
+                    ign = m & (gt | eq);  // only cells heated this tick can cross the threshold
+                    m = 0u;
+                }
                 uint32_t* hrow = s.hits + ((size_t)(valid_env ? env : 0) * W + x) * H;
                 while (m) {
                     const int y = __ffs(m) - 1;
@@ -464,7 +510,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             }
             // ---- auto-reset (batched-env convention: the returned obs is the new episode's first)
             if (c.auto_reset && act && done) {
-                reset_rows<L, FB>(r, a, s, c, nullptr, env, x, validmask);
+                reset_rows<L, FB, UNI>(r, a, s, c, nullptr, env, x, validmask);
                 a.refresh_wind(s.wind);
             }
             __syncwarp();
@@ -486,7 +532,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     }
     if (valid_env) {
 #pragma unroll
-        for (int p = 0; p < 7 + FB; ++p) s.planes[word_index(s, p, env, x, 0)] = r.get(p);
+        for (int p = 0; p < 7 + FB + (UNI ? kHitBits : 0); ++p) s.planes[word_index(s, p, env, x, 0)] = r.get(p);
         if (x == 0) {
             int4* sp = reinterpret_cast<int4*>(s.scal + (size_t)env * WF_NSCALARS);
             sp[0] = make_int4(a.alive, a.ax, a.ay, a.dead);
@@ -505,10 +551,13 @@ cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO
     const int epw = 32 / L;
     const int envs_per_block = kWarpsPerBlock * epw;
     const dim3 grid((s.N + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
-    if (L == 16 && s.FB == 5) warp_kernel<16, 5><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 16 && s.FB == 8) warp_kernel<16, 8><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 32 && s.FB == 5) warp_kernel<32, 5><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 32 && s.FB == 8) warp_kernel<32, 8><<<grid, block, 0, stream>>>(s, c, io);
+    if (s.HB != 0 && (s.HB != kHitBits || s.FB != 5)) return cudaErrorInvalidValue;
+    if (L == 16 && s.FB == 5 && s.HB) warp_kernel<16, 5, true><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 32 && s.FB == 5 && s.HB) warp_kernel<32, 5, true><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 16 && s.FB == 5) warp_kernel<16, 5, false><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 16 && s.FB == 8) warp_kernel<16, 8, false><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 32 && s.FB == 5) warp_kernel<32, 5, false><<<grid, block, 0, stream>>>(s, c, io);
+    else if (L == 32 && s.FB == 8) warp_kernel<32, 8, false><<<grid, block, 0, stream>>>(s, c, io);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
