@@ -156,8 +156,8 @@ constexpr int kStreamWords = 100;  // 3*32*32/32 = 96 words + spill-over of the 
 
 template <int L>
 __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
-                                         uint32_t* stream, const uint32_t* spread3, int lane, int sub, int x, int W,
-                                         int H, int env0, int n_valid) {
+                                         uint32_t* stream, const uint32_t* spread3, const uint2* tab8, int lane, int sub,
+                                         int x, int W, int H, int env0, int n_valid) {
     // obs_step: start of this step's [N][W][H][3] block; env0: first env of the warp; n_valid: how many
     // of the warp's envs exist.  The warp's envs are adjacent in memory, so they share ONE bit stream.
     const int nbits = W * H * 3;
@@ -192,10 +192,8 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         uint8_t* o8 = static_cast<uint8_t*>(obs_step) + (size_t)env0 * nbits;
         if ((tbits & 7) == 0 && (reinterpret_cast<uintptr_t>(o8) & 7u) == 0) {
             uint2* o64 = reinterpret_cast<uint2*>(o8);  // output bytes 8j..8j+7 = stream bits 8j..8j+7
-            for (int j = lane; j < (tbits >> 3); j += 32) {
-                const uint32_t b8 = (stream[j >> 2] >> ((j & 3) * 8)) & 255u;
-                o64[j] = make_uint2(((b8 & 15u) * 0x00204081u) & 0x01010101u, ((b8 >> 4) * 0x00204081u) & 0x01010101u);
-            }
+            const uint8_t* stream8 = reinterpret_cast<const uint8_t*>(stream);
+            for (int j = lane; j < (tbits >> 3); j += 32) o64[j] = tab8[stream8[j]];  // byte of 8 stream bits -> 8 bytes
         } else if ((tbits & 3) == 0 && (reinterpret_cast<uintptr_t>(o8) & 3u) == 0) {
             uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
             for (int j = lane; j < (tbits >> 2); j += 32) {
@@ -222,11 +220,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
     __shared__ uint32_t stream_all[kWarpsPerBlock][kStreamWords];
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
+    __shared__ uint2 tab8[256];        // bit i of the index -> byte i
     for (int v = threadIdx.x; v < 256; v += blockDim.x) {
         uint32_t o = 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
         spread3[v] = o;
+        tab8[v] = make_uint2(((v & 15u) * 0x00204081u) & 0x01010101u, (((v >> 4) & 15u) * 0x00204081u) & 0x01010101u);
     }
     __syncthreads();
 
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
         __syncwarp();
         if (io.obs != nullptr) {
             emit_obs<L>(io.obs, io.obs_dtype, (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask,
-                        stream_warp, spread3, lane, sub, x, W, H, env0, n_valid);
+                        stream_warp, spread3, tab8, lane, sub, x, W, H, env0, n_valid);
         }
     } else {
         // ---------------- K x ForestFire.step(action) ----------------
@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                     ablk_idx = a.t >> 2;
                 }
                 const uint32_t aw = (a.t & 3u) == 0u ? ablk[0] : (a.t & 3u) == 1u ? ablk[1] : (a.t & 3u) == 2u ? ablk[2] : ablk[3];
-                action = (int)(aw % (uint32_t)c.n_actions);
+                const uint32_t na = (uint32_t)c.n_actions;
+                action = (na & (na - 1u)) == 0u ? (int)(aw & (na - 1u)) : (int)(aw % na);
             }
             if (io.actions_out != nullptr && valid_env && x == 0) io.actions_out[(size_t)k * s.N + env] = action;
             // ---- action: Agent.move :141-155 / toggle_digging :136-138 (agents[0] exists while alive)
@@ -517,8 +518,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             if (io.obs != nullptr) {
                 const size_t step_bytes = (size_t)s.N * W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
                 emit_obs<L>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
-                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, lane,
-                            sub, x, W, H, env0, n_valid);
+                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, tab8,
+                            lane, sub, x, W, H, env0, n_valid);
             }
         }
     }
