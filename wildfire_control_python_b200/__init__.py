@@ -8,7 +8,8 @@ The compute lives in ``libwildfire_b200.so`` (csrc/, sm_100a) behind include/wil
 from . import _lib
 from .constants import METADATA, grass, layer, make_metadata, types
 
-__all__ = ["BatchedForestFire", "ForestFire", "METADATA", "grass", "layer", "types", "make_metadata", "build"]
+__all__ = ["BatchedForestFire", "ForestFire", "METADATA", "grass", "layer", "types", "make_metadata", "build",
+           "DQN", "DQN_SARSA", "DQN_DUEL", "DQN_BOTH"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -22,4 +23,7 @@ def __getattr__(name):  # torch is imported lazily so that `import wildfire_cont
     if name == "ForestFire":
         from .compat import ForestFire
         return ForestFire
+    if name in ("DQN", "DQN_SARSA", "DQN_DUEL", "DQN_BOTH"):
+        from . import agents
+        return getattr(agents, name)
     raise AttributeError(name)

@@ -1,0 +1,601 @@
+"""Torch restatement of the reference's four learners.
+
+    DQN        DQN.py:9-443          Flatten -> Dense(50, sigmoid) -> Dense(n_actions), Adam(lr=alpha, clipvalue=1), MSE,
+                                     replay deque(memory_size), eps-greedy, target network synced every target_update steps
+    DQN_SARSA  DQN_SARSA.py:7-191    on-policy target r + gamma * Q_target(s', a')
+    DQN_DUEL   DQN_DUEL.py:13-48     dueling head  Q = V + (A - mean A)
+    DQN_BOTH   DQN_BOTH.py:4-8       both (same MRO mix-in as the reference)
+
+Same class names, constructor, methods and log format (``Logs/<name>`` JSON readable by the
+reference's analyze.py), so ``main.py -r -t DQN|SARSA|DDQN|BOTH|Baseline`` style loops run against the
+CUDA environment: ``sim`` is ``wildfire_control_python_b200.ForestFire`` (or anything with the
+reference's ``reset / step / render / W.agents / METADATA`` surface).
+
+What is B200-native here: the environment step is the CUDA path behind the C ABI; the replay memory
+lives in device tensors and one ``replay()`` is two batched forward passes of the target network and
+one optimiser step (the reference issues 2 x batch_size single-sample ``predict`` calls, DQN.py:164-176).
+The learning rule itself is unchanged: the regression target of a sample is the TARGET network's
+Q-vector with the taken action's entry replaced (DQN.py:166-176), loss = MSE over all outputs.
+Keras is not a dependency; weights are saved as ``.npz`` with Keras' layer names
+(``dense_1/kernel:0`` ...), kernels in Keras' [in, out] orientation.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import time
+
+import numpy as np
+import torch
+from torch import nn
+
+from .constants import DQN_DEFAULTS
+
+
+class ReplayMemory:
+    """``collections.deque(maxlen=...)`` of transitions (DQN.py:20, :205-206), stored as device tensors.
+
+    ``maxlen=None`` grows without bound, like the plain ``deque()`` collect_memories switches to
+    (DQN.py:290).  Sampling is uniform without replacement (``random.sample``, DQN.py:161).
+    """
+
+    def __init__(self, obs_shape, device, maxlen=None, with_aprime=False):
+        self.maxlen, self.device, self.with_aprime = maxlen, device, with_aprime
+        self.obs_shape = tuple(obs_shape)
+        self._cap = 0
+        self._n = 0       # number of valid entries
+        self._head = 0    # position of the oldest entry once the ring is full
+        self._grow(min(maxlen, 4096) if maxlen else 4096)
+
+    def _grow(self, cap):
+        def buf(shape, dtype):
+            t = torch.zeros((cap,) + shape, dtype=dtype, device=self.device)
+            return t
+        new = dict(s=buf(self.obs_shape, torch.uint8), sp=buf(self.obs_shape, torch.uint8), a=buf((), torch.int64),
+                   ap=buf((), torch.int64), r=buf((), torch.float32), d=buf((), torch.bool))
+        if self._cap:
+            for k, t in new.items():
+                t[: self._cap] = getattr(self, "_" + k)
+        for k, t in new.items():
+            setattr(self, "_" + k, t)
+        self._cap = cap
+
+    def __len__(self):
+        return self._n
+
+    def _as_obs(self, x):
+        t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
+        return t.reshape(self.obs_shape).to(device=self.device, dtype=torch.uint8)
+
+    def append(self, state, action, reward, sprime, done, aprime=0):
+        if self.maxlen is not None and self._n == self.maxlen:
+            i = self._head  # full: the oldest entry is dropped, like deque(maxlen)
+            self._head = (self._head + 1) % self.maxlen
+        else:
+            if self._n == self._cap:
+                self._grow(min(2 * self._cap, self.maxlen) if self.maxlen else 2 * self._cap)
+            i = self._n
+            self._n += 1
+        self._s[i] = self._as_obs(state)
+        self._sp[i] = self._as_obs(sprime)
+        self._a[i], self._ap[i], self._r[i], self._d[i] = int(action), int(aprime), float(reward), bool(done)
+
+    def append_bulk(self, states, actions, rewards, sprimes, dones, aprimes=None):
+        """Append M transitions held in device tensors (unbounded memories only)."""
+        assert self.maxlen is None
+        m = int(actions.shape[0])
+        while self._n + m > self._cap:
+            self._grow(2 * self._cap)
+        sl = slice(self._n, self._n + m)
+        self._s[sl] = states.reshape((m,) + self.obs_shape).to(self.device, torch.uint8)
+        self._sp[sl] = sprimes.reshape((m,) + self.obs_shape).to(self.device, torch.uint8)
+        self._a[sl] = actions.to(self.device, torch.int64)
+        self._ap[sl] = 0 if aprimes is None else aprimes.to(self.device, torch.int64)
+        self._r[sl] = rewards.to(self.device, torch.float32)
+        self._d[sl] = dones.to(self.device, torch.bool)
+        self._n += m
+
+    def sample(self, batch_size):
+        idx = torch.as_tensor(random.sample(range(self._n), batch_size), device=self.device)
+        return (self._s[idx], self._a[idx], self._r[idx], self._sp[idx], self._ap[idx], self._d[idx])
+
+
+class _QNet(nn.Module):
+    """DQN.make_network (DQN.py:209-233): Flatten -> Dense(50, sigmoid) -> Dense(n_actions, linear)."""
+
+    def __init__(self, n_in, n_actions):
+        super().__init__()
+        self.dense_1 = nn.Linear(n_in, 50)
+        self.dense_2 = nn.Linear(50, n_actions)
+        _keras_init(self)
+
+    def forward(self, x):
+        return self.dense_2(torch.sigmoid(self.dense_1(x.flatten(1))))
+
+
+class _DuelNet(nn.Module):
+    """DQN_DUEL.make_network (DQN_DUEL.py:18-48): advantage and value streams, q = v + (a - mean(a))."""
+
+    def __init__(self, n_in, n_actions):
+        super().__init__()
+        self.dense_1 = nn.Linear(n_in, 50)       # advantage stream
+        self.dense_2 = nn.Linear(50, n_actions)
+        self.dense_3 = nn.Linear(n_in, 50)       # value stream
+        self.dense_4 = nn.Linear(50, 1)
+        _keras_init(self)
+
+    def forward(self, x):
+        x = x.flatten(1)
+        adv = self.dense_2(torch.sigmoid(self.dense_1(x)))
+        val = self.dense_4(torch.sigmoid(self.dense_3(x)))
+        return val + (adv - adv.mean(dim=1, keepdim=True))
+
+
+def _keras_init(net):
+    """Keras Dense defaults: glorot_uniform kernel, zero bias."""
+    for m in net.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.zeros_(m.bias)
+
+
+class DQN:
+    def __init__(self, sim, name="no_name", verbose=True, device=None):
+        # Constants and such (DQN.py:10-17)
+        self.sim = sim
+        self.name = name
+        self.METADATA = dict(DQN_DEFAULTS)
+        self.METADATA.update(sim.METADATA)
+        self.action_size = self.sim.n_actions
+        self.DEBUG = getattr(sim, "DEBUG", 1)
+        self.verbose = verbose
+        if device is None:
+            device = getattr(getattr(sim, "_batch", None), "device", None) or ("cuda" if torch.cuda.is_available() else "cpu")
+        self.device = torch.device(device)
+        self.obs_shape = (self.sim.W.WIDTH, self.sim.W.HEIGHT, self.sim.W.DEPTH)
+
+        # DQN memory (DQN.py:20)
+        self.memory = self._new_memory(self.METADATA["memory_size"])
+
+        # Information to save to file (DQN.py:23-32)
+        self.logs = {
+            "best_reward": -10000,
+            "total_rewards": list(),
+            "agent_pos": list(),
+            "agent_deaths": list(),
+            "maps": list(),
+            "init_memories": 0,
+            "total_time": 0,
+            "n_episodes": 0,
+        }
+
+        # DQN parameters (DQN.py:35-41)
+        self.max_eps = self.METADATA["max_eps"]
+        self.min_eps = self.METADATA["min_eps"]
+        self.eps_decay_rate = self.METADATA["eps_decay_rate"]
+        self.eps = self.max_eps
+        self.gamma = self.METADATA["gamma"]
+        self.alpha = self.METADATA["alpha"]
+        self.target_update_freq = self.METADATA["target_update"]
+
+        # Network and target network (DQN.py:44-46)
+        self.model = self.make_network()
+        self.target = self.make_network()
+        self.target.load_state_dict(self.model.state_dict())
+        # Adam(lr=alpha, clipvalue=1) with Keras' epsilon; loss = mse (DQN.py:227-230)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.alpha, eps=1e-7)
+
+        if self.verbose:
+            width, height = self.METADATA["width"], self.METADATA["height"]
+            print("\n\t[Parameters]")
+            print("[decay]", self.METADATA["eps_decay_rate"])
+            print("[alpha]", self.METADATA["alpha"])
+            print("[gamma]", self.METADATA["gamma"])
+            print("[batch]", self.METADATA["batch_size"])
+            print("[size]", f"{width}x{height}")
+            print("[wind speed]", self.METADATA["wind"][0] if self.METADATA["wind"] != "random" else "random")
+            print("[target upd]", self.METADATA["target_update"], "\n")
+
+    # ------------------------------------------------------------------ learning
+    _SARSA = False
+
+    def _new_memory(self, maxlen):
+        return ReplayMemory(self.obs_shape, self.device, maxlen=maxlen, with_aprime=self._SARSA)
+
+    def _as_batch(self, state):
+        """np.reshape(state, [1] + shape) of the reference; a device float tensor here."""
+        t = state if torch.is_tensor(state) else torch.as_tensor(np.asarray(state))
+        return t.reshape((1,) + self.obs_shape).to(device=self.device, dtype=torch.float32)
+
+    def learn(self, n_episodes=1000):  # DQN.py:65-153
+        start_time = time.time()
+        self.logs["n_episodes"] = n_episodes
+        target_update_counter = self.target_update_freq
+        for episode in range(n_episodes):
+            done = False
+            total_reward = 0
+            t0 = time.time()
+            state = self._as_batch(self.sim.reset())
+            if self.DEBUG > 0:
+                self.logs["agent_pos"].append((self.sim.W.agents[0].x, self.sim.W.agents[0].y))
+            while not done:
+                action = self.choose_action(state)
+                sprime, reward, done, _ = self.sim.step(action)
+                sprime = self._as_batch(sprime)
+                self.remember(state, action, reward, sprime, done)
+                if len(self.memory) > self.METADATA["batch_size"]:
+                    self.replay()
+                target_update_counter -= 1
+                if target_update_counter == 0:
+                    target_update_counter = self.target_update_freq
+                    self.target.load_state_dict(self.model.state_dict())
+                state = sprime
+                total_reward += reward
+            self._end_of_episode(episode, total_reward, t0)
+        self.logs["total_time"] = round(time.time() - start_time, 3)
+        self.write_data()
+
+    def _end_of_episode(self, episode, total_reward, t0):  # DQN.py:120-148
+        dead = len(self.sim.W.agents) == 0
+        if self.DEBUG > 0:
+            self.logs["agent_deaths"].append(dead)
+        if total_reward >= 0.9 * self.logs["best_reward"] or total_reward > 300:
+            map_string = self._render_string()
+            if total_reward > self.logs["best_reward"]:
+                self.logs["best_reward"] = total_reward
+            if self.DEBUG > 0:
+                self.logs["maps"].append([episode, map_string])
+        if self.verbose:
+            print(f"[Episode {episode + 1}]\tTime: {round(time.time() - t0, 3)}")
+            print(f"\t\tEpsilon: {round(self.eps, 3)}")
+            print(f"\t\tAgent dead: {dead}")
+            print(f"\t\tReward: {round(total_reward, 0)}\n")
+        self.decay_epsilon(episode)
+        self.logs["total_rewards"].append(total_reward)
+
+    def _render_string(self):
+        try:
+            return self.sim.render(print_map=self.verbose)
+        except TypeError:
+            return self.sim.render()
+
+    def _bootstrap(self, q_next, aprime):
+        """Value of S' used in the target: max_a Q_target(S', a) (DQN.py:174-175)."""
+        return q_next.max(dim=1).values
+
+    def replay_targets(self, batch):
+        """The regression targets of one replay batch (DQN.py:164-180): the target network's Q-vector
+        of S with the taken action's entry replaced by r (terminal) or r + gamma * bootstrap(S')."""
+        s, a, r, sp, ap, d = batch
+        with torch.no_grad():
+            pred = self.target(s.float())
+            boot = self._bootstrap(self.target(sp.float()), ap)
+            upd = torch.where(d, r, r + self.gamma * boot)
+            pred[torch.arange(len(a), device=pred.device), a] = upd
+        return pred
+
+    def replay(self):  # DQN.py:156-185
+        batch = self.memory.sample(self.METADATA["batch_size"])
+        targets = self.replay_targets(batch)
+        loss = nn.functional.mse_loss(self.model(batch[0].float()), targets)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        nn.utils.clip_grad_value_(self.model.parameters(), 1.0)  # Adam(clipvalue=1)
+        self.optimizer.step()
+        return float(loss.detach())
+
+    def choose_action(self, state, eps=None):  # DQN.py:188-196
+        eps_threshold = self.eps if eps is None else eps
+        if random.uniform(0, 1) > eps_threshold:
+            with torch.no_grad():
+                return int(self.model(self._as_batch(state)).argmax(dim=1)[0])
+        return int(np.random.choice(self.METADATA["n_actions"]))
+
+    def decay_epsilon(self, episode_num=None):  # DQN.py:199-202
+        self.eps = self.min_eps + (self.max_eps - self.min_eps) * np.exp(-self.eps_decay_rate * episode_num)
+
+    def remember(self, state, action, reward, sprime, done):  # DQN.py:205-206
+        self.memory.append(state, action, reward, sprime, done)
+
+    def make_network(self):  # DQN.py:209-233
+        return _QNet(int(np.prod(self.obs_shape)), self.action_size).to(self.device)
+
+    # ------------------------------------------------------------------ helpers
+    def play_optimal(self, eps=0, delay=0.1):  # DQN.py:240-253
+        done = False
+        total_reward = 0
+        state = self.sim.reset()
+        while not done:
+            self.sim.render()
+            self.show_info(self._as_batch(state))
+            action = self.choose_action(state, eps=eps)
+            state, reward, done, _ = self.sim.step(action)
+            total_reward += reward
+            time.sleep(delay)
+        self.sim.render()
+        print(f"Total reward: {total_reward}")
+        return total_reward
+
+    def show_info(self, state):  # DQN.py:256-276
+        print(f"Wind Speed: {self.sim.W.wind_speed}")
+        print(f"Wind direction: {self.sim.W.wind_vector}")
+        with torch.no_grad():
+            qvals = self.model(self._as_batch(state))[0].cpu().numpy()
+        key_map = {0: "N", 1: "S", 2: "E", 3: "W", 4: "D", 5: " "}
+        print("| ", end="")
+        for idx, val in enumerate(qvals):
+            val = round(float(val), 2)
+            extra_space = " " if val > 0 else ""
+            print(f"{key_map[idx]} : {extra_space}{val:.2f} | ", end="")
+            if idx == 1:
+                print("\n| ", end="")
+        print(f"\nBest Action: {key_map[int(np.argmax(qvals))]}\n")
+
+    def collect_memories(self, num_of_episodes=100, perform_baseline=False):  # DQN.py:286-348
+        """Demonstration data: walk clockwise round the fire; keep only the episodes that contain it.
+        With ``perform_baseline`` nothing is stored: the heuristic policy is just evaluated."""
+        if not num_of_episodes:
+            return
+        self.memory = self._new_memory(None)  # `self.memory = deque()`: unbounded (DQN.py:290)
+        success_count = 0
+        episode = 0
+        while True:
+            total_reward = 0
+            memories = list()
+            done = False
+            state = self._as_batch(self.sim.reset())
+            while not done:
+                action = self.choose_randomwalk_action()
+                sprime, reward, done, _ = self.sim.step(action)
+                sprime = self._as_batch(sprime)
+                memories.append((state, action, reward, sprime, done))
+                state = sprime
+                total_reward += reward
+                if not perform_baseline and reward == self.METADATA["contained_bonus"]:
+                    success_count += 1
+                    for m in memories:
+                        self.remember(*m)
+                    done = True
+                    if success_count == num_of_episodes:
+                        self.logs["init_memories"] = len(self.memory)
+                        return
+            if perform_baseline:
+                self.logs["total_rewards"].append(total_reward)
+                if self.verbose and episode % 100 == 0:
+                    print(f"Episode {episode}/{num_of_episodes}")
+                self.logs["agent_deaths"].append(len(self.sim.W.agents) == 0)
+                if episode == num_of_episodes - 1:
+                    self.logs["n_episodes"] = num_of_episodes
+                    break
+                episode += 1
+        self.write_data()
+
+    def collect_memories_batched(self, num_of_episodes=100, n_envs=1024, k_steps=256, seed=0):
+        """``collect_memories`` (DQN.py:286-348, DQN_SARSA.py:148-191) over ``n_envs`` environments at once:
+        the heuristic walk policy runs ON THE DEVICE (``wf_rollout_policy``), whole rollouts of ``k_steps`` steps
+        per launch, and the transitions of the episodes that contain the fire (from their reset up to and
+        including the step that pays the containment bonus) are gathered into the replay memory.
+        Only episodes that start in the first half of a rollout are considered, so that slow containments
+        are not under-represented; an episode still undecided at the end of its rollout is dropped.
+        Returns the number of environment steps simulated."""
+        from .batched import BatchedForestFire
+        from .constants import DQN_DEFAULTS as _D
+        if not num_of_episodes:
+            return 0
+        keys = {k: v for k, v in self.METADATA.items() if k not in _D and k not in ("debug", "a_speed_iter", "seed", "auto_reset")}
+        env = BatchedForestFire(n_envs, device=self.device if self.device.type == "cuda" else None, auto_reset=True, seed=seed, **keys)
+        bonus = self.METADATA["contained_bonus"]
+        self.memory = self._new_memory(None)
+        success, simulated = 0, 0
+        try:
+            while success < num_of_episodes:
+                obs0 = env.reset().clone()
+                obs, rew, done, acts = env.rollout(k_steps, policy="walk", return_actions=True)
+                simulated += k_steps * n_envs
+                rew_c, done_c = rew.cpu().numpy(), done.cpu().numpy()
+                t_idx, e_idx = [], []
+                for i in range(n_envs):
+                    bounds = list(np.nonzero(done_c[:, i])[0]) + [k_steps - 1]
+                    start = 0
+                    for end in bounds:
+                        if start >= k_steps // 2 or start > end:
+                            break
+                        hit = np.nonzero(rew_c[start:end + 1, i] == bonus)[0]
+                        if len(hit):
+                            t_idx.append(np.arange(start, start + hit[0] + 1))
+                            e_idx.append(np.full(hit[0] + 1, i))
+                            success += 1
+                            if success == num_of_episodes:
+                                break
+                        start = end + 1
+                    if success == num_of_episodes:
+                        break
+                if t_idx:
+                    t = torch.as_tensor(np.concatenate(t_idx), device=obs.device)
+                    e = torch.as_tensor(np.concatenate(e_idx), device=obs.device)
+                    prev = torch.where((t > 0)[:, None, None, None], obs[(t - 1).clamp(min=0), e], obs0[e])
+                    nxt = acts[(t + 1).clamp(max=k_steps - 1), e]
+                    self.memory.append_bulk(prev, acts[t, e], rew[t, e], obs[t, e], done[t, e], nxt if self._SARSA else None)
+        finally:
+            env.close()
+        self.logs["init_memories"] = len(self.memory)
+        return simulated
+
+    def choose_randomwalk_action(self, avoid_fire=True):  # DQN.py:353-389
+        if not self.sim.W.agents:
+            return 0
+        key_map = {"N": 0, "S": 1, "E": 2, "W": 3}
+        width, height = self.sim.W.WIDTH, self.sim.W.HEIGHT
+        agent_x, agent_y = self.sim.W.agents[0].x, self.sim.W.agents[0].y
+        mid_x, mid_y = (int(width / 2), int(height / 2))
+        count = 0
+        while True:
+            if agent_x >= mid_x and agent_y > mid_y:
+                possible_actions = ["S", "W"]
+            if agent_x > mid_x and agent_y <= mid_y:
+                possible_actions = ["S", "E"]
+            if agent_x <= mid_x and agent_y < mid_y:
+                possible_actions = ["N", "E"]
+            if agent_x < mid_x and agent_y >= mid_y:
+                possible_actions = ["N", "W"]
+            action = key_map[np.random.choice(possible_actions)]
+            if not avoid_fire:
+                break
+            fire_at_loc = self.sim.W.agents[0].fire_in_direction(action)
+            if not fire_at_loc or count > 10:
+                break
+            count += 1
+        return action
+
+    # ------------------------------------------------------------------ persistence
+    out_dir = "."  # Logs/ and Models/ are created below this directory (the reference uses the cwd)
+
+    def write_data(self):  # DQN.py:392-424
+        self.logs["metadata"] = self.METADATA
+        n_episodes = self.logs["n_episodes"]
+        n_episodes = n_episodes / 1000 if n_episodes >= 1000 else 0
+        memories = self.logs["init_memories"]
+        name = self.sim.get_name(self.sim.W.WIDTH, int(n_episodes), memories, self.name)
+        logs_dir, models_dir = os.path.join(self.out_dir, "Logs"), os.path.join(self.out_dir, "Models")
+        counter = 0
+        while os.path.isfile(os.path.join(logs_dir, name)) or os.path.isfile(os.path.join(models_dir, name + ".npz")):
+            if counter > 0:
+                name = name[: -len(str(counter))]
+            name = name + str(counter)
+            counter += 1
+        os.makedirs(logs_dir, exist_ok=True)
+        os.makedirs(models_dir, exist_ok=True)
+        self.save_model(name)
+        with open(os.path.join(logs_dir, name), "w") as file:
+            json.dump(self.logs, file, default=_jsonable)
+        return name
+
+    def get_weights(self):
+        """Keras-style weight dict: ``dense_k/kernel:0`` [in, out] and ``dense_k/bias:0``."""
+        out = {}
+        for lname, m in self.model.named_children():
+            out[f"{lname}/kernel:0"] = m.weight.detach().t().contiguous().cpu().numpy()
+            out[f"{lname}/bias:0"] = m.bias.detach().cpu().numpy()
+        return out
+
+    def set_weights(self, weights):
+        with torch.no_grad():
+            for lname, m in self.model.named_children():
+                m.weight.copy_(torch.as_tensor(np.asarray(weights[f"{lname}/kernel:0"])).t())
+                m.bias.copy_(torch.as_tensor(np.asarray(weights[f"{lname}/bias:0"])))
+        self.target.load_state_dict(self.model.state_dict())
+
+    def save_model(self, name):  # DQN.py:441-443
+        path = os.path.join(self.out_dir, "Models", name)
+        np.savez(path, **self.get_weights())
+        return path + ".npz"
+
+    def load_model(self, path=None):  # DQN.py:427-438 (interactive when no path is given)
+        if path is None:
+            all_names = sorted(os.listdir(os.path.join(self.out_dir, "Models")))
+            print("\nChoose a model from the list below to load:")
+            for idx, n in enumerate(all_names):
+                print(f"\t[{idx}] {n}")
+            try:
+                path = os.path.join(self.out_dir, "Models", all_names[int(input(f"Select one [0-{len(all_names) - 1}]: \n"))])
+            except (ValueError, IndexError):
+                print("Invalid Selection")
+                return
+        with np.load(path) as z:
+            self.set_weights({k: z[k] for k in z.files})
+        if self.verbose:
+            print("Model loaded!")
+
+
+def _jsonable(o):
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    if isinstance(o, (np.bool_,)):
+        return bool(o)
+    raise TypeError(f"not JSON serialisable: {type(o)}")
+
+
+class DQN_SARSA(DQN):
+    _SARSA = True
+
+    def __init__(self, sim, name="no_name", verbose=True, device=None):
+        DQN.__init__(self, sim, name, verbose, device)
+
+    def learn(self, n_episodes=1000):  # DQN_SARSA.py:12-100
+        start_time = time.time()
+        self.logs["n_episodes"] = n_episodes
+        target_update_counter = self.target_update_freq
+        for episode in range(n_episodes):
+            done = False
+            total_reward = 0
+            t0 = time.time()
+            state = self._as_batch(self.sim.reset())
+            action = self.choose_action(state)
+            while not done:
+                sprime, reward, done, _ = self.sim.step(action)
+                sprime = self._as_batch(sprime)
+                aprime = self.choose_action(sprime)
+                self.remember(state, action, reward, sprime, aprime, done)
+                if len(self.memory) > self.METADATA["batch_size"]:
+                    self.replay()
+                target_update_counter -= 1
+                if target_update_counter == 0:
+                    target_update_counter = self.target_update_freq
+                    self.target.load_state_dict(self.model.state_dict())
+                state = sprime
+                action = aprime
+                total_reward += reward
+            self._end_of_episode(episode, total_reward, t0)
+        self.logs["total_time"] = round(time.time() - start_time, 3)
+        self.write_data()
+
+    def _bootstrap(self, q_next, aprime):
+        """On-policy value of S': Q_target(S', A') (DQN_SARSA.py:120-121)."""
+        return q_next.gather(1, aprime[:, None])[:, 0]
+
+    def remember(self, state, action, reward, sprime, aprime, done):  # DQN_SARSA.py:134-135
+        self.memory.append(state, action, reward, sprime, done, aprime)
+
+    def collect_memories(self, num_of_successes=100):  # DQN_SARSA.py:148-191
+        if not num_of_successes:
+            return
+        self.memory = self._new_memory(None)
+        success_count = 0
+        while True:
+            memories = []
+            done = False
+            state = self._as_batch(self.sim.reset())
+            action = self.choose_randomwalk_action()
+            while not done:
+                sprime, reward, done, _ = self.sim.step(action)
+                sprime = self._as_batch(sprime)
+                aprime = self.choose_randomwalk_action()
+                memories.append((state, action, reward, sprime, aprime, done))
+                state = sprime
+                action = aprime
+                if reward == self.METADATA["contained_bonus"]:
+                    success_count += 1
+                    for m in memories:
+                        self.remember(*m)
+                    done = True
+                    if success_count == num_of_successes:
+                        self.logs["init_memories"] = len(self.memory)
+                        return
+
+
+class DQN_DUEL(DQN):
+    def __init__(self, sim, name="no_name", verbose=True, device=None):
+        DQN.__init__(self, sim, name, verbose, device)
+
+    def make_network(self):  # DQN_DUEL.py:18-48
+        return _DuelNet(int(np.prod(self.obs_shape)), self.action_size).to(self.device)
+
+
+class DQN_BOTH(DQN_SARSA, DQN_DUEL):  # DQN_BOTH.py:4-8
+    def __init__(self, sim, name="no_name", verbose=True, device=None):
+        DQN_SARSA.__init__(self, sim, name, verbose, device)

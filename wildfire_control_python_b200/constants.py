@@ -1,6 +1,7 @@
 """Environment parameters -- same key names and defaults as the reference's module-global
 ``METADATA`` dict (Simulation/constants.py:30-47) and ``grass`` cell parameters
-(Simulation/utility.py:94-102).  The DQN hyper-parameters of that dict are out of scope.
+(Simulation/utility.py:94-102).  The DQN hyper-parameters of that dict (constants.py:48-56) are
+carried along for the learners of ``agents.py``; the environment ignores them.
 
 Unlike the reference (WIDTH/HEIGHT frozen at import, environment.py:22-23) the size is an
 ordinary per-instance parameter here.
@@ -28,6 +29,18 @@ METADATA = {
     "allow_dig_toggle": False,
 }
 
+# DQN parameters (Simulation/constants.py:48-56), read by agents.py only
+DQN_DEFAULTS = {
+    "memory_size": 20000,
+    "max_eps": 1.0,
+    "min_eps": 0.01,
+    "eps_decay_rate": 0.005,
+    "gamma": 0.999,
+    "alpha": 0.005,
+    "target_update": 20,
+    "batch_size": 32,
+}
+
 grass = {"heat": 0.3, "fuel": 20, "threshold": 3, "radius": 1}
 
 # Simulation/utility.py:115-140
@@ -44,6 +57,7 @@ EXTRA_DEFAULTS = {"seed": 0, "extra_ignitions": 0, "auto_reset": False, "env_id_
 
 def make_metadata(**overrides) -> dict:
     m = dict(METADATA)
+    m.update(DQN_DEFAULTS)
     m.update(grass)
     m.update(EXTRA_DEFAULTS)
     if "size" in overrides:
