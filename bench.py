@@ -10,9 +10,9 @@ ACTION stream, auto-reset on done).  Prints one JSON line (rank 0); DESIGN.md se
 every field.
 
   value         device-resident throughput over EXACTLY K timed steps (CUDA events, max over ranks).
-                warp family: fused wf_rollout launches of `steps_per_launch` steps; tile family: a
-                CUDA-graph replay of `steps_per_graph_replay` steps.  Obs/reward/done of EVERY step are
-                written to HBM into a buffer larger than L2.
+                Both families run `steps_per_launch` steps per wf_rollout launch (warp family: state in
+                registers; tile family: one thread-block cluster per env).  Obs/reward/done of EVERY step
+                are written to HBM into a buffer larger than L2.
   e2e           the same metric through the host-buffer C-ABI call wf_step_host (page-locked host
                 buffers): per step actions H2D, step, obs + reward + done D2H, synchronise; wall clock.
   per_step_launch   one wf_step per step with device-resident actions (Python loop, and CUDA graph).
@@ -224,7 +224,7 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, no_graph: bool,
     launches = env.launch_count - launches0 + (replays[0] - replays0) * launches_per_chunk
     res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": K, "chunk": chunk, "fused": fused, "graph": graph is not None,
            "ms": ms_max, "launches": int(launches), "value": world * N * K / (ms_max * 1e-3),
-           "obs_mb": obs_buf.numel() / 1e6, "family": env.kernel_family}
+           "obs_mb": obs_buf.numel() / 1e6, "family": env.kernel_family, "state_bytes": env.state_bytes_per_env}
 
     if with_per_step:
         Kp = min(K, 2000)
@@ -342,6 +342,7 @@ def measure_policy(D: Dist, name: str, K: int, Wm: int):
     Kt = reps * G_STEPS
     res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": Kt, "chunk": 1, "fused": True, "graph": True, "ms": ms,
            "launches": Kt, "value": world * N * Kt / (ms * 1e-3), "obs_mb": obs.numel() / 1e6, "family": env.kernel_family,
+           "state_bytes": env.state_bytes_per_env,
            "stats": env.stats(), "policy": "torch MLP 588-50(sigmoid)-4, eps-greedy 0.1, inside a 16-step CUDA graph"}
     env.close()
     return res
@@ -353,10 +354,11 @@ def roofline_of(res, world):
     per_gpu_steps = res["value"] / world
     achieved = per_gpu_steps * W * H * BYTES_PER_CELL_UPDATE / 1e9
     if res["family"] == "warp":  # state stays in registers across a launch: only outputs (+ state once per launch) touch HBM
-        own = W * H * 3 + 8 + 1 + 2 * 1616 / res["chunk"]
+        own = W * H * 3 + 8 + 1 + 2 * res["state_bytes"] / res["chunk"]
         kernel = "wf::warp_kernel"
-        note = ("c2 state (4096 envs x 1.6 KB) lives in registers/L2: this kernel is issue/latency-bound "
-                "(ncu: DRAM 7 %, issue slots 52 %); the HBM roofline is reported because the contract asks for it")
+        note = (f"state ({N} envs x {res['state_bytes']} B) lives in registers across a launch and in L2 between launches: "
+                "this kernel is issue/latency-bound (ncu r01: DRAM 7 %, issue slots 50 %, 2 048 warps for 592 scheduler "
+                "slots); the HBM roofline is reported because the contract asks for it")
     else:  # dense pass per step: G, B, S read + S_next written (tick), F, I read + 96 B written (observation) per 32 cells
         own = W * H * (3 * 4 / 32 + 4 / 32 + 2 * 4 / 32 + 3)
         kernel = "wf::tile_rollout_kernel"
