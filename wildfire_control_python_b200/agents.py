@@ -486,6 +486,52 @@ class DQN:
                 m.bias.copy_(torch.as_tensor(np.asarray(weights[f"{lname}/bias:0"])))
         self.target.load_state_dict(self.model.state_dict())
 
+    def load_keras_weights(self, path):
+        """Load a network trained by the REFERENCE: a Keras ``save_weights`` HDF5 file from its ``Models/``
+        tree (DQN.py:441-443), read without h5py/Keras by ``keras_h5.read_keras_weights``."""
+        from .keras_h5 import canonical_dense_names, read_keras_weights
+        self.set_weights(canonical_dense_names(read_keras_weights(path)))
+
+    def evaluate_batched(self, n_envs=4096, episodes_per_env=1, eps=None, seed=0, max_steps=100000):
+        """Roll the current policy out on ``n_envs`` CUDA environments at once (eps-greedy, DQN.py:188-196) and
+        return (total reward, agent died) of the first ``episodes_per_env`` episodes of every env -- the
+        quantity ``logs['total_rewards']`` / ``logs['agent_deaths']`` hold per training episode."""
+        from .batched import BatchedForestFire
+        from .constants import DQN_DEFAULTS as _D
+        eps = self.min_eps if eps is None else eps
+        keys = {k: v for k, v in self.METADATA.items() if k not in _D and k not in ("debug", "a_speed_iter", "seed", "auto_reset")}
+        env = BatchedForestFire(n_envs, device=self.device, auto_reset=True, seed=seed, **keys)
+        dev = self.device
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        returns = torch.zeros((n_envs, episodes_per_env), dtype=torch.float64, device=dev)
+        died = torch.zeros((n_envs, episodes_per_env), dtype=torch.bool, device=dev)
+        acc = torch.zeros(n_envs, dtype=torch.float64, device=dev)
+        n_done = torch.zeros(n_envs, dtype=torch.int64, device=dev)
+        rows = torch.arange(n_envs, device=dev)
+        death_penalty = float(self.METADATA["death_penalty"])
+        try:
+            obs = env.reset()
+            for step in range(max_steps):
+                with torch.no_grad():
+                    greedy = self.model(obs.float()).argmax(dim=1).to(torch.int32)
+                explore = torch.rand(n_envs, device=dev, generator=gen) < eps
+                rnd = torch.randint(0, self.action_size, (n_envs,), device=dev, dtype=torch.int32, generator=gen)
+                obs, rew, done, _ = env.step(torch.where(explore, rnd, greedy))
+                acc += rew
+                live = done & (n_done < episodes_per_env)
+                slot = n_done.clamp(max=episodes_per_env - 1)
+                returns[rows[live], slot[live]] = acc[live]
+                died[rows[live], slot[live]] = rew[live] == death_penalty
+                acc = torch.where(done, torch.zeros_like(acc), acc)
+                n_done += done.to(torch.int64)
+                if step % 16 == 15 and bool((n_done >= episodes_per_env).all()):
+                    break
+            else:
+                raise RuntimeError("evaluate_batched: some episodes did not finish")
+        finally:
+            env.close()
+        return returns.flatten().cpu().numpy(), died.flatten().cpu().numpy()
+
     def save_model(self, name):  # DQN.py:441-443
         path = os.path.join(self.out_dir, "Models", name)
         np.savez(path, **self.get_weights())
