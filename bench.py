@@ -300,11 +300,22 @@ def measure_policy(D: Dist, name: str, K: int, Wm: int):
     N, W, H = wl["n_envs"], wl["meta"]["width"], wl["meta"]["height"]
     env = BatchedForestFire(N, device=dev, auto_reset=True, seed=0, env_id_base=rank * N, **wl["meta"])
     obs = env.reset()
-    g = torch.Generator(device=dev).manual_seed(1234)  # same weights on every rank
-    w1 = torch.randn(W * H * 3, 50, device=dev, generator=g) * 0.05
-    b1 = torch.zeros(50, device=dev)
-    w2 = torch.randn(50, env.n_actions, device=dev, generator=g) * 0.05
-    b2 = torch.zeros(env.n_actions, device=dev)
+    # The policy: a network the REFERENCE trained (Models/14-sized/SARSA9-..., read by keras_h5 without h5py; the
+    # file travels as a test fixture), else fixed-seed random weights of the same architecture.
+    wpath = os.path.join(ROOT, "tests", "golden", "keras", "SARSA9-14s-10k-47298m-06-24-0808")
+    if os.path.isfile(wpath) and (W, H) == (14, 14):
+        from wildfire_control_python_b200.keras_h5 import read_keras_weights
+        kw = read_keras_weights(wpath)
+        w1, b1, w2, b2 = (torch.as_tensor(kw[k]).to(dev) for k in
+                          ("dense_1/kernel:0", "dense_1/bias:0", "dense_2/kernel:0", "dense_2/bias:0"))
+        policy_name = "the reference's trained DQN_SARSA network SARSA9-14s-10k-47298m (Keras weights)"
+    else:
+        g = torch.Generator(device=dev).manual_seed(1234)  # same weights on every rank
+        w1 = torch.randn(W * H * 3, 50, device=dev, generator=g) * 0.05
+        b1 = torch.zeros(50, device=dev)
+        w2 = torch.randn(50, env.n_actions, device=dev, generator=g) * 0.05
+        b2 = torch.zeros(env.n_actions, device=dev)
+        policy_name = "random-weight network"
     actions = torch.zeros(N, dtype=torch.int32, device=dev)
     gen = torch.Generator(device=dev).manual_seed(77 + rank)
 
@@ -343,7 +354,8 @@ def measure_policy(D: Dist, name: str, K: int, Wm: int):
     res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": Kt, "chunk": 1, "fused": True, "graph": True, "ms": ms,
            "launches": Kt, "value": world * N * Kt / (ms * 1e-3), "obs_mb": obs.numel() / 1e6, "family": env.kernel_family,
            "state_bytes": env.state_bytes_per_env,
-           "stats": env.stats(), "policy": "torch MLP 588-50(sigmoid)-4, eps-greedy 0.1, inside a 16-step CUDA graph"}
+           "stats": env.stats(),
+           "policy": f"torch MLP 588-50(sigmoid)-4 = {policy_name}, eps-greedy 0.1, inside a 16-step CUDA graph"}
     env.close()
     return res
 
