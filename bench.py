@@ -349,13 +349,34 @@ def measure_policy(D: Dist, name: str, K: int, Wm: int):
         graph.replay()
     ev1.record()
     D.barrier()
+    ms_torch = D.max_over_ranks(ev0.elapsed_time(ev1))
+    Kt_torch = reps * G_STEPS
+    via_torch = {"value": world * N * Kt_torch / (ms_torch * 1e-3), "unit": "env-steps/s", "steps": Kt_torch,
+                 "us_per_step": ms_torch * 1e3 / Kt_torch,
+                 "how": "obs -> float -> torch MLP -> eps-greedy -> wf_step, 16 steps per CUDA-graph replay"}
+    # The same policy evaluated INSIDE the step kernel (WF_POLICY_MLP): first layer kept incrementally as a sum of
+    # weight rows of the observation bits, 64 steps per launch, obs/reward/done of every step still written.
+    chunk = 64
+    env.set_policy_mlp(w1, b1, w2, b2, eps=0.1)
+    out = (torch.empty((chunk, N, W, H, 3), dtype=torch.uint8, device=dev), torch.empty((chunk, N), dtype=torch.float64, device=dev),
+           torch.empty((chunk, N), dtype=torch.uint8, device=dev))
+    nl = max(1, K // chunk)
+    for _ in range(max(1, Wm // chunk) + 2):
+        env.rollout(chunk, policy="mlp", out=out)
+    D.barrier()
+    l0 = env.launch_count
+    ev0.record()
+    for _ in range(nl):
+        env.rollout(chunk, policy="mlp", out=out)
+    ev1.record()
+    D.barrier()
     ms = D.max_over_ranks(ev0.elapsed_time(ev1))
-    Kt = reps * G_STEPS
-    res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": Kt, "chunk": 1, "fused": True, "graph": True, "ms": ms,
-           "launches": Kt, "value": world * N * Kt / (ms * 1e-3), "obs_mb": obs.numel() / 1e6, "family": env.kernel_family,
-           "state_bytes": env.state_bytes_per_env,
-           "stats": env.stats(),
-           "policy": f"torch MLP 588-50(sigmoid)-4 = {policy_name}, eps-greedy 0.1, inside a 16-step CUDA graph"}
+    Kt = nl * chunk
+    res = {"name": name, "wl": wl, "N": N, "W": W, "H": H, "K": Kt, "chunk": chunk, "fused": True, "graph": False, "ms": ms,
+           "launches": env.launch_count - l0, "value": world * N * Kt / (ms * 1e-3), "obs_mb": out[0].numel() / 1e6,
+           "family": env.kernel_family, "state_bytes": env.state_bytes_per_env, "stats": env.stats(), "via_torch": via_torch,
+           "policy": f"MLP 588-50(sigmoid)-4 = {policy_name}, eps-greedy 0.1, evaluated inside the step kernel (WF_POLICY_MLP); "
+                     "`via_torch` is the same policy through torch ops"}
     env.close()
     return res
 
@@ -436,6 +457,7 @@ def run_ours(args, wl):
     if "policy" in res:
         line["config"]["policy"] = res["policy"]
         line["steps"] = res["K"]
+        line["via_torch"] = res["via_torch"]
     if sec is not None:
         line["secondary"] = {"c4": {
             "workload": WORKLOADS["c4"]["desc"], "value": sec["value"], "unit": "env-steps/s", "steps": sec["K"],

@@ -123,13 +123,25 @@ int wf_rollout(wf_env* env, int32_t k_steps, const int32_t* actions_dev, void* o
 /* Action sources of wf_rollout_policy. */
 enum {
     WF_POLICY_STREAM = 0, /* uniform random action from the ACTION stream (same as wf_rollout with NULL actions) */
-    WF_POLICY_WALK = 1    /* the reference's heuristic "walk round the fire" demonstration / Baseline policy:
+    WF_POLICY_WALK = 1,   /* the reference's heuristic "walk round the fire" demonstration / Baseline policy:
                              DQN.choose_randomwalk_action, DQN.py:353-389 (draws from the POLICY stream) */
+    WF_POLICY_MLP = 2     /* the reference's Q-network evaluated inside the step kernel, eps-greedy
+                             (DQN.choose_action DQN.py:188-196 on DQN.make_network DQN.py:209-233);
+                             weights from wf_set_policy_mlp; grids up to 32x32 only */
 };
 /* wf_rollout with the actions chosen on the device by a built-in policy (DQN.collect_memories' inner loop,
  * DQN.py:303-308: choose_randomwalk_action -> sim.step).  actions_out_dev: [K][N] int32 or NULL. */
 int wf_rollout_policy(wf_env* env, int32_t k_steps, int32_t policy, int32_t* actions_out_dev, void* obs_dev,
                       int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream);
+
+/* The network of WF_POLICY_MLP: Flatten(W,H,3) -> Dense(hidden, sigmoid) -> Dense(n_actions, linear), Keras
+ * orientation (kernel[in][out], in = (x*H + y)*3 + channel).  Host pointers; copied.  For the dueling
+ * head (DQN_DUEL.py:18-48) pass the ADVANTAGE stream: argmax_a (V + A_a - mean A) = argmax_a A_a.
+ * eps: probability of a uniformly random action instead of the greedy one (EXPLORE Philox stream:
+ * step t uses words 2*(t&1), 2*(t&1)+1 of block t>>1: explore iff word < eps * 2^32, action = word' % n_actions).
+ * hidden <= 64, n_actions <= 8. */
+int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1_host, const float* kernel2_host,
+                      const float* bias2_host, int32_t hidden, double eps);
 
 /* Host-buffer variant of wf_step (what a CPU-side caller of the reference would bind):
  * copies actions H2D, steps, copies obs/reward/done D2H and synchronises.  Buffers should

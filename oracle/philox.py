@@ -18,6 +18,8 @@ replace those draws by this stream:
     stream 2   = IGNITE  index = k-th extra ignition, words 0/1 -> (x, y)
     stream 3   = POLICY  draws of the heuristic walk policy (DQN.py:353-389) at step t:
                  draw j (j < 12) is word (j & 3) of the block with index = 3 * t + (j >> 2)
+    stream 4   = EXPLORE eps-greedy of the in-kernel Q-network at step t: words 2*(t & 1), 2*(t & 1) + 1
+                 of the block with index = t >> 1  (explore iff word < eps * 2^32; action = word' % n_actions)
     a draw u picks ``seq[u % len(seq)]``;  randint(a, b) -> a + u % (b - a + 1)
 """
 from __future__ import annotations
@@ -32,6 +34,7 @@ STREAM_RESET = 0
 STREAM_ACTION = 1
 STREAM_IGNITE = 2
 STREAM_POLICY = 3
+STREAM_EXPLORE = 4
 
 
 def philox4x32_10(ctr, key):
@@ -61,6 +64,12 @@ def action_draw(seed: int, env_id: int, episode: int, t: int) -> int:
 
 def policy_draw(seed: int, env_id: int, episode: int, t: int, j: int) -> int:
     return philox4x32_10((env_id, episode, 3 * t + (j >> 2), STREAM_POLICY), seed_key(seed))[j & 3]
+
+
+def explore_draw(seed: int, env_id: int, episode: int, t: int):
+    """eps-greedy draws of the in-kernel Q-network at step t: (explore word, random-action word)."""
+    w = philox4x32_10((env_id, episode, t >> 1, STREAM_EXPLORE), seed_key(seed))
+    return (w[2], w[3]) if (t & 1) else (w[0], w[1])
 
 
 def ignite_draw(seed: int, env_id: int, episode: int, k: int):

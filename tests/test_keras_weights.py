@@ -114,9 +114,68 @@ def test_reference_policy_earns_its_logged_return_on_the_cuda_env(name):
     sim = ForestFire(width=meta["size"], height=meta["size"], seed=1)
     ag = cls(sim, verbose=False)
     ag.load_keras_weights(os.path.join(HERE, name))
-    rets, died = ag.evaluate_batched(n_envs=8192, episodes_per_env=2, eps=log["min_eps"], seed=3)
+    rets, died = ag.evaluate_batched(n_envs=8192, episodes_per_env=2, eps=log["min_eps"], seed=3)  # Q-network in the step kernel
+    rets_t, died_t = ag.evaluate_batched(n_envs=4096, episodes_per_env=1, eps=log["min_eps"], seed=4, in_kernel=False)  # via torch
     se = rets.std() / np.sqrt(len(rets))
     assert len(rets) == 16384 and se < 6
+    assert abs(rets_t.mean() - rets.mean()) < 5 * (se + rets_t.std() / np.sqrt(len(rets_t)))
+    assert abs(died_t.mean() - died.mean()) < 0.015
     # the log's own figure is an average over 2500 episodes of a still-changing policy: +-25 covers its noise
     assert abs(rets.mean() - log["mean_last_2500"]) < 4 * se + 25, (rets.mean(), se, log["mean_last_2500"])
     assert abs(died.mean() - log["death_rate_last_2500"]) < 0.02, (died.mean(), log["death_rate_last_2500"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,eps", [(sorted(KAT)[0], 0.05), (sorted(KAT)[1], 0.0), (sorted(KAT)[1], 0.3)])
+def test_in_kernel_q_network_chooses_the_reference_networks_actions(name, eps):
+    """WF_POLICY_MLP: the step kernel evaluates the Q-network itself (first layer kept incrementally as a sum of
+    weight rows).  Every chosen action is checked against a float64 evaluation of the same weights on the
+    observation the policy saw -- greedy steps must pick a maximiser of Q (up to float32 rounding), explored
+    steps must follow the shared EXPLORE Philox stream -- and the trajectory against the oracle."""
+    import torch
+    from oracle import philox
+    from oracle import wf_oracle as wo
+    from tests.gpu_util import make_pair, to_np
+    meta = KAT[name]
+    size = meta["size"]
+    cfg = dict(width=size, height=size, seed=77)
+    w = {k: v.astype(np.float64) for k, v in read_keras_weights(os.path.join(HERE, name)).items()}
+    N, K = 67, 300
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    gpu.set_policy_mlp(w["dense_1/kernel:0"], w["dense_1/bias:0"], w["dense_2/kernel:0"], w["dense_2/bias:0"], eps=eps)
+    obs0 = to_np(gpu.reset())
+    for e in orc:
+        e.reset()
+    obs, rew, done, acts = gpu.rollout(K, policy="mlp", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    eps_u32 = 0xFFFFFFFF if eps >= 1.0 else int(eps * 4294967296.0)
+
+    def qvals(o):
+        x = o.reshape(-1).astype(np.float64)
+        return (1.0 / (1.0 + np.exp(-np.clip(x @ w["dense_1/kernel:0"] + w["dense_1/bias:0"], -60, 60)))) @ w["dense_2/kernel:0"] \
+            + w["dense_2/bias:0"]
+
+    n_explored = n_greedy = n_ties = 0
+    for i, e in enumerate(orc):
+        episode, t = 0, 0
+        for k in range(K):
+            seen = obs0[i] if k == 0 else obs[k - 1, i]
+            u0, u1 = philox.explore_draw(cfg["seed"], i, episode, t)
+            a = int(acts[k, i])
+            if u0 < eps_u32:
+                assert a == u1 % 4, (i, k)
+                n_explored += 1
+            else:
+                q = qvals(seen)
+                assert q[a] >= q.max() - 1e-3 * max(1.0, abs(q.max())), (i, k, a, q)
+                n_ties += int(a != int(np.argmax(q)))
+                n_greedy += 1
+            o, r, d, _ = e.step(a)
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k)
+            t += 1
+            if d:
+                o = e.reset()
+                episode, t = episode + 1, 0
+            assert np.array_equal(obs[k, i], o), (i, k)
+    assert n_greedy > 0.6 * N * K and n_ties < 0.002 * n_greedy
+    assert (n_explored == 0) if eps == 0 else abs(n_explored / (N * K) - eps) < 0.02

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 WF_OK, WF_ERR_INVALID, WF_ERR_CUDA, WF_ERR_STATE = 0, -1, -2, -3
 WF_OBS_U8, WF_OBS_F32 = 0, 1
-WF_POLICY_STREAM, WF_POLICY_WALK = 0, 1
+WF_POLICY_STREAM, WF_POLICY_WALK, WF_POLICY_MLP = 0, 1, 2
 WF_NSCALARS = 16
 (S_ALIVE, S_AX, S_AY, S_DEAD, S_DIGGING, S_VISIBLE, S_RUNNING, S_FIRE_AT_BORDER, S_LATCHED, S_EPISODE, S_T,
  S_WIND_ID, S_WIND_X, S_WIND_Y, S_N_BURNING, S_RESERVED) = range(16)
@@ -82,6 +82,7 @@ def lib():
     L.wf_step.argtypes = [vp, i32p, vp, C.c_int32, f64p, u8p, vp]
     L.wf_rollout.argtypes = [vp, C.c_int32, i32p, vp, C.c_int32, f64p, u8p, vp]
     L.wf_rollout_policy.argtypes = [vp, C.c_int32, C.c_int32, i32p, vp, C.c_int32, f64p, u8p, vp]
+    L.wf_set_policy_mlp.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_double]
     L.wf_step_host.argtypes = [vp, i32p, vp, C.c_int32, f64p, u8p]
     L.wf_get_state.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, u8p, i32p, vp]
     L.wf_set_state.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, i32p, vp]
@@ -97,7 +98,7 @@ def lib():
     L.wf_launch_count.restype = C.c_int64
     L.wf_state_bytes_per_env.argtypes = [vp]
     L.wf_state_bytes_per_env.restype = C.c_int64
-    for name in ("wf_create", "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_step_host", "wf_get_state", "wf_set_state",
+    for name in ("wf_create", "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state",
                  "wf_set_fire_to", "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -111,7 +112,7 @@ def check(rc: int):
 
 EXPORTED_SYMBOLS = [
     "wf_default_config", "wf_create", "wf_destroy", "wf_last_error", "wf_abi_version", "wf_kernel_family",
-    "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_step_host", "wf_get_state", "wf_set_state", "wf_set_fire_to",
+    "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state", "wf_set_fire_to",
     "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset", "wf_philox_kat", "wf_launch_count",
     "wf_state_bytes_per_env",
 ]

@@ -492,15 +492,26 @@ class DQN:
         from .keras_h5 import canonical_dense_names, read_keras_weights
         self.set_weights(canonical_dense_names(read_keras_weights(path)))
 
-    def evaluate_batched(self, n_envs=4096, episodes_per_env=1, eps=None, seed=0, max_steps=100000):
+    def evaluate_batched(self, n_envs=4096, episodes_per_env=1, eps=None, seed=0, max_steps=100000, in_kernel=None):
         """Roll the current policy out on ``n_envs`` CUDA environments at once (eps-greedy, DQN.py:188-196) and
         return (total reward, agent died) of the first ``episodes_per_env`` episodes of every env -- the
-        quantity ``logs['total_rewards']`` / ``logs['agent_deaths']`` hold per training episode."""
+        quantity ``logs['total_rewards']`` / ``logs['agent_deaths']`` hold per training episode.
+
+        ``in_kernel`` (default: whenever the grid fits the warp kernel family, <= 32x32): the Q-network is
+        evaluated INSIDE the step kernel (``wf_rollout_policy(WF_POLICY_MLP)``), 64 steps per launch;
+        otherwise torch evaluates it between two ``wf_step`` calls."""
         from .batched import BatchedForestFire
         from .constants import DQN_DEFAULTS as _D
         eps = self.min_eps if eps is None else eps
         keys = {k: v for k, v in self.METADATA.items() if k not in _D and k not in ("debug", "a_speed_iter", "seed", "auto_reset")}
         env = BatchedForestFire(n_envs, device=self.device, auto_reset=True, seed=seed, **keys)
+        if in_kernel is None:
+            in_kernel = env.kernel_family == "warp"
+        if in_kernel:
+            try:
+                return self._evaluate_in_kernel(env, n_envs, episodes_per_env, eps, max_steps)
+            finally:
+                env.close()
         dev = self.device
         gen = torch.Generator(device=dev).manual_seed(seed)
         returns = torch.zeros((n_envs, episodes_per_env), dtype=torch.float64, device=dev)
@@ -531,6 +542,39 @@ class DQN:
         finally:
             env.close()
         return returns.flatten().cpu().numpy(), died.flatten().cpu().numpy()
+
+    def _evaluate_in_kernel(self, env, n_envs, episodes_per_env, eps, max_steps, chunk=64):
+        w = self.get_weights()  # dense_1 / dense_2 are the advantage stream of a dueling head: argmax Q = argmax A
+        env.set_policy_mlp(w["dense_1/kernel:0"], w["dense_1/bias:0"], w["dense_2/kernel:0"], w["dense_2/bias:0"], eps=eps)
+        env.reset()
+        death_penalty = float(self.METADATA["death_penalty"])
+        returns = np.zeros((n_envs, episodes_per_env))
+        died = np.zeros((n_envs, episodes_per_env), dtype=bool)
+        n_done = np.zeros(n_envs, dtype=np.int64)
+        carry = np.zeros(n_envs)  # reward of the running episode before this chunk
+        for _ in range(0, max_steps, chunk):
+            _, rew, done = env.rollout(chunk, policy="mlp", obs=False)
+            rew, done = rew.cpu().numpy(), done.cpu().numpy()
+            c = carry[None, :] + np.cumsum(rew, axis=0)
+            e_idx, k_idx = np.nonzero(done.T)  # episode ends, sorted by env then step
+            at_end = c[k_idx, e_idx]
+            same = np.r_[False, e_idx[1:] == e_idx[:-1]]
+            ret = at_end - np.where(same, np.r_[0.0, at_end[:-1]], 0.0)
+            first = np.r_[True, ~same[1:]] if len(e_idx) else np.zeros(0, bool)
+            rank = np.arange(len(e_idx)) - np.maximum.accumulate(np.where(first, np.arange(len(e_idx)), 0))
+            slot = n_done[e_idx] + rank
+            keep = slot < episodes_per_env
+            returns[e_idx[keep], slot[keep]] = ret[keep]
+            died[e_idx[keep], slot[keep]] = rew[k_idx[keep], e_idx[keep]] == death_penalty
+            last = np.zeros(n_envs)
+            if len(e_idx):
+                is_last = np.r_[e_idx[1:] != e_idx[:-1], True]
+                last[e_idx[is_last]] = at_end[is_last]
+            carry = c[-1] - last
+            n_done += np.bincount(e_idx, minlength=n_envs)
+            if (n_done >= episodes_per_env).all():
+                return returns.flatten(), died.flatten()
+        raise RuntimeError("evaluate_batched: some episodes did not finish")
 
     def save_model(self, name):  # DQN.py:441-443
         path = os.path.join(self.out_dir, "Models", name)

@@ -164,14 +164,15 @@ class BatchedForestFire:
         """``k_steps`` consecutive ``step`` calls in one launch (state stays on chip in between).
 
         ``actions``: ``[K, N]`` ints, or ``None`` = chosen on the device by ``policy``:
-        ``"stream"`` (uniform random, ACTION stream) or ``"walk"`` (the reference's heuristic
-        demonstration / Baseline policy ``DQN.choose_randomwalk_action``, DQN.py:353-389).
+        ``"stream"`` (uniform random, ACTION stream), ``"walk"`` (the reference's heuristic
+        demonstration / Baseline policy ``DQN.choose_randomwalk_action``, DQN.py:353-389) or ``"mlp"``
+        (the Q-network given to ``set_policy_mlp``, eps-greedy, evaluated inside the step kernel).
         ``out``: optional ``(obs_or_None, reward, done_u8)`` buffers to write into.
         Returns ``(obs [K,N,W,H,3] or None, reward [K,N], done [K,N])`` (+ ``actions [K,N]`` if asked).
         """
         K, N = int(k_steps), self.n_envs
         a = None if actions is None else self._as_i32(actions, (K, N))
-        pol = {"stream": _lib.WF_POLICY_STREAM, "walk": _lib.WF_POLICY_WALK}[policy]
+        pol = {"stream": _lib.WF_POLICY_STREAM, "walk": _lib.WF_POLICY_WALK, "mlp": _lib.WF_POLICY_MLP}[policy]
         with torch.cuda.device(self.device):
             if out is not None:
                 o, r, d = out
@@ -191,6 +192,20 @@ class BatchedForestFire:
         if return_actions:
             return o, r, d.view(torch.bool), chosen
         return o, r, d.view(torch.bool)
+
+    def set_policy_mlp(self, kernel1, bias1, kernel2, bias2, eps: float = 0.0):
+        """Weights of the in-kernel Q-network (``rollout(policy="mlp")``): Keras orientation, ``kernel1``
+        ``[W*H*3, hidden]``, ``kernel2`` ``[hidden, n_actions]`` (DQN.make_network, DQN.py:209-233; for a
+        dueling head pass the advantage stream).  ``eps``: exploration rate (DQN.choose_action :188-196)."""
+        arrs = [np.ascontiguousarray(torch.as_tensor(a).detach().cpu().numpy() if torch.is_tensor(a) else a, dtype=np.float32)
+                for a in (kernel1, bias1, kernel2, bias2)]
+        k1, b1, k2, b2 = arrs
+        hidden = int(b1.shape[0])
+        if k1.shape != (self.width * self.height * 3, hidden) or k2.shape != (hidden, self.n_actions) or b2.shape != (self.n_actions,):
+            raise ValueError(f"weight shapes {[a.shape for a in arrs]} do not fit a {self.width}x{self.height}x3 -> {hidden} -> "
+                             f"{self.n_actions} network")
+        _lib.check(_lib.lib().wf_set_policy_mlp(self._h, k1.ctypes.data, b1.ctypes.data, k2.ctypes.data, b2.ctypes.data,
+                                                hidden, float(eps)))
 
     def step_host(self, actions):
         """Host-buffer step through ``wf_step_host``: H2D actions, step, D2H obs/reward/done, sync.

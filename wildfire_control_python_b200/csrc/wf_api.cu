@@ -37,6 +37,8 @@ struct wf_env {
     int32_t a_iter;  // METADATA['a_speed_iter']: one per handle, not reset by reset() (Q8)
     int64_t launches;
     TileState* tstate;
+    float* mlp_dev;      // WF_POLICY_MLP weights: w1 | base | w2 | b2
+    MlpPolicy mlp;       // device pointers into mlp_dev (hid == 0: not set)
     // wf_step_host staging
     cudaStream_t hstream;
     bool host_direct, host_obs_direct;
@@ -330,6 +332,7 @@ void wf_destroy(wf_env* e) {
     if (e->tstate) tile_destroy(e->tstate);
     cudaFree(e->st.planes); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
     cudaFree(e->wind_dev);
+    cudaFree(e->mlp_dev);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
     if (e->hstream) cudaStreamDestroy(e->hstream);
     delete e;
@@ -361,7 +364,8 @@ int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* 
         TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, e->a_iter, 1, 0, nullptr};
         WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
     } else {
-        WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H), 0, nullptr};
+        WarpIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 1, e->a_iter, 1, magic_for(e->st.H), 0, nullptr,
+                  MlpPolicy{}};
         WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
         e->launches += 1;
     }
@@ -381,7 +385,12 @@ static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, 
                         void* obs_dev, int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     if (k_steps < 1) return fail(WF_ERR_INVALID, "k_steps must be >= 1");
-    if (policy != WF_POLICY_STREAM && policy != WF_POLICY_WALK) return fail(WF_ERR_INVALID, "unknown policy");
+    if (policy != WF_POLICY_STREAM && policy != WF_POLICY_WALK && policy != WF_POLICY_MLP)
+        return fail(WF_ERR_INVALID, "unknown policy");
+    if (policy == WF_POLICY_MLP && !actions_dev) {
+        if (e->tile) return fail(WF_ERR_INVALID, "WF_POLICY_MLP is implemented for grids up to 32x32 (warp family) only");
+        if (e->mlp.hid == 0) return fail(WF_ERR_STATE, "WF_POLICY_MLP: call wf_set_policy_mlp first");
+    }
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -393,7 +402,7 @@ static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, 
         return WF_OK;
     }
     WarpIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0,
-              magic_for(e->st.H), policy, actions_out};
+              magic_for(e->st.H), policy, actions_out, e->mlp};
     WF_CUDA(launch_warp_family(e->st, e->sc, io, st));
     e->launches += 1;
     e->a_iter = advance_a_iter(e, k_steps);
@@ -408,6 +417,42 @@ int wf_rollout(wf_env* e, int32_t k_steps, const int32_t* actions_dev, void* obs
 int wf_rollout_policy(wf_env* e, int32_t k_steps, int32_t policy, int32_t* actions_out_dev, void* obs_dev,
                       int32_t obs_dtype, double* reward_dev, uint8_t* done_dev, void* stream) {
     return rollout_impl(e, k_steps, nullptr, policy, actions_out_dev, obs_dev, obs_dtype, reward_dev, done_dev, stream);
+}
+
+int wf_set_policy_mlp(wf_env* e, const float* k1, const float* b1, const float* k2, const float* b2, int32_t hidden,
+                      double eps) {
+    if (!e || !k1 || !b1 || !k2 || !b2) return fail(WF_ERR_INVALID, "null argument");
+    if (hidden < 1 || hidden > 64) return fail(WF_ERR_INVALID, "hidden must be in 1..64");
+    if (e->cfg.n_actions > 8) return fail(WF_ERR_INVALID, "WF_POLICY_MLP supports at most 8 actions");
+    if (!(eps >= 0.0 && eps <= 1.0)) return fail(WF_ERR_INVALID, "eps must be in [0, 1]");
+    WF_CUDA(cudaSetDevice(e->device));
+    const DevState& s = e->st;
+    const int n_in = s.W * s.H * 3, A = e->cfg.n_actions;
+    const size_t n_w1 = (size_t)n_in * hidden, total = n_w1 + hidden + (size_t)hidden * A + A;
+    std::string buf(total * sizeof(float), '\0');
+    float* h = reinterpret_cast<float*>(&buf[0]);
+    std::memcpy(h, k1, n_w1 * sizeof(float));
+    float* base = h + n_w1;
+    for (int j = 0; j < hidden; ++j) {  // the empty map: every cell free (channel 2), no fire, no agent
+        double acc = b1[j];
+        for (int cell = 0; cell < s.W * s.H; ++cell) acc += k1[(size_t)(cell * 3 + 2) * hidden + j];
+        base[j] = (float)acc;
+    }
+    std::memcpy(base + hidden, k2, (size_t)hidden * A * sizeof(float));
+    std::memcpy(base + hidden + (size_t)hidden * A, b2, A * sizeof(float));
+    cudaFree(e->mlp_dev);
+    e->mlp_dev = nullptr;
+    e->mlp = MlpPolicy{};
+    WF_CUDA(cudaMalloc(&e->mlp_dev, total * sizeof(float)));
+    WF_CUDA(cudaMemcpy(e->mlp_dev, h, total * sizeof(float), cudaMemcpyHostToDevice));
+    e->mlp.w1 = e->mlp_dev;
+    e->mlp.base = e->mlp_dev + n_w1;
+    e->mlp.w2 = e->mlp.base + hidden;
+    e->mlp.b2 = e->mlp.w2 + (size_t)hidden * A;
+    e->mlp.hid = hidden;
+    e->mlp.n_actions = A;
+    e->mlp.eps_u32 = eps >= 1.0 ? 0xffffffffu : (uint32_t)(eps * 4294967296.0);
+    return WF_OK;
 }
 
 int wf_step(wf_env* e, const int32_t* actions_dev, void* obs_dev, int32_t obs_dtype, double* reward_dev,

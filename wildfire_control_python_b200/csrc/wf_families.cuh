@@ -4,6 +4,16 @@
 
 namespace wf {
 
+// Q-network of WF_POLICY_MLP, device pointers (owned by the handle).
+struct MlpPolicy {
+    const float* w1;    // [n_in][hid], Keras orientation
+    const float* base;  // [hid]: bias1 + sum over cells of w1[(cell, channel 2)] -- the all-free, no-fire, no-agent map
+    const float* w2;    // [hid][n_actions]
+    const float* b2;    // [n_actions]
+    int32_t hid, n_actions;
+    uint32_t eps_u32;   // explore iff a 32-bit draw is below this
+};
+
 struct WarpIO {
     const int32_t* actions;  // [K][N] or nullptr (ACTION stream)
     void* obs;               // [K][N][W][H][3] or nullptr
@@ -13,8 +23,9 @@ struct WarpIO {
     const wf_init* init;     // reset mode: [N] or nullptr
     int32_t obs_dtype, K, a_iter0, reset_mode;
     uint32_t magicH;         // ceil(2^32 / H)
-    int32_t policy;          // actions == nullptr: WF_POLICY_STREAM or WF_POLICY_WALK
+    int32_t policy;          // actions == nullptr: WF_POLICY_STREAM, WF_POLICY_WALK or WF_POLICY_MLP
     int32_t* actions_out;    // [K][N] or nullptr: the actions the policy chose
+    MlpPolicy mlp;           // WF_POLICY_MLP only
 };
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 

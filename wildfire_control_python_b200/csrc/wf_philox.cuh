@@ -9,12 +9,13 @@
 //   stream 1 ACTION: step t of the episode = word (t & 3) of block t >> 2; action = word % n_actions
 //   stream 2 IGNITE: index = k-th extra ignition; cell = (word0 % W, word1 % H)
 //   stream 3 POLICY: heuristic walk policy, step t: draw j (< 12) = word (j & 3) of block 3t + (j >> 2)
+//   stream 4 EXPLORE: eps-greedy of the in-kernel Q-network: step t = words 2(t&1), 2(t&1)+1 of block t >> 1
 #pragma once
 #include <stdint.h>
 
 namespace wf {
 
-constexpr uint32_t kStreamReset = 0u, kStreamAction = 1u, kStreamIgnite = 2u, kStreamPolicy = 3u;
+constexpr uint32_t kStreamReset = 0u, kStreamAction = 1u, kStreamIgnite = 2u, kStreamPolicy = 3u, kStreamExplore = 4u;
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {

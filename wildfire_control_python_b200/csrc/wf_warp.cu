@@ -213,7 +213,13 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
 // ignites when its TOTAL hit count reaches kmin, so `temp` is a 7-bit counter per cell, bit-sliced in
 // registers (planes HC0..HC6); heat transfer + ignition test are ~40 word-parallel logic instructions
 // per tick instead of a data-dependent loop over hit counters in memory.
-template <int L, int FB, bool UNI>
+// MLP: the Q-network of WF_POLICY_MLP is evaluated in here (DQN.choose_action, DQN.py:188-196).  Its inputs
+// are the observation bits, so the first layer is a SUM OF WEIGHT ROWS: every lane keeps a few hidden
+// pre-activations in float64 and, per step, only adds / subtracts the rows of the bits that changed
+// (agent cell, dug cell, ignitions, burn-outs; everything after a reset).
+constexpr int kHidMax = 64, kActMax = 8;
+
+template <int L, int FB, bool UNI, bool MLP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, StepCfg c, WarpIO io) {
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
@@ -266,6 +272,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
 
     long long n_steps_done = 0;
 
+    // WF_POLICY_MLP: hidden pre-activations of units j = x + L*i, and the observation they were computed from
+    constexpr int HPL = kHidMax / L;
+    double hacc[MLP ? HPL : 1];
+    uint32_t pA = 0u, pF = 0u, pFree = validmask;  // the empty map: what `base` stands for
+    if (MLP) {
+#pragma unroll
+        for (int i = 0; i < HPL; ++i) hacc[i] = (x + L * i < io.mlp.hid) ? (double)io.mlp.base[x + L * i] : 0.0;
+    }
+
     if (io.reset_mode) {
         // ---------------- ForestFire.reset() ----------------
         const bool doit = valid_env && (io.mask == nullptr || io.mask[env] != 0);
@@ -287,6 +302,76 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             int action;
             if (io.actions != nullptr) {
                 action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
+            } else if (MLP) {
+                const int hid = io.mlp.hid, A = io.mlp.n_actions;
+                // ---- first layer, incrementally: rows of the observation bits that changed since the last evaluation
+                const uint32_t cA = (a.vis && x == a.ax) ? (1u << a.ay) : 0u, cF = r.F, cFree = ~r.I & validmask;
+                const uint32_t dA = cA ^ pA, dF = cF ^ pF, dFree = cFree ^ pFree;
+                pA = cA; pF = cF; pFree = cFree;
+                uint32_t rows = group_bits(__ballot_sync(FULL, (dA | dF | dFree) != 0u));
+                while (__any_sync(FULL, rows != 0u)) {
+                    const bool have = rows != 0u;
+                    const int row = have ? __ffs(rows) - 1 : 0;
+                    rows &= rows - 1u;
+                    const int src = sub * L + row;
+                    uint32_t bA = __shfl_sync(FULL, dA, src), bF = __shfl_sync(FULL, dF, src), bR = __shfl_sync(FULL, dFree, src);
+                    const uint32_t nA = __shfl_sync(FULL, cA, src), nF = __shfl_sync(FULL, cF, src), nR = __shfl_sync(FULL, cFree, src);
+                    if (!have) bA = bF = bR = 0u;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        uint32_t m = ch == 0 ? bA : ch == 1 ? bF : bR;
+                        const uint32_t now = ch == 0 ? nA : ch == 1 ? nF : nR;
+                        while (m) {
+                            const int y = __ffs(m) - 1;
+                            m &= m - 1u;
+                            const float* wrow = io.mlp.w1 + (size_t)((row * H + y) * 3 + ch) * hid;
+                            const bool on = (now >> y) & 1u;
+#pragma unroll
+                            for (int i = 0; i < HPL; ++i) {
+                                const int j = x + L * i;
+                                if (j < hid) {
+                                    const double wv = (double)wrow[j];
+                                    hacc[i] = on ? hacc[i] + wv : hacc[i] - wv;
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- sigmoid, second layer, argmax (np.argmax: the first maximum)
+                float q[kActMax];
+#pragma unroll
+                for (int b = 0; b < kActMax; ++b) q[b] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < HPL; ++i) {
+                    const int j = x + L * i;
+                    if (j < hid) {
+                        const float sj = 1.0f / (1.0f + __expf(-(float)hacc[i]));
+#pragma unroll
+                        for (int b = 0; b < kActMax; ++b)
+                            if (b < A) q[b] = fmaf(sj, io.mlp.w2[j * A + b], q[b]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < kActMax; ++b) {
+                    if (b < A) {
+#pragma unroll
+                        for (int o = L / 2; o > 0; o >>= 1) q[b] += __shfl_xor_sync(FULL, q[b], o, L);
+                        q[b] += io.mlp.b2[b];
+                    }
+                }
+                int greedy = 0;
+                float best = q[0];
+#pragma unroll
+                for (int b = 1; b < kActMax; ++b)
+                    if (b < A && q[b] > best) { best = q[b]; greedy = b; }
+                // ---- eps-greedy: EXPLORE stream, one Philox block serves two consecutive steps
+                if ((a.t & 1u) == 0u || ablk_ep != a.episode || ablk_idx != (a.t >> 1)) {
+                    philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, a.t >> 1, kStreamExplore, c.key0, c.key1, ablk);
+                    ablk_ep = a.episode;
+                    ablk_idx = a.t >> 1;
+                }
+                const uint32_t u0 = (a.t & 1u) ? ablk[2] : ablk[0], u1 = (a.t & 1u) ? ablk[3] : ablk[1];
+                action = (u0 < io.mlp.eps_u32) ? (int)(u1 % (uint32_t)c.n_actions) : greedy;
             } else if (io.policy == WF_POLICY_WALK) {
                 // DQN.choose_randomwalk_action (DQN.py:353-389): walk clockwise round the fire origin,
                 // re-draw (at most 11 times) while the move would step onto a burning cell.
@@ -553,13 +638,25 @@ cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO
     const int envs_per_block = kWarpsPerBlock * epw;
     const dim3 grid((s.N + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
     if (s.HB != 0 && (s.HB != kHitBits || s.FB != 5)) return cudaErrorInvalidValue;
-    if (L == 16 && s.FB == 5 && s.HB) warp_kernel<16, 5, true><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 32 && s.FB == 5 && s.HB) warp_kernel<32, 5, true><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 16 && s.FB == 5) warp_kernel<16, 5, false><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 16 && s.FB == 8) warp_kernel<16, 8, false><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 32 && s.FB == 5) warp_kernel<32, 5, false><<<grid, block, 0, stream>>>(s, c, io);
-    else if (L == 32 && s.FB == 8) warp_kernel<32, 8, false><<<grid, block, 0, stream>>>(s, c, io);
+    const bool mlp = io.policy == WF_POLICY_MLP && io.actions == nullptr && !io.reset_mode;
+    if (mlp && (io.mlp.hid < 1 || io.mlp.hid > kHidMax || io.mlp.n_actions > kActMax)) return cudaErrorInvalidValue;
+#define WF_LAUNCH(LL, FF, UU, MM) warp_kernel<LL, FF, UU, MM><<<grid, block, 0, stream>>>(s, c, io)
+    if (mlp) {
+        if (L == 16 && s.FB == 5 && s.HB) WF_LAUNCH(16, 5, true, true);
+        else if (L == 32 && s.FB == 5 && s.HB) WF_LAUNCH(32, 5, true, true);
+        else if (L == 16 && s.FB == 5) WF_LAUNCH(16, 5, false, true);
+        else if (L == 16 && s.FB == 8) WF_LAUNCH(16, 8, false, true);
+        else if (L == 32 && s.FB == 5) WF_LAUNCH(32, 5, false, true);
+        else if (L == 32 && s.FB == 8) WF_LAUNCH(32, 8, false, true);
+        else return cudaErrorInvalidValue;
+    } else if (L == 16 && s.FB == 5 && s.HB) WF_LAUNCH(16, 5, true, false);
+    else if (L == 32 && s.FB == 5 && s.HB) WF_LAUNCH(32, 5, true, false);
+    else if (L == 16 && s.FB == 5) WF_LAUNCH(16, 5, false, false);
+    else if (L == 16 && s.FB == 8) WF_LAUNCH(16, 8, false, false);
+    else if (L == 32 && s.FB == 5) WF_LAUNCH(32, 5, false, false);
+    else if (L == 32 && s.FB == 8) WF_LAUNCH(32, 8, false, false);
     else return cudaErrorInvalidValue;
+#undef WF_LAUNCH
     return cudaGetLastError();
 }
 
