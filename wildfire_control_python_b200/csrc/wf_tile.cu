@@ -2,7 +2,7 @@
 //
 // Same bit-plane state as the warp family (wf_common.cuh) but resident in HBM: a row x of H cells is
 // HW = ceil(H/32) words.  ONE thread-block cluster (1..8 CTAs, chosen so that all envs together fill
-// the 148 SMs) owns one environment for a whole K-step rollout; CTA r of the cluster owns the r-th
+// the 148 SMs; 16 with the non-portable opt-in) owns one environment for a whole K-step rollout; CTA r of the cluster owns the r-th
 // contiguous slice of the env's words.  Everything the reference does in ForestFire.step happens in
 // this one kernel, per step:
 //
@@ -59,6 +59,8 @@ struct StepShared {
 };
 
 int tile_extra_planes() { return 3; }
+
+constexpr int kMaxCluster = 16;  // CTAs per cluster: 8 is the portable limit, 16 needs the non-portable opt-in
 
 // Phase timing of one probe CTA (debug builds only: -DWF_TILE_TIMING; read with wf_debug_tile_timing).
 #ifdef WF_TILE_TIMING
@@ -152,7 +154,7 @@ struct Env {
 // Sum the CTAs' partial reductions red[0..3] over the cluster into ss.tot[0..3] (and clear red).
 // Call with red[] complete (after a __syncthreads); returns with ss.tot visible to the whole CTA.
 template <bool CL>
-__device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[8][4], int& par, StepShared& ss) {
+__device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[kMaxCluster][4], int& par, StepShared& ss) {
     if (CL) {
         if (e.tid < 4 * e.CS) st_shared_cluster(&xch[par][e.rank][e.tid & 3], (uint32_t)(e.tid >> 2), red[e.tid & 3]);
         cluster_barrier();
@@ -176,7 +178,7 @@ __device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[8][4
 // Reach plane: R = finite cells 4-connected to a finite border point (flood from the border over
 // ~fm_inf).  Whole cluster; in-place monotone relaxation until a full sweep changes nothing anywhere.
 template <bool CL>
-__device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[8][4], int& par, StepShared& ss) {
+__device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[kMaxCluster][4], int& par, StepShared& ss) {
     const int W = e.W, H = e.H, HW = e.HW;
     uint32_t* R = e.plane(t.P_R);
     const uint32_t* I = e.plane(P_I);
@@ -729,7 +731,7 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
 // Agent.__init__ (:100-113), extra ignitions, reach plane, burning count.  Whole cluster.
 template <int FB, bool CL>
 __device__ void reset_env(const Env& e, const DevState& s, const StepCfg& c, const TilePar& t, const wf_init* init,
-                          int32_t* sc, StepShared& ss, int* red, int (*xch)[8][4], int& par) {
+                          int32_t* sc, StepShared& ss, int* red, int (*xch)[kMaxCluster][4], int& par) {
     const int W = e.W, H = e.H, HW = e.HW, tid = e.tid, T = e.T;
     const size_t pstride = e.pstride;
     const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;  // every thread reads the old value ...
@@ -885,7 +887,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
     extern __shared__ uint32_t qmem[];  // per-warp active-word queues (7 x 32 * VW words each); observation staging
     __shared__ int32_t sc[WF_NSCALARS];
     __shared__ int red[4];
-    __shared__ int xch[2][8][4];
+    __shared__ int xch[2][kMaxCluster][4];
     __shared__ StepShared ss;
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
@@ -1021,7 +1023,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
 // (after wf_set_state / wf_set_fire_to).  One CTA per env.
 __global__ void rebuild_kernel(DevState s, TilePar t) {
     __shared__ int red[4];
-    __shared__ int xch[2][8][4];
+    __shared__ int xch[2][kMaxCluster][4];
     __shared__ StepShared ss;
     Env e;
     e.tid = threadIdx.x; e.T = blockDim.x; e.CS = 1; e.rank = 0; e.env = blockIdx.x;
@@ -1077,11 +1079,15 @@ static void choose_geometry(const DevState& s, int& T, int& CS) {
     if (p == 2048) { T = 256; CS = 8; }
     const int t_env = env_int("WF_TILE_T", 0), cs_env = env_int("WF_TILE_CS", 0);
     if (t_env == 128 || t_env == 256 || t_env == 512) T = t_env;
-    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) CS = cs_env;
+    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8 || cs_env == 16) CS = cs_env;
 }
 
 template <int FB, int VW, bool CL>
 static cudaError_t set_smem_attr() {
+    if (CL) {
+        cudaError_t e = cudaFuncSetAttribute(tile_rollout_kernel<FB, VW, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(tile_rollout_kernel<FB, VW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 4 * 28);
 }
 
