@@ -1,0 +1,31 @@
+"""Live differential test: the C oracle against the UNMODIFIED Python reference, step by step.
+
+Runs only where the reference tree exists (the build container; `/root/reference` does not travel to
+the GPU box -- there the committed golden trajectories of tests/golden/ stand in).  It is the pytest
+face of `python -m oracle.validate_oracle` (69 000 steps over 23 scenarios, run by hand): a bounded
+number of steps of every scenario, every plane / scalar / observation / reward / done compared, and
+for the `walk_*` scenarios the reference's own `DQN.choose_randomwalk_action` against the oracle's
+restatement, action by action.
+"""
+import os
+
+import pytest
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/Simulation"), reason="reference tree not present on this box")
+
+
+def _scenarios():
+    try:
+        from oracle.validate_oracle import SCENARIOS
+        return SCENARIOS
+    except Exception:  # the harness imports the reference at module import time
+        return []
+
+
+@pytest.mark.parametrize("sc", _scenarios(), ids=lambda s: s["name"])
+def test_oracle_equals_python_reference(sc):
+    from oracle.validate_oracle import run
+    st = run(sc, 350)
+    assert st["steps"] == 350 and st["maxerr"] <= 1e-12
+    if sc.get("policy", "").startswith(("ring", "walk")):
+        assert st["contained"] >= 1  # the scripted / heuristic walks do contain the fire
