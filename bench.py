@@ -282,7 +282,11 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, no_graph: bool,
         te = D.max_over_ranks(time.perf_counter() - t0)
         res["e2e"] = {"value": world * N * Ke / te, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
                       "d2h_bytes_per_step": N * W * H * 3 + N * 8 + N, "steps": Ke, "us_per_step": te * 1e6 / Ke,
-                      "api": "wf_step_host, page-locked host buffers (actions/reward/done zero-copy, obs one DMA copy)"}
+                      "host_threads": env.host_threads,
+                      "api": ("wf_step_host, page-locked host buffers: actions/reward/done zero-copy; observation sent as a bit "
+                              "stream into mapped host memory and expanded to the uint8 array by the library's host threads"
+                              if env.host_threads else
+                              "wf_step_host, page-locked host buffers (actions/reward/done zero-copy, obs one DMA copy)")}
     res["stats"] = env.stats()
     env.close()
     del obs_buf, rew_buf, done_buf, out, env

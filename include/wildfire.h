@@ -145,9 +145,19 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
 
 /* Host-buffer variant of wf_step (what a CPU-side caller of the reference would bind):
  * copies actions H2D, steps, copies obs/reward/done D2H and synchronises.  Buffers should
- * be page-locked for full PCIe rate; pageable memory works but is slower. */
+ * be page-locked for full PCIe rate; pageable memory works but is slower.
+ * With page-locked buffers, uint8 observations and a grid up to 32x32 the observation crosses PCIe as a
+ * bit stream and is expanded into obs_host by a small pool of host threads (WF_HOST_THREADS, default
+ * min(8, cores / 2 / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead). */
 int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32_t obs_dtype,
                  double* reward_host, uint8_t* done_host);
+/* Host threads wf_step_host uses to expand observations (0: the packed path has not been used). */
+int wf_host_threads(const wf_env* env);
+/* The host half of that path on its own (no GPU needed): expand a packed observation buffer -- one record of
+ * ceil(e * W*H*3 / 32) uint32 words per group of e consecutive envs (e = 2 if W <= 16 else 1), bit k of a
+ * record = element k of the group's [e][W][H][3] block -- into uint8 obs_host[n_envs][W][H][3]. */
+int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t n_envs, int32_t width,
+                         int32_t height, int32_t threads);
 
 /* ---- state access (parity injection, checkpointing) --------------------------------
  * Canonical planes, device pointers, any may be NULL:

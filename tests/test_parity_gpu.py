@@ -235,20 +235,30 @@ def test_f32_observation_equals_u8():
         assert ob.dtype == torch.float32 and torch.equal(oa.float(), ob) and torch.equal(ra, rb) and torch.equal(da, db)
 
 
-def test_step_host_roundtrip():
-    cfg = dict(width=14, height=14, seed=501)
-    gpu, orc = make_pair(16, cfg)
+@pytest.mark.parametrize("cfg,n_envs,packed", [(dict(width=14, height=14, seed=501), 16, "1"), (dict(width=14, height=14, seed=502), 33, "1"),
+                                               (dict(width=10, height=10, seed=503), 7, "1"), (dict(width=32, height=32, seed=504), 5, "1"),
+                                               (dict(width=17, height=13, seed=505, wind="random"), 9, "1"),
+                                               (dict(width=14, height=14, seed=506), 16, "0"), (dict(width=40, height=36, seed=507), 6, "1")],
+                         ids=["14_even", "14_odd", "10", "32", "17x13", "14_unpacked", "tile_40x36"])
+def test_step_host_roundtrip(monkeypatch, cfg, n_envs, packed):
+    """wf_step_host with page-locked host buffers: the packed path (observation bit stream into mapped host
+    memory + host-thread expansion, grids up to 32x32), the plain uint8 path (WF_HOST_PACKED=0) and the tile family."""
+    monkeypatch.setenv("WF_HOST_PACKED", packed)
+    monkeypatch.setenv("WF_HOST_THREADS", "3")
+    gpu, orc = make_pair(n_envs, cfg)
     gpu.reset()
     for e in orc:
         e.reset()
-    for s in range(30):
+    for s in range(40):
         acts = np.array([e.random_action() for e in orc], np.int32)
         obs, rew, done, _ = gpu.step_host(acts)
         for i, e in enumerate(orc):
             if not e.planes()["running"]:
                 continue
             o, r, d, _ = e.step(int(acts[i]))
-            assert rew[i] == r and bool(done[i]) == d and np.array_equal(obs[i], o)
+            assert rew[i] == r and bool(done[i]) == d and np.array_equal(obs[i], o), (s, i)
+    want_threads = 3 if (packed == "1" and max(cfg["width"], cfg["height"]) <= 32) else 0
+    assert gpu.host_threads == want_threads
 
 
 def test_set_state_free_burn_known_answer():

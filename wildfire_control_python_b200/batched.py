@@ -299,6 +299,11 @@ class BatchedForestFire:
         return int(_lib.lib().wf_launch_count(self._h))
 
     @property
+    def host_threads(self) -> int:
+        """Host threads ``step_host`` uses to expand packed observations (0 if that path is not in use)."""
+        return int(_lib.lib().wf_host_threads(self._h))
+
+    @property
     def state_bytes_per_env(self) -> int:
         return int(_lib.lib().wf_state_bytes_per_env(self._h))
 

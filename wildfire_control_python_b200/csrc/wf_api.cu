@@ -13,6 +13,16 @@
 
 using namespace wf;
 
+namespace wf {  // wf_hostpool.cpp
+class HostPool;
+HostPool* hostpool_create(int threads);
+void hostpool_destroy(HostPool* p);
+int hostpool_threads(const HostPool* p);
+void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words, int64_t env_bits,
+                     int64_t envs_per_record, int64_t n_envs);
+int hostpool_default_threads();
+}  // namespace wf
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -47,6 +57,12 @@ struct wf_env {
     size_t h_obs_bytes;
     double* h_reward;
     uint8_t* h_done;
+    // packed-observation path of wf_step_host: mapped page-locked record buffer + expansion threads
+    bool host_packed;
+    uint32_t* h_packed;      // host address
+    uint32_t* h_packed_dev;  // device alias
+    size_t h_packed_words;
+    HostPool* pool;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -334,12 +350,27 @@ void wf_destroy(wf_env* e) {
     cudaFree(e->wind_dev);
     cudaFree(e->mlp_dev);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
+    if (e->h_packed) cudaFreeHost(e->h_packed);
+    if (e->pool) hostpool_destroy(e->pool);
     if (e->hstream) cudaStreamDestroy(e->hstream);
     delete e;
 }
 
 const char* wf_kernel_family(const wf_env* e) { return e ? (e->tile ? "tile" : "warp") : ""; }
 int64_t wf_launch_count(const wf_env* e) { return e ? e->launches : 0; }
+int wf_host_threads(const wf_env* e) { return (e && e->pool) ? hostpool_threads(e->pool) : 0; }
+
+int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t n_envs, int32_t width, int32_t height,
+                         int32_t threads) {
+    if (!packed_host || !obs_host || n_envs < 1 || width < 1 || height < 1 || width > 32 || height > 32 || threads < 1)
+        return fail(WF_ERR_INVALID, "wf_expand_packed_obs: bad argument");
+    const int epw = width <= 16 ? 2 : 1;
+    const int64_t env_bits = (int64_t)width * height * 3, records = (n_envs + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
+    HostPool* p = hostpool_create(threads);
+    hostpool_expand(p, packed_host, obs_host, records, rec_words, env_bits, epw, n_envs);
+    hostpool_destroy(p);
+    return WF_OK;
+}
 int64_t wf_state_bytes_per_env(const wf_env* e) {
     if (!e) return 0;
     const DevState& s = e->st;
@@ -347,7 +378,8 @@ int64_t wf_state_bytes_per_env(const wf_env* e) {
 }
 
 static int check_obs(const void* obs, int32_t dtype) {
-    if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32) return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8 or WF_OBS_F32");
+    if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32 && dtype != kObsPacked)
+        return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8 or WF_OBS_F32");
     if (obs && (reinterpret_cast<uintptr_t>(obs) & 15u)) return fail(WF_ERR_INVALID, "obs pointer must be 16-byte aligned");
     return WF_OK;
 }
@@ -487,6 +519,9 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const std::string mode = m ? m : "hybrid";
         e->host_direct = mode != "copy";
         e->host_obs_direct = mode == "direct";
+        // WF_HOST_PACKED=0 switches the packed-observation path off (uint8 array over PCIe, no host threads)
+        const char* pk = getenv("WF_HOST_PACKED");
+        e->host_packed = !(pk && pk[0] == '0');
     }
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
@@ -496,6 +531,29 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
     void* r_d = e->host_direct ? mapped_alias(reward_host) : nullptr;
     void* d_d = e->host_direct ? mapped_alias(done_host) : nullptr;
     const bool small_direct = a_d && (r_d || !reward_host) && (d_d || !done_host);
+    if (small_direct && e->host_packed && !e->tile && obs_host && obs_dtype == WF_OBS_U8) {
+        // Packed path (grids up to 32x32): the kernel stores the observation BIT STREAM straight into mapped
+        // page-locked memory (8x fewer bytes over PCIe than the uint8 array, no DMA to launch) and the host
+        // thread pool expands it into the caller's buffer -- the compute the reference spends in np.dstack.
+        const int epw = 32 / s.RS;
+        const int64_t env_bits = (int64_t)s.W * s.H * 3, records = (s.N + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
+        const size_t need = (size_t)records * rec_words;
+        if (e->h_packed_words < need) {
+            if (e->h_packed) cudaFreeHost(e->h_packed);
+            e->h_packed = nullptr;
+            e->h_packed_words = 0;
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_packed), need * sizeof(uint32_t), cudaHostAllocMapped));
+            WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->h_packed_dev), e->h_packed, 0));
+            e->h_packed_words = need;
+        }
+        if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
+        int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->h_packed_dev, kObsPacked, static_cast<double*>(r_d),
+                         static_cast<uint8_t*>(d_d), e->hstream);
+        if (rc != WF_OK) return rc;
+        WF_CUDA(cudaStreamSynchronize(e->hstream));
+        hostpool_expand(e->pool, e->h_packed, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw, s.N);
+        return WF_OK;
+    }
     if (small_direct) {
         // The SMs' stores over PCIe reach ~39 GB/s, a DMA copy ~48 GB/s (measured, tools/e2e_modes.py):
         // the 16-36 KB of actions/reward/done go zero-copy (no per-copy latency), the observation block

@@ -23,6 +23,10 @@
 
 namespace wf {
 
+// Internal observation format of wf_step_host: the bit stream itself (1 bit per element), one record of
+// ceil(envs_per_warp * W*H*3 / 32) words per warp; expanded to bytes by the host thread pool (wf_hostpool.cpp).
+constexpr int kObsPacked = 100;
+
 enum Plane : int { P_G = 0, P_F, P_BT, P_D, P_WT, P_B, P_I, P_FU0 };  // + FB fuel planes (+ S0, S1, R for tiles)
 
 constexpr int kMaxWind = 27;  // 3 speeds x 9 vectors (environment.py:189-190) or 1 fixed entry

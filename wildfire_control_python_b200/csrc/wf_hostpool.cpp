@@ -1,0 +1,164 @@
+// wf_hostpool.cpp -- host half of wf_step_host's packed-observation path (plain C++, no CUDA).
+//
+// World.get_state (environment.py:399-402) is three 0/1 planes: over PCIe the step kernel sends the
+// bit stream itself (1 bit per element, 8x fewer bytes than the uint8 array) and the host expands it
+// into the caller's [N][W][H][3] uint8 buffer: output bytes 8i..8i+7 = the 8 bits of input byte i
+// (one PDEP per 8 output bytes, or a 256-entry table without BMI2).  A small persistent thread pool
+// splits the records; workers spin briefly for the next step and then sleep on a condition variable.
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace wf {
+
+struct ExpandJob {
+    const uint32_t* packed;  // [records][rec_words]
+    uint8_t* out;            // [n_envs][env_bits] bytes
+    int64_t records, rec_words, env_bits, envs_per_record, n_envs;
+};
+
+static uint64_t g_tab[256];
+static std::once_flag g_tab_once;
+static void init_tab() {
+    for (int v = 0; v < 256; ++v) {
+        uint64_t o = 0;
+        for (int i = 0; i < 8; ++i) o |= (uint64_t)((v >> i) & 1) << (8 * i);
+        g_tab[v] = o;
+    }
+}
+
+static void expand_table(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+    for (int64_t i = 0; i < nbytes; ++i) std::memcpy(out + 8 * i, &g_tab[in[i]], 8);
+}
+#if defined(__x86_64__)
+__attribute__((target("bmi2"))) static void expand_pdep(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+    for (int64_t i = 0; i < nbytes; ++i) {
+        const uint64_t v = _pdep_u64((uint64_t)in[i], 0x0101010101010101ull);
+        std::memcpy(out + 8 * i, &v, 8);
+    }
+}
+#endif
+
+static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
+#if defined(__x86_64__)
+    static const bool bmi2 = __builtin_cpu_supports("bmi2");
+#else
+    static const bool bmi2 = false;
+#endif
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t env0 = r * j.envs_per_record;
+        const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
+        const int64_t bits = nenv * j.env_bits;
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(j.packed + r * j.rec_words);
+        uint8_t* out = j.out + env0 * j.env_bits;
+#if defined(__x86_64__)
+        if (bmi2) expand_pdep(in, out, bits >> 3);
+        else
+#endif
+            expand_table(in, out, bits >> 3);
+        for (int64_t b = bits & ~(int64_t)7; b < bits; ++b) out[b] = (in[b >> 3] >> (b & 7)) & 1;  // ragged tail
+    }
+}
+
+class HostPool {
+public:
+    explicit HostPool(int n) : n_(n < 1 ? 1 : n) {
+        std::call_once(g_tab_once, init_tab);
+        for (int t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            seq_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (auto& th : workers_) th.join();
+    }
+    int threads() const { return n_; }
+    void run(const ExpandJob& job) {
+        job_ = job;
+        pending_.store(n_ - 1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);  // pairs with the sleepers' predicate check
+            seq_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        slice(0);
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+    }
+
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        _mm_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void slice(int t) {
+        const int64_t per = (job_.records + n_ - 1) / n_;
+        const int64_t r0 = per * t, r1 = (r0 + per < job_.records) ? r0 + per : job_.records;
+        if (r0 < r1) expand_records(job_, r0, r1);
+    }
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            int spins = 0;
+            while (seq_.load(std::memory_order_acquire) == seen) {
+                if (++spins < 20000) {  // ~50-100 us of spinning covers the gap between two steps of a tight loop
+                    cpu_relax();
+                    continue;
+                }
+                std::unique_lock<std::mutex> lk(m_);
+                sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                cv_.wait(lk, [&] { return seq_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+            }
+            seen = seq_.load(std::memory_order_acquire);
+            if (stop_) return;
+            slice(t);
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    ExpandJob job_{};
+    std::atomic<uint64_t> seq_{0};
+    std::atomic<int> pending_{0}, sleepers_{0};
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// C-level hooks used by wf_api.cu
+HostPool* hostpool_create(int threads) { return new HostPool(threads); }
+void hostpool_destroy(HostPool* p) { delete p; }
+int hostpool_threads(const HostPool* p) { return p ? p->threads() : 0; }
+void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words, int64_t env_bits,
+                     int64_t envs_per_record, int64_t n_envs) {
+    ExpandJob j{packed, out, records, rec_words, env_bits, envs_per_record, n_envs};
+    p->run(j);
+}
+int hostpool_default_threads() {
+    if (const char* v = getenv("WF_HOST_THREADS")) {
+        const int n = atoi(v);
+        if (n >= 1) return n > 64 ? 64 : n;
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    int local = 1;  // ranks sharing this host (torchrun sets LOCAL_WORLD_SIZE)
+    if (const char* v = getenv("LOCAL_WORLD_SIZE")) local = atoi(v) > 0 ? atoi(v) : 1;
+    int n = (int)(hc ? hc : 4) / (2 * local);
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+}  // namespace wf
