@@ -148,7 +148,9 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * be page-locked for full PCIe rate; pageable memory works but is slower.
  * With page-locked buffers, uint8 observations and a grid up to 32x32 the observation crosses PCIe as a
  * bit stream and is expanded into obs_host by a small pool of host threads (WF_HOST_THREADS, default
- * min(8, cores / 2 / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead). */
+ * min(12, 3/4 of the cores / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead,
+ * WF_HOST_PACKED=direct stores the bit stream straight into mapped host memory instead of one DMA copy;
+ * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed). */
 int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32_t obs_dtype,
                  double* reward_host, uint8_t* done_host);
 /* Host threads wf_step_host uses to expand observations (0: the packed path has not been used). */

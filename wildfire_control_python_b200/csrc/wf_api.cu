@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <chrono>
 
 #include "wf_families.cuh"
 
@@ -61,8 +62,12 @@ struct wf_env {
     bool host_packed;
     uint32_t* h_packed;      // host address
     uint32_t* h_packed_dev;  // device alias
+    uint32_t* d_packed;      // HBM staging (WF_HOST_PACKED=dma: kernel -> HBM -> one DMA copy)
+    bool packed_dma;
     size_t h_packed_words;
     HostPool* pool;
+    double t_launch, t_sync, t_expand;  // WF_HOST_TIMING=1: accumulated seconds of the packed path's three parts
+    int64_t t_calls;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -350,7 +355,11 @@ void wf_destroy(wf_env* e) {
     cudaFree(e->wind_dev);
     cudaFree(e->mlp_dev);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
+    if (e->t_calls && getenv("WF_HOST_TIMING"))
+        fprintf(stderr, "wf_step_host (packed path), %lld calls: launch %.2f us, sync %.2f us, expand %.2f us per call\n",
+                (long long)e->t_calls, 1e6 * e->t_launch / e->t_calls, 1e6 * e->t_sync / e->t_calls, 1e6 * e->t_expand / e->t_calls);
     if (e->h_packed) cudaFreeHost(e->h_packed);
+    cudaFree(e->d_packed);
     if (e->pool) hostpool_destroy(e->pool);
     if (e->hstream) cudaStreamDestroy(e->hstream);
     delete e;
@@ -522,6 +531,7 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         // WF_HOST_PACKED=0 switches the packed-observation path off (uint8 array over PCIe, no host threads)
         const char* pk = getenv("WF_HOST_PACKED");
         e->host_packed = !(pk && pk[0] == '0');
+        e->packed_dma = !(pk && std::string(pk) == "direct");  // default: stage in HBM, one DMA copy ("direct": zero-copy stores)
     }
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
@@ -540,18 +550,31 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const size_t need = (size_t)records * rec_words;
         if (e->h_packed_words < need) {
             if (e->h_packed) cudaFreeHost(e->h_packed);
+            cudaFree(e->d_packed);
             e->h_packed = nullptr;
+            e->d_packed = nullptr;
             e->h_packed_words = 0;
+            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_packed), need * sizeof(uint32_t)));
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_packed), need * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->h_packed_dev), e->h_packed, 0));
             e->h_packed_words = need;
         }
         if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
-        int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->h_packed_dev, kObsPacked, static_cast<double*>(r_d),
-                         static_cast<uint8_t*>(d_d), e->hstream);
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->packed_dma ? e->d_packed : e->h_packed_dev, kObsPacked,
+                         static_cast<double*>(r_d), static_cast<uint8_t*>(d_d), e->hstream);
         if (rc != WF_OK) return rc;
+        if (e->packed_dma)
+            WF_CUDA(cudaMemcpyAsync(e->h_packed, e->d_packed, need * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->hstream));
+        const auto t1 = std::chrono::steady_clock::now();
         WF_CUDA(cudaStreamSynchronize(e->hstream));
+        const auto t2 = std::chrono::steady_clock::now();
         hostpool_expand(e->pool, e->h_packed, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw, s.N);
+        const auto t3 = std::chrono::steady_clock::now();
+        e->t_launch += std::chrono::duration<double>(t1 - t0).count();
+        e->t_sync += std::chrono::duration<double>(t2 - t1).count();
+        e->t_expand += std::chrono::duration<double>(t3 - t2).count();
+        e->t_calls += 1;
         return WF_OK;
     }
     if (small_direct) {

@@ -3,7 +3,7 @@
 // World.get_state (environment.py:399-402) is three 0/1 planes: over PCIe the step kernel sends the
 // bit stream itself (1 bit per element, 8x fewer bytes than the uint8 array) and the host expands it
 // into the caller's [N][W][H][3] uint8 buffer: output bytes 8i..8i+7 = the 8 bits of input byte i
-// (one PDEP per 8 output bytes, or a 256-entry table without BMI2).  A small persistent thread pool
+// (AVX2: 32 output bytes per iteration; else one PDEP per 8 output bytes, or a 256-entry table).  A small persistent thread pool
 // splits the records; workers spin briefly for the next step and then sleep on a condition variable.
 #include <atomic>
 #include <condition_variable>
@@ -48,9 +48,28 @@ __attribute__((target("bmi2"))) static void expand_pdep(const uint8_t* in, uint8
 }
 #endif
 
+#if defined(__x86_64__)
+// 4 input bytes -> 32 output bytes per iteration: broadcast, route byte k/8 to lane k, test bit k%8.
+__attribute__((target("avx2"))) static void expand_avx2(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+    const __m256i route = _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3);
+    const __m256i bit = _mm256_set1_epi64x((long long)0x8040201008040201ull);
+    const __m256i one = _mm256_set1_epi8(1);
+    int64_t i = 0;
+    for (; i + 4 <= nbytes; i += 4) {
+        uint32_t v;
+        std::memcpy(&v, in + i, 4);
+        const __m256i b = _mm256_shuffle_epi8(_mm256_set1_epi32((int)v), route);
+        const __m256i r = _mm256_and_si256(_mm256_cmpeq_epi8(_mm256_and_si256(b, bit), bit), one);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + 8 * i), r);
+    }
+    for (; i < nbytes; ++i) std::memcpy(out + 8 * i, &g_tab[in[i]], 8);
+}
+#endif
+
 static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
 #if defined(__x86_64__)
     static const bool bmi2 = __builtin_cpu_supports("bmi2");
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
 #else
     static const bool bmi2 = false;
 #endif
@@ -61,7 +80,8 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
         const uint8_t* in = reinterpret_cast<const uint8_t*>(j.packed + r * j.rec_words);
         uint8_t* out = j.out + env0 * j.env_bits;
 #if defined(__x86_64__)
-        if (bmi2) expand_pdep(in, out, bits >> 3);
+        if (avx2) expand_avx2(in, out, bits >> 3);
+        else if (bmi2) expand_pdep(in, out, bits >> 3);
         else
 #endif
             expand_table(in, out, bits >> 3);
@@ -157,8 +177,8 @@ int hostpool_default_threads() {
     unsigned hc = std::thread::hardware_concurrency();
     int local = 1;  // ranks sharing this host (torchrun sets LOCAL_WORLD_SIZE)
     if (const char* v = getenv("LOCAL_WORLD_SIZE")) local = atoi(v) > 0 ? atoi(v) : 1;
-    int n = (int)(hc ? hc : 4) / (2 * local);
-    return n < 1 ? 1 : (n > 8 ? 8 : n);
+    int n = (int)(hc ? hc : 4) * 3 / (4 * local);  // three quarters of this rank's share of the cores, at most 12
+    return n < 1 ? 1 : (n > 12 ? 12 : n);
 }
 
 }  // namespace wf
