@@ -15,6 +15,9 @@ every field.
                 are written to HBM into a buffer larger than L2.
   e2e           the same metric through the host-buffer C-ABI call wf_step_host (page-locked host
                 buffers): per step actions H2D, step, obs + reward + done D2H, synchronise; wall clock.
+                For grids up to 32x32 the observation crosses PCIe as a bit stream (d2h_bytes_per_step
+                counts those bytes) and the library's host threads expand it into the caller's uint8
+                [N][W][H][3] buffer inside the timed region (obs_bytes_delivered_per_step).
   per_step_launch   one wf_step per step with device-resident actions (Python loop, and CUDA graph).
   roofline      dominant kernel; algorithmic bytes per SURVEY.md 8(d) (15 B per cell-update) and,
                 beside it, the bytes this layout must move.
@@ -280,8 +283,15 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, no_graph: bool,
             env.step_host(host_actions[3 + k])
         torch.cuda.synchronize()
         te = D.max_over_ranks(time.perf_counter() - t0)
+        obs_bytes = N * W * H * 3
+        if env.host_threads:  # packed path: one record of ceil(e * W*H*3 / 32) words per e envs (e = 2 if W <= 16 else 1)
+            epw = 2 if W <= 16 else 1
+            d2h_obs = ((N + epw - 1) // epw) * ((epw * W * H * 3 + 31) // 32) * 4
+        else:
+            d2h_obs = obs_bytes
         res["e2e"] = {"value": world * N * Ke / te, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
-                      "d2h_bytes_per_step": N * W * H * 3 + N * 8 + N, "steps": Ke, "us_per_step": te * 1e6 / Ke,
+                      "d2h_bytes_per_step": d2h_obs + N * 8 + N, "obs_bytes_delivered_per_step": obs_bytes,
+                      "steps": Ke, "us_per_step": te * 1e6 / Ke,
                       "host_threads": env.host_threads,
                       "api": ("wf_step_host, page-locked host buffers: actions/reward/done zero-copy; observation sent as a bit "
                               "stream into mapped host memory and expanded to the uint8 array by the library's host threads"
