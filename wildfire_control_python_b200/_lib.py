@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "wildfire.h")]
     newest = max(os.path.getmtime(p) for p in srcs)
     if force or not os.path.isfile(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
-        r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+        r = subprocess.run(["make", "-j4", "-C", CSRC], capture_output=True, text=True)
         if verbose or r.returncode != 0:
             print(r.stdout[-4000:], r.stderr[-8000:])
         if r.returncode != 0:
