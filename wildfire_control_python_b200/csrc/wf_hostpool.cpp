@@ -6,6 +6,7 @@
 // (AVX2: 32 output bytes per iteration; else one PDEP per 8 output bytes, or a 256-entry table).  A small persistent thread pool
 // splits the records; workers spin briefly for the next step and then sleep on a condition variable.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
@@ -133,9 +134,12 @@ private:
     void loop(int t) {
         uint64_t seen = 0;
         for (;;) {
+            const auto t_idle = std::chrono::steady_clock::now();
             int spins = 0;
             while (seq_.load(std::memory_order_acquire) == seen) {
-                if (++spins < 20000) {  // ~50-100 us of spinning covers the gap between two steps of a tight loop
+                // ~150 us of spinning covers the gap between two steps of a tight loop; then sleep, so that an
+                // idle handle (or a caller that computes for long between steps) gets its cores back
+                if ((++spins & 63) != 0 || std::chrono::steady_clock::now() - t_idle < std::chrono::microseconds(150)) {
                     cpu_relax();
                     continue;
                 }
