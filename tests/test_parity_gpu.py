@@ -86,6 +86,8 @@ SCENARIOS = [
     dict(width=100, height=70, seed=110, wind=[0.85, (1, 0)], extra_ignitions=10, a_speed=2),
     dict(width=48, height=33, seed=111, allow_dig_toggle=True, n_actions=6, wind=[0.85, (0, -1)], extra_ignitions=2),
     dict(width=33, height=20, seed=112, fuel=50, threshold=4.0),
+    # 4 words per row (128-bit path) with a ragged last word: H = 100
+    dict(width=120, height=100, seed=113, wind=[0.85, (0, 1)], extra_ignitions=5),
 ]
 
 
