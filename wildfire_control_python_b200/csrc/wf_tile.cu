@@ -9,6 +9,7 @@
 //   agent phase   thread 0 of every CTA (redundantly, from identical inputs): action, Agent.move /
 //                 toggle_digging / is_dead (environment.py:116-171), local articulation test for the
 //                 reach plane.  Reads only; the dig is applied by the thread that owns the word.
+//                 (Runs while the other warps still emit the previous step's observation.)
 //   barrier X     (cluster)  nobody writes a plane before everybody has read the agent's surroundings
 //   tick          stream G, B and the heat-source mask S (1 bit/cell: burning and fuel >= 2) of the
 //                 slice; words that burn or are heated are queued in shared memory and handed one per
@@ -55,6 +56,7 @@ struct StepShared {
     int32_t tot[4];       // cluster totals: burning cells, grass cells, ignition on edge, burning touches reach
     int32_t reset_now;
     int32_t obs_vis, obs_ax, obs_ay;  // agent_pos layer of the observation being emitted
+    int32_t obs_ctr;                  // next 128-word observation group of this CTA (dynamic distribution)
     uint32_t stat[ST_N];  // this launch's contribution to the handle's statistics (flushed once, at the end)
 };
 
@@ -627,8 +629,10 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
 // consecutive words in shared memory (3 KB of output); then lane l expands the 16 stream bits of
 // 16-byte chunk it*32+l with two lookups in a byte -> 8 bytes table: every store instruction writes
 // 512 contiguous bytes.  2 plane words in, 96 bytes out per word.
+// ctr (optional, shared, zeroed by the caller): the warps take their 128-word groups from this counter instead of
+// a fixed stride, so that a warp that starts late (warp 0 runs the next step's agent phase first) does less.
 __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int obs_dtype, const uint32_t* spread3,
-                                               const uint2* tab8, uint32_t* stage_all, int vis, int ax, int ay) {
+                                               const uint2* tab8, uint32_t* stage_all, int vis, int ax, int ay, int* ctr = nullptr) {
     const int W = e.W, H = e.H, HW = e.HW;
     const int lane = e.tid & 31, warp = e.tid >> 5, nwarps = e.T >> 5;
     const uint32_t* PF = e.plane(P_F);
@@ -645,16 +649,24 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
         const int n128 = (e.hi - e.lo) >> 7;  // full 128-word groups of this slice
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         uint4 F4 = z4, I4 = z4;
-        if (warp < n128) {
-            F4 = *reinterpret_cast<const uint4*>(PF + e.lo + warp * 128 + 4 * lane);
-            I4 = *reinterpret_cast<const uint4*>(PI + e.lo + warp * 128 + 4 * lane);
+        auto next_group = [&](int prev) -> int {  // warp-uniform
+            if (ctr == nullptr) return prev < 0 ? warp : prev + nwarps;
+            int v = 0;
+            if (lane == 0) v = atomicAdd(ctr, 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+        int gi = next_group(-1);
+        if (gi < n128) {
+            F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gi * 128 + 4 * lane);
+            I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gi * 128 + 4 * lane);
         }
-        for (int gi = warp; gi < n128; gi += nwarps) {
+        while (gi < n128) {
             const int g = e.lo + gi * 128;
             const uint4 Fc = F4, Ic = I4;
-            if (gi + nwarps < n128) {
-                F4 = *reinterpret_cast<const uint4*>(PF + g + nwarps * 128 + 4 * lane);
-                I4 = *reinterpret_cast<const uint4*>(PI + g + nwarps * 128 + 4 * lane);
+            const int gn = next_group(gi);
+            if (gn < n128) {
+                F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gn * 128 + 4 * lane);
+                I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gn * 128 + 4 * lane);
             }
             const uint32_t Fw[4] = {Fc.x, Fc.y, Fc.z, Fc.w}, Iw[4] = {Ic.x, Ic.y, Ic.z, Ic.w};
 #pragma unroll
@@ -680,6 +692,7 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
                 __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
             }
             __syncwarp();
+            gi = gn;
         }
         g_first = e.lo + n128 * 128;  // the slice's tail (< 128 words) takes the narrow path
     }
@@ -933,12 +946,18 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
         if (io.obs != nullptr) emit_obs_slice(e, io.obs, io.obs_dtype, spread3, tab8, qmem, sc[WF_S_VISIBLE], sc[WF_S_AX], sc[WF_S_AY]);
     } else {
         // ---------------- K x ForestFire.step(action) ----------------
+        // The agent phase of step k+1 (one thread, a few dependent loads) runs while the other warps emit the
+        // observation of step k: nothing writes a plane between barrier Y of step k and barrier X of step k+1.
         int it = io.a_iter0;
+        auto tick_of = [&](int& iter) -> int {  // the fire ticks once every a_speed steps (forest_fire.py:40-43)
+            iter -= 1;
+            const int dt = (iter == 0);
+            if (dt) iter = c.a_speed;
+            return dt;
+        };
+        int do_tick = tick_of(it);
+        if (tid == 0 && io.K > 0) agent_phase(e, c, t, io, s, 0, do_tick, sc, ss, writer);
         for (int k = 0; k < io.K; ++k) {
-            it -= 1;
-            const int do_tick = (it == 0);  // the fire ticks once every a_speed steps (forest_fire.py:40-43)
-            if (do_tick) it = c.a_speed;
-            if (tid == 0) agent_phase(e, c, t, io, s, k, do_tick, sc, ss, writer);
             WF_TSTAMP(0);
             sync_env<CL>();  // barrier X
             WF_TSTAMP(1);
@@ -994,6 +1013,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                     }
                     ss.reset_now = c.auto_reset && is_done;
                     ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
+                    ss.obs_ctr = 0;
                 }
             } else if (tid == 0) {  // frozen env: reward 0, done 1, nothing moves
                 if (writer) {
@@ -1002,15 +1022,23 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                 }
                 ss.reset_now = 0;
                 ss.obs_vis = sc[WF_S_VISIBLE]; ss.obs_ax = sc[WF_S_AX]; ss.obs_ay = sc[WF_S_AY];
+                ss.obs_ctr = 0;
             }
             WF_TSTAMP(5);
             __syncthreads();
             WF_TSTAMP(6);
-            if (ss.reset_now) reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
+            if (ss.reset_now) {
+                reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
+                if (tid == 0) ss.obs_ctr = 0;
+                __syncthreads();
+            }
             WF_TSTAMP(7);
+            const int obs_vis = ss.obs_vis, obs_ax = ss.obs_ax, obs_ay = ss.obs_ay;
+            do_tick = tick_of(it);  // of step k+1
+            if (tid == 0 && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
             if (io.obs != nullptr)
                 emit_obs_slice(e, static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype, spread3, tab8, qmem,
-                               ss.obs_vis, ss.obs_ax, ss.obs_ay);
+                               obs_vis, obs_ax, obs_ay, &ss.obs_ctr);
             WF_TSTAMP(8);
         }
     }
