@@ -208,32 +208,44 @@ class DQN:
         t = state if torch.is_tensor(state) else torch.as_tensor(np.asarray(state))
         return t.reshape((1,) + self.obs_shape).to(device=self.device, dtype=torch.float32)
 
-    def learn(self, n_episodes=1000):  # DQN.py:65-153
-        start_time = time.time()
+    def learn(self, n_episodes=1000):
+        """The training loop of DQN.learn (DQN.py:65-153) and DQN_SARSA.learn (DQN_SARSA.py:12-100): one episode
+        after another, one ``replay`` per step once the memory holds more than a batch, target network
+        refreshed every ``target_update`` steps, epsilon decayed per episode, logs written at the end.
+        The on-policy variant picks the next action BEFORE storing the transition (it is part of it)."""
+        t_run = time.time()
         self.logs["n_episodes"] = n_episodes
-        target_update_counter = self.target_update_freq
+        until_sync = self.target_update_freq
+        batch = self.METADATA["batch_size"]
         for episode in range(n_episodes):
-            done = False
-            total_reward = 0
-            t0 = time.time()
+            t_episode = time.time()
             state = self._as_batch(self.sim.reset())
-            if self.DEBUG > 0:
-                self.logs["agent_pos"].append((self.sim.W.agents[0].x, self.sim.W.agents[0].y))
+            if self.DEBUG > 0 and not self._SARSA:  # only DQN.learn records the start cell (DQN.py:89-91)
+                me = self.sim.W.agents[0]
+                self.logs["agent_pos"].append((me.x, me.y))
+            action = self.choose_action(state) if self._SARSA else None
+            episode_return, done = 0, False
             while not done:
-                action = self.choose_action(state)
-                sprime, reward, done, _ = self.sim.step(action)
-                sprime = self._as_batch(sprime)
-                self.remember(state, action, reward, sprime, done)
-                if len(self.memory) > self.METADATA["batch_size"]:
+                if not self._SARSA:
+                    action = self.choose_action(state)
+                observed, reward, done, _ = self.sim.step(action)
+                observed = self._as_batch(observed)
+                if self._SARSA:
+                    upcoming = self.choose_action(observed)
+                    self.remember(state, action, reward, observed, upcoming, done)
+                else:
+                    upcoming = None
+                    self.remember(state, action, reward, observed, done)
+                if len(self.memory) > batch:
                     self.replay()
-                target_update_counter -= 1
-                if target_update_counter == 0:
-                    target_update_counter = self.target_update_freq
+                until_sync -= 1
+                if until_sync == 0:
+                    until_sync = self.target_update_freq
                     self.target.load_state_dict(self.model.state_dict())
-                state = sprime
-                total_reward += reward
-            self._end_of_episode(episode, total_reward, t0)
-        self.logs["total_time"] = round(time.time() - start_time, 3)
+                state, action = observed, upcoming
+                episode_return += reward
+            self._end_of_episode(episode, episode_return, t_episode)
+        self.logs["total_time"] = round(time.time() - t_run, 3)
         self.write_data()
 
     def _end_of_episode(self, episode, total_reward, t0):  # DQN.py:120-148
@@ -332,43 +344,51 @@ class DQN:
                 print("\n| ", end="")
         print(f"\nBest Action: {key_map[int(np.argmax(qvals))]}\n")
 
-    def collect_memories(self, num_of_episodes=100, perform_baseline=False):  # DQN.py:286-348
-        """Demonstration data: walk clockwise round the fire; keep only the episodes that contain it.
-        With ``perform_baseline`` nothing is stored: the heuristic policy is just evaluated."""
+    def collect_memories(self, num_of_episodes=100, perform_baseline=False):
+        """Demonstration data (DQN.py:286-348, DQN_SARSA.py:148-191): the heuristic walk round the fire drives the
+        env; an episode's transitions enter the (now unbounded, DQN.py:290) memory only if it pays the
+        containment bonus, and it is cut there; stop after ``num_of_episodes`` such episodes.
+        ``perform_baseline`` (main.py:60-61): store nothing, play ``num_of_episodes`` whole episodes of the
+        heuristic policy and log their returns and deaths."""
         if not num_of_episodes:
             return
-        self.memory = self._new_memory(None)  # `self.memory = deque()`: unbounded (DQN.py:290)
-        success_count = 0
-        episode = 0
+        self.memory = self._new_memory(None)
+        bonus = self.METADATA["contained_bonus"]
+        kept, played = 0, 0
         while True:
-            total_reward = 0
-            memories = list()
-            done = False
+            episode, episode_return, done = [], 0, False
             state = self._as_batch(self.sim.reset())
+            action = self.choose_randomwalk_action() if self._SARSA else None
             while not done:
-                action = self.choose_randomwalk_action()
-                sprime, reward, done, _ = self.sim.step(action)
-                sprime = self._as_batch(sprime)
-                memories.append((state, action, reward, sprime, done))
-                state = sprime
-                total_reward += reward
-                if not perform_baseline and reward == self.METADATA["contained_bonus"]:
-                    success_count += 1
-                    for m in memories:
-                        self.remember(*m)
-                    done = True
-                    if success_count == num_of_episodes:
+                if not self._SARSA:
+                    action = self.choose_randomwalk_action()
+                observed, reward, done, _ = self.sim.step(action)
+                observed = self._as_batch(observed)
+                if self._SARSA:
+                    upcoming = self.choose_randomwalk_action()
+                    episode.append((state, action, reward, observed, upcoming, done))
+                else:
+                    upcoming = None
+                    episode.append((state, action, reward, observed, done))
+                state, action = observed, upcoming
+                episode_return += reward
+                if not perform_baseline and reward == bonus:
+                    kept += 1
+                    for transition in episode:
+                        self.remember(*transition)
+                    if kept == num_of_episodes:
                         self.logs["init_memories"] = len(self.memory)
                         return
+                    break
             if perform_baseline:
-                self.logs["total_rewards"].append(total_reward)
-                if self.verbose and episode % 100 == 0:
-                    print(f"Episode {episode}/{num_of_episodes}")
+                self.logs["total_rewards"].append(episode_return)
                 self.logs["agent_deaths"].append(len(self.sim.W.agents) == 0)
-                if episode == num_of_episodes - 1:
+                if self.verbose and played % 100 == 0:
+                    print(f"Episode {played}/{num_of_episodes}")
+                played += 1
+                if played == num_of_episodes:
                     self.logs["n_episodes"] = num_of_episodes
                     break
-                episode += 1
         self.write_data()
 
     def collect_memories_batched(self, num_of_episodes=100, n_envs=1024, k_steps=256, seed=0):
@@ -422,30 +442,32 @@ class DQN:
         self.logs["init_memories"] = len(self.memory)
         return simulated
 
-    def choose_randomwalk_action(self, avoid_fire=True):  # DQN.py:353-389
-        if not self.sim.W.agents:
+    @staticmethod
+    def _clockwise_options(ax, ay, mid_x, mid_y):
+        """The two moves that keep the agent circling the fire origin clockwise (DQN.py:369-376); actions are
+        0 N, 1 S, 2 E, 3 W.  The four half-open quadrants tile the map except the origin itself."""
+        if ax >= mid_x and ay > mid_y:
+            return (1, 3)
+        if ax > mid_x and ay <= mid_y:
+            return (1, 2)
+        if ax <= mid_x and ay < mid_y:
+            return (0, 2)
+        if ax < mid_x and ay >= mid_y:
+            return (0, 3)
+        raise UnboundLocalError("the agent stands on the fire origin: the reference has no move for that cell")
+
+    def choose_randomwalk_action(self, avoid_fire=True):
+        """DQN.choose_randomwalk_action (DQN.py:353-389): a random one of the two clockwise moves, redrawn (at most
+        11 times) while it would step onto a burning cell.  0 when the agent is gone (SARSA asks anyway)."""
+        live = self.sim.W.agents
+        if not live:
             return 0
-        key_map = {"N": 0, "S": 1, "E": 2, "W": 3}
-        width, height = self.sim.W.WIDTH, self.sim.W.HEIGHT
-        agent_x, agent_y = self.sim.W.agents[0].x, self.sim.W.agents[0].y
-        mid_x, mid_y = (int(width / 2), int(height / 2))
-        count = 0
-        while True:
-            if agent_x >= mid_x and agent_y > mid_y:
-                possible_actions = ["S", "W"]
-            if agent_x > mid_x and agent_y <= mid_y:
-                possible_actions = ["S", "E"]
-            if agent_x <= mid_x and agent_y < mid_y:
-                possible_actions = ["N", "E"]
-            if agent_x < mid_x and agent_y >= mid_y:
-                possible_actions = ["N", "W"]
-            action = key_map[np.random.choice(possible_actions)]
-            if not avoid_fire:
+        me = live[0]
+        options = self._clockwise_options(me.x, me.y, int(self.sim.W.WIDTH / 2), int(self.sim.W.HEIGHT / 2))
+        for attempt in range(12):
+            action = options[int(np.random.choice(2))]
+            if not avoid_fire or not me.fire_in_direction(action):
                 break
-            fire_at_loc = self.sim.W.agents[0].fire_in_direction(action)
-            if not fire_at_loc or count > 10:
-                break
-            count += 1
         return action
 
     # ------------------------------------------------------------------ persistence
@@ -616,34 +638,6 @@ class DQN_SARSA(DQN):
     def __init__(self, sim, name="no_name", verbose=True, device=None):
         DQN.__init__(self, sim, name, verbose, device)
 
-    def learn(self, n_episodes=1000):  # DQN_SARSA.py:12-100
-        start_time = time.time()
-        self.logs["n_episodes"] = n_episodes
-        target_update_counter = self.target_update_freq
-        for episode in range(n_episodes):
-            done = False
-            total_reward = 0
-            t0 = time.time()
-            state = self._as_batch(self.sim.reset())
-            action = self.choose_action(state)
-            while not done:
-                sprime, reward, done, _ = self.sim.step(action)
-                sprime = self._as_batch(sprime)
-                aprime = self.choose_action(sprime)
-                self.remember(state, action, reward, sprime, aprime, done)
-                if len(self.memory) > self.METADATA["batch_size"]:
-                    self.replay()
-                target_update_counter -= 1
-                if target_update_counter == 0:
-                    target_update_counter = self.target_update_freq
-                    self.target.load_state_dict(self.model.state_dict())
-                state = sprime
-                action = aprime
-                total_reward += reward
-            self._end_of_episode(episode, total_reward, t0)
-        self.logs["total_time"] = round(time.time() - start_time, 3)
-        self.write_data()
-
     def _bootstrap(self, q_next, aprime):
         """On-policy value of S': Q_target(S', A') (DQN_SARSA.py:120-121)."""
         return q_next.gather(1, aprime[:, None])[:, 0]
@@ -651,31 +645,8 @@ class DQN_SARSA(DQN):
     def remember(self, state, action, reward, sprime, aprime, done):  # DQN_SARSA.py:134-135
         self.memory.append(state, action, reward, sprime, done, aprime)
 
-    def collect_memories(self, num_of_successes=100):  # DQN_SARSA.py:148-191
-        if not num_of_successes:
-            return
-        self.memory = self._new_memory(None)
-        success_count = 0
-        while True:
-            memories = []
-            done = False
-            state = self._as_batch(self.sim.reset())
-            action = self.choose_randomwalk_action()
-            while not done:
-                sprime, reward, done, _ = self.sim.step(action)
-                sprime = self._as_batch(sprime)
-                aprime = self.choose_randomwalk_action()
-                memories.append((state, action, reward, sprime, aprime, done))
-                state = sprime
-                action = aprime
-                if reward == self.METADATA["contained_bonus"]:
-                    success_count += 1
-                    for m in memories:
-                        self.remember(*m)
-                    done = True
-                    if success_count == num_of_successes:
-                        self.logs["init_memories"] = len(self.memory)
-                        return
+    def collect_memories(self, num_of_successes=100):  # DQN_SARSA.py:148-191 (no baseline mode there)
+        return DQN.collect_memories(self, num_of_successes, perform_baseline=False)
 
 
 class DQN_DUEL(DQN):
