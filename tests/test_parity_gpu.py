@@ -342,3 +342,32 @@ def test_tile_cluster_geometries_match_oracle(monkeypatch, T, CS, cfg):
                     o = e.reset()
                 assert np.array_equal(obs[k, i], o), f"{policy} env {i} step {k}: obs"
         compare_states(f"after {policy} rollout", gpu, orc)
+
+
+def test_burning_border_point_is_not_its_own_goal():
+    """W > H: the reference's literal border points [HEIGHT-1, y] (environment.py:222) form a column INSIDE the
+    map, and for 24x13 the fire origin (12, 6) sits on it.  pyastar.astar_path returns an empty path when
+    start == goal (pyastar.py:53-62), so the walk policy's ring round the origin pays the containment bonus
+    although the burning cell is a border point itself (found by tools/soak.py; the Python reference agrees
+    with the oracle on this trajectory)."""
+    cfg = dict(width=24, height=13, seed=387835340, wind=[0.54, (1, 1)], allow_dig_toggle=True, n_actions=6, a_speed=2,
+               fuel=40, threshold=4.5)
+    N, K = 21, 71
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    obs, rew, done, acts = gpu.rollout(K, policy="walk", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    n_bonus = 0
+    for i, e in enumerate(orc):
+        for k in range(K):
+            assert acts[k, i] == e.walk_action(), (i, k)
+            o, r, d, _ = e.step(int(acts[k, i]))
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k, rew[k, i], r)
+            n_bonus += int(r == 1000)
+            if d:
+                o = e.reset()
+            assert np.array_equal(obs[k, i], o), (i, k)
+    assert n_bonus >= N // 2
+    compare_states("end", gpu, orc)

@@ -457,7 +457,7 @@ __device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride
     return B & ge2;  // sources of the next tick: burning with fuel >= 2
 }
 
-// Does a burning cell of word `wi` sit in, or next to, the border-connected region R?  Words of other
+// Does a burning cell of word `wi` sit next to the border-connected region R?  Words of other
 // CTAs' slices may not show this step's dig yet: the dug cell is masked out here (digw, digclr).
 __device__ __forceinline__ bool touches_reach(const uint32_t* R, int wi, uint32_t B, int x, int w, int W, int HW, int digw,
                                               uint32_t digclr) {
@@ -465,8 +465,9 @@ __device__ __forceinline__ bool touches_reach(const uint32_t* R, int wi, uint32_
         const uint32_t v = R[j];
         return j == digw ? (v & ~digclr) : v;
     };
-    uint32_t near = ld(wi);
-    near |= (near << 1) | (near >> 1);
+    // its 4 NEIGHBOURS (A* ignores the start cell's cost and finds no path when start == goal, pyastar.py:53-62)
+    const uint32_t own = ld(wi);
+    uint32_t near = (own << 1) | (own >> 1);
     if (x > 0) near |= ld(wi - HW);
     if (x < W - 1) near |= ld(wi + HW);
     if (w > 0) near |= ld(wi - 1) >> 31;

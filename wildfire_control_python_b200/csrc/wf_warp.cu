@@ -547,7 +547,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             bool contained = false;
             if (__any_sync(FULL, check)) {
                 const uint32_t free_ = ~r.I & validmask;
-                uint32_t reach = free_ & seedmask;
+                // A border point that is itself the burning start cell is NOT reachable for the reference
+                // (pyastar.astar_path returns an empty path when start == goal, pyastar.py:53-62), so burning
+                // border points do not seed the flood; they remain valid goals for their neighbours (below).
+                // Only maps with W > H have such points off the rim (the literal [HEIGHT-1, y] column).
+                const uint32_t seeds = free_ & seedmask;
+                uint32_t reach = seeds & ~r.B;
                 for (;;) {  // flood fill: cells with a finite-cost 4-connected path to a finite border point
                     uint32_t n = hfill(reach, free_);
                     uint32_t u = __shfl_up_sync(FULL, n, 1, L), d = __shfl_down_sync(FULL, n, 1, L);
@@ -558,12 +563,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                     reach = n;
                     if (!__any_sync(FULL, changed)) break;
                 }
-                uint32_t u = __shfl_up_sync(FULL, reach, 1, L), d = __shfl_down_sync(FULL, reach, 1, L);
+                const uint32_t goal = reach | seeds;  // connected to a border point, or a border point itself
+                uint32_t u = __shfl_up_sync(FULL, goal, 1, L), d = __shfl_down_sync(FULL, goal, 1, L);
                 if (x == 0) u = 0u;
                 if (x == L - 1) d = 0u;
-                // A* ignores the start cell's own cost (astar.cpp:89-90, Q5): a burning cell reaches the
-                // border iff it or one of its 4 neighbours is in `reach`.
-                const uint32_t near = reach | (reach << 1) | (reach >> 1) | u | d;
+                // A* ignores the start cell's own cost (astar.cpp:89-90, Q5) and finds nothing when the start is
+                // the goal: a burning cell reaches the border iff one of its 4 NEIGHBOURS is such a cell.
+                const uint32_t near = (goal << 1) | (goal >> 1) | u | d;
                 contained = !group_bits(__ballot_sync(FULL, (r.B & near) != 0u));
             }
             double rew = 0.0;
