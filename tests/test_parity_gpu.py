@@ -394,3 +394,32 @@ def test_burning_border_point_is_a_goal_for_other_burning_cells():
                 o = e.reset()
             assert np.array_equal(obs[k, i], o), (i, k)
     compare_states("end", gpu, orc)
+
+
+@pytest.mark.parametrize("T,CS", [(0, 0), (128, 16), (256, 2)])
+def test_tile_burning_border_point_sealed_in_a_pocket(monkeypatch, T, CS):
+    """Third W > H case from tools/soak.py (70x33, wind blowing the fire onto the interior border-point column
+    x = 32 inside the agent's ring): the only border point of the pocket is the burning cell itself, so the
+    reference pays the containment bonus.  Tile family: needs the scratch flood from the cold border points."""
+    monkeypatch.setenv("WF_TILE_T", str(T))
+    monkeypatch.setenv("WF_TILE_CS", str(CS))
+    cfg = dict(width=70, height=33, seed=359706589, wind="random")
+    N, K = 3, 87
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    obs, rew, done, acts = gpu.rollout(K, policy="walk", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    n_bonus = 0
+    for i, e in enumerate(orc):
+        for k in range(K):
+            assert acts[k, i] == e.walk_action(), (i, k)
+            o, r, d, _ = e.step(int(acts[k, i]))
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k, rew[k, i], r)
+            n_bonus += int(r == 1000)
+            if d:
+                o = e.reset()
+            assert np.array_equal(obs[k, i], o), (i, k)
+    assert n_bonus >= 1
+    compare_states("end", gpu, orc)

@@ -53,7 +53,8 @@ struct StepShared {
     uint32_t dig_bit;
     int32_t dig_clear_R;  // the dug cell leaves the reach plane
     int32_t need_flood;   // ... and may disconnect it: re-flood before the tick
-    int32_t tot[4];       // cluster totals: burning cells, grass cells, ignition on edge, burning touches reach
+    int32_t tot[8];       // cluster totals: burning cells, grass cells, ignition on edge, burning touches reach,
+                          // a burning cell is a border point (W > H maps only); 5..7 unused
     int32_t reset_now;
     int32_t obs_vis, obs_ax, obs_ay;  // agent_pos layer of the observation being emitted
     int32_t obs_ctr;                  // next 128-word observation group of this CTA (dynamic distribution)
@@ -62,6 +63,7 @@ struct StepShared {
 
 int tile_extra_planes() { return 3; }
 
+constexpr int kRed = 8;  // per-env reductions exchanged per step (power of two; T >= kRed * kMaxCluster)
 constexpr int kMaxCluster = 16;  // CTAs per cluster: 8 is the portable limit, 16 needs the non-portable opt-in
 
 // Phase timing of one probe CTA (debug builds only: -DWF_TILE_TIMING; read with wf_debug_tile_timing).
@@ -156,11 +158,11 @@ struct Env {
 // Sum the CTAs' partial reductions red[0..3] over the cluster into ss.tot[0..3] (and clear red).
 // Call with red[] complete (after a __syncthreads); returns with ss.tot visible to the whole CTA.
 template <bool CL>
-__device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[kMaxCluster][4], int& par, StepShared& ss) {
+__device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[kMaxCluster][kRed], int& par, StepShared& ss) {
     if (CL) {
-        if (e.tid < 4 * e.CS) st_shared_cluster(&xch[par][e.rank][e.tid & 3], (uint32_t)(e.tid >> 2), red[e.tid & 3]);
+        if (e.tid < kRed * e.CS) st_shared_cluster(&xch[par][e.rank][e.tid & (kRed - 1)], (uint32_t)(e.tid / kRed), red[e.tid & (kRed - 1)]);
         cluster_barrier();
-        if (e.tid < 4) {
+        if (e.tid < kRed) {
             int v = 0;
             for (int r = 0; r < e.CS; ++r) v += xch[par][r][e.tid];
             ss.tot[e.tid] = v;
@@ -168,7 +170,7 @@ __device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[kMax
         }
         par ^= 1;
     } else {
-        if (e.tid < 4) {
+        if (e.tid < kRed) {
             ss.tot[e.tid] = red[e.tid];
             red[e.tid] = 0;
         }
@@ -179,14 +181,18 @@ __device__ __forceinline__ void exchange(const Env& e, int* red, int (*xch)[kMax
 // ---------------------------------------------------------------------------------------------
 // Reach plane: R = finite cells 4-connected to a finite border point (flood from the border over
 // ~fm_inf).  Whole cluster; in-place monotone relaxation until a full sweep changes nothing anywhere.
+// `plane`: where the result goes (the persistent reach plane, or a scratch plane); `cold_only`: burning border
+// points are not sources (see seed_cells_touch).
 template <bool CL>
-__device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[kMaxCluster][4], int& par, StepShared& ss) {
+__device__ void flood(const Env& e, const TilePar& t, int* red, int (*xch)[kMaxCluster][kRed], int& par, StepShared& ss,
+                      int plane = -1, bool cold_only = false) {
     const int W = e.W, H = e.H, HW = e.HW;
-    uint32_t* R = e.plane(t.P_R);
+    uint32_t* R = e.plane(plane < 0 ? t.P_R : plane);
     const uint32_t* I = e.plane(P_I);
+    const uint32_t* Bp = e.plane(P_B);
     for (int i = e.lo + e.tid; i < e.hi; i += e.T) {
         const int x = e.row_of(i), w = i - x * HW;
-        R[i] = seed_word(W, H, x, w) & ~I[i];
+        R[i] = seed_word(W, H, x, w) & ~I[i] & (cold_only ? ~Bp[i] : 0xffffffffu);
     }
     sync_env<CL>();
     for (;;) {
@@ -507,7 +513,7 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
     const uint32_t* const Rp = e.plane(t.P_R);
     const int wid = sc[WF_S_WIND_ID];
     const int kmin = s.wind->uniform[wid] ? s.wind->kmin[wid] : -1;
-    int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0;
+    int my_nb = 0, my_ng = 0, my_edge = 0, my_touch = 0, my_bseed = 0;
     const int nu = (e.hi - e.lo + VW - 1) / VW;
     for (int ub = warp; ub * 32 < nu; ub += nwarps) {
         const int u = ub * 32 + lane;
@@ -574,7 +580,11 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
                 for (int k = 0; k < VW; ++k) {
                     my_nb += __popc(B[k]);
                     my_ng += __popc(G[k]);
-                    if (B[k] && want_touch && touches_reach(Rp, i + k, B[k], x, w0 + k, W, HW, digw_R, digclr)) my_touch = 1;
+                    if (B[k] && want_touch) {  // burning border points are judged by seed_cells_touch
+                        const uint32_t sw = seed_word(W, H, x, w0 + k);
+                        if (B[k] & sw) my_bseed = 1;
+                        if ((B[k] & ~sw) && touches_reach(Rp, i + k, B[k] & ~sw, x, w0 + k, W, HW, digw_R, digclr)) my_touch = 1;
+                    }
                 }
             }
         }
@@ -606,7 +616,11 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
             P[(size_t)snxt * pstride] = sn;
             my_nb += __popc(Bq);
             my_ng += __popc(Gq);
-            if (Bq && want_touch && touches_reach(Rp, wi, Bq, x, w, W, HW, digw_R, digclr)) my_touch = 1;
+            if (Bq && want_touch) {
+                const uint32_t sw = seed_word(W, H, x, w);
+                if (Bq & sw) my_bseed = 1;
+                if ((Bq & ~sw) && touches_reach(Rp, wi, Bq & ~sw, x, w, W, HW, digw_R, digclr)) my_touch = 1;
+            }
         }
         __syncwarp();
     }
@@ -615,12 +629,49 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
     my_ng = __reduce_add_sync(FULL, my_ng);
     my_edge = __any_sync(FULL, my_edge);
     my_touch = __any_sync(FULL, my_touch);
+    my_bseed = __any_sync(FULL, my_bseed);
     if (lane == 0) {
         if (my_nb) atomicAdd(&red[0], my_nb);
         if (my_ng) atomicAdd(&red[1], my_ng);
         if (my_edge) atomicOr(&red[2], 1);
         if (my_touch) atomicOr(&red[3], 1);
+        if (my_bseed) atomicOr(&red[4], 1);
     }
+}
+
+// Burning cells that are border points themselves.  For the reference a border point is not a goal for the A*
+// search that STARTS on it (pyastar.astar_path returns an empty path when start == goal, pyastar.py:53-62), so such
+// a cell reaches the border only through a neighbour that is a finite border point or is connected to a border
+// point that does not burn.  (Other burning cells simply test their neighbours against R, which is seeded by all
+// finite border points.)  Off the rim such cells exist only on W > H maps -- the literal [HEIGHT-1, y] column of
+// environment.py:222 -- so this rarely runs: flood a scratch plane from the cold border points, test, done.
+// Whole cluster; returns (in every thread) whether one of those cells reaches the border.
+template <bool CL>
+__device__ bool seed_cells_touch(const Env& e, const TilePar& t, int scratch_plane, int* red, int (*xch)[kMaxCluster][kRed],
+                                 int& par, StepShared& ss) {
+    const int W = e.W, H = e.H, HW = e.HW;
+    flood<CL>(e, t, red, xch, par, ss, scratch_plane, true);
+    const uint32_t* Rc = e.plane(scratch_plane);
+    const uint32_t* I = e.plane(P_I);
+    const uint32_t* B = e.plane(P_B);
+    int hit = 0;
+    for (int i = e.lo + e.tid; i < e.hi; i += e.T) {
+        const int x = e.row_of(i), w = i - x * HW;
+        const uint32_t b = B[i] & seed_word(W, H, x, w);
+        if (!b) continue;
+        auto goal = [&](int j, int xx, int ww) -> uint32_t { return Rc[j] | (seed_word(W, H, xx, ww) & ~I[j]); };
+        const uint32_t own = goal(i, x, w);
+        uint32_t near = (own << 1) | (own >> 1);
+        if (x > 0) near |= goal(i - HW, x - 1, w);
+        if (x < W - 1) near |= goal(i + HW, x + 1, w);
+        if (w > 0) near |= goal(i - 1, x, w - 1) >> 31;
+        if (w < HW - 1) near |= goal(i + 1, x, w + 1) << 31;
+        if (b & near) hit = 1;
+    }
+    if (hit) red[0] = 1;
+    __syncthreads();
+    exchange<CL>(e, red, xch, par, ss);
+    return ss.tot[0] != 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -745,7 +796,7 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
 // Agent.__init__ (:100-113), extra ignitions, reach plane, burning count.  Whole cluster.
 template <int FB, bool CL>
 __device__ void reset_env(const Env& e, const DevState& s, const StepCfg& c, const TilePar& t, const wf_init* init,
-                          int32_t* sc, StepShared& ss, int* red, int (*xch)[kMaxCluster][4], int& par) {
+                          int32_t* sc, StepShared& ss, int* red, int (*xch)[kMaxCluster][kRed], int& par) {
     const int W = e.W, H = e.H, HW = e.HW, tid = e.tid, T = e.T;
     const size_t pstride = e.pstride;
     const uint32_t episode = (uint32_t)sc[WF_S_EPISODE] + 1u;  // every thread reads the old value ...
@@ -900,8 +951,8 @@ template <int FB, int VW, bool CL>
 __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kernel(DevState s, StepCfg c, TilePar t, TileIO io) {
     extern __shared__ uint32_t qmem[];  // per-warp active-word queues (7 x 32 * VW words each); observation staging
     __shared__ int32_t sc[WF_NSCALARS];
-    __shared__ int red[4];
-    __shared__ int xch[2][kMaxCluster][4];
+    __shared__ int red[kRed];
+    __shared__ int xch[2][kMaxCluster][kRed];
     __shared__ StepShared ss;
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
@@ -930,7 +981,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
         tab8[v] = b8;
     }
     if (tid < WF_NSCALARS) sc[tid] = s.scal[(size_t)e.env * WF_NSCALARS + tid];
-    if (tid < 4) red[tid] = 0;
+    if (tid < kRed) red[tid] = 0;
     if (tid < ST_N) ss.stat[tid] = 0u;
     __syncthreads();
     int par = 0;
@@ -978,26 +1029,34 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                 WF_TSTAMP(3);
                 const int cur = sc[WF_S_RESERVED];
                 exchange<CL>(e, red, xch, par, ss);  // barrier Y
+                const int n_burning = ss.tot[0], n_grass = ss.tot[1], edge_ignition = ss.tot[2];
+                int touches = ss.tot[3];
+                const bool searching = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && n_burning > 0 && !(do_tick && edge_ignition);
+                if (ss.tot[4] && searching && !touches) {  // rare (W > H maps): a burning cell is a border point itself
+                    __syncthreads();  // every thread has read ss.tot
+                    const int scratch = ticking ? ((cur & 1) ? t.P_S1 : t.P_S0) : ((cur & 1) ? t.P_S0 : t.P_S1);  // not the current sources
+                    touches = seed_cells_touch<CL>(e, t, scratch, red, xch, par, ss) ? 1 : 0;
+                }
                 WF_TSTAMP(4);
                 if (tid == 0) {
                     // ---- RUNNING (forest_fire.py:105-106), World.get_reward (environment.py:342-390)
                     if (ticking) sc[WF_S_RESERVED] = cur ^ 1;  // the source mask just written becomes current
-                    const bool anyB = ss.tot[0] > 0;
-                    sc[WF_S_N_BURNING] = ss.tot[0];
+                    const bool anyB = n_burning > 0;
+                    sc[WF_S_N_BURNING] = n_burning;
                     if (do_tick) {
-                        if (ss.tot[2]) sc[WF_S_FIRE_AT_BORDER] = 1;
+                        if (edge_ignition) sc[WF_S_FIRE_AT_BORDER] = 1;
                         if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
                     }
                     double rew;
                     const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
-                    if (check && !ss.tot[3]) {
+                    if (check && !touches) {
                         sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
                         rew = c.contained_bonus;
                         ss.stat[ST_CONTAINED] += 1u;
                     } else if (!sc[WF_S_ALIVE]) {
                         rew = c.death_penalty;
                     } else if (!anyB) {
-                        rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)ss.tot[1], (double)(s.W * s.H)));
+                        rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)n_grass, (double)(s.W * s.H)));
                     } else {
                         rew = c.default_reward;
                     }
@@ -1051,8 +1110,8 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
 // S := B & (fuel >= 2) in the env's current source plane, R re-flooded, n_burning recounted
 // (after wf_set_state / wf_set_fire_to).  One CTA per env.
 __global__ void rebuild_kernel(DevState s, TilePar t) {
-    __shared__ int red[4];
-    __shared__ int xch[2][kMaxCluster][4];
+    __shared__ int red[kRed];
+    __shared__ int xch[2][kMaxCluster][kRed];
     __shared__ StepShared ss;
     Env e;
     e.tid = threadIdx.x; e.T = blockDim.x; e.CS = 1; e.rank = 0; e.env = blockIdx.x;
@@ -1063,7 +1122,7 @@ __global__ void rebuild_kernel(DevState s, TilePar t) {
     e.hits = s.hits + (size_t)e.env * t.cells;
     int32_t* sc = s.scal + (size_t)e.env * WF_NSCALARS;
     const int cur = sc[WF_S_RESERVED] & 1;
-    if (e.tid < 4) red[e.tid] = 0;
+    if (e.tid < kRed) red[e.tid] = 0;
     __syncthreads();
     int n = 0;
     for (int i = e.tid; i < e.nwords; i += e.T) {
