@@ -423,3 +423,27 @@ def test_tile_burning_border_point_sealed_in_a_pocket(monkeypatch, T, CS):
             assert np.array_equal(obs[k, i], o), (i, k)
     assert n_bonus >= 1
     compare_states("end", gpu, orc)
+
+
+@pytest.mark.parametrize("T,CS", [(256, 2), (128, 1), (512, 2)])
+def test_tile_slices_with_a_tail_emit_clean_observations(monkeypatch, T, CS):
+    """130x128 over a cluster of 2: each CTA's slice is a few 128-word groups plus a tail that takes the narrow
+    observation path; the two paths stage in shared memory at the same time (race found by tools/soak.py)."""
+    monkeypatch.setenv("WF_TILE_T", str(T))
+    monkeypatch.setenv("WF_TILE_CS", str(CS))
+    cfg = dict(width=130, height=128, seed=667898885, make_rivers=True)
+    N = 5
+    gpu, orc = make_pair(N, cfg, auto_reset=True)
+    for rep in range(4):
+        obs = to_np(gpu.reset())
+        for i, e in enumerate(orc):
+            assert np.array_equal(obs[i], e.reset()), (rep, i)
+    obs, rew, done, acts = gpu.rollout(40, policy="walk", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    for i, e in enumerate(orc):
+        for k in range(40):
+            o, r, d, _ = e.step(int(acts[k, i]))
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k)
+            if d:
+                o = e.reset()
+            assert np.array_equal(obs[k, i], o), (i, k)

@@ -690,7 +690,10 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
     const uint32_t* PF = e.plane(P_F);
     const uint32_t* PI = e.plane(P_I);
     const int aw = vis ? ax * HW + (ay >> 5) : -1;
-    uint32_t* stage = stage_all + warp * 96;  // 32 words x 96 bits
+    // Every warp stages in its OWN region, whichever path it takes: a warp on the narrow path (a slice's tail)
+    // must not write where another warp is still emitting a 128-word group (found by tools/soak.py: 130x128,
+    // cluster of 2).  384 words per warp exist whenever the wide path does (HW % 4 == 0 <=> VW == 4).
+    uint32_t* stage = stage_all + warp * ((HW & 3) == 0 ? 384 : 96);  // 32 words x 96 bits
     const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
     int g_first = e.lo;
     if (obs_dtype == WF_OBS_U8 && (H & 31) == 0 && (HW & 3) == 0) {
