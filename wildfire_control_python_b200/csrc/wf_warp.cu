@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                 // fire_at_border has switched the search off), so the second flood is normally skipped.
                 const uint32_t from_cold = flood(seeds & ~r.B);
                 uint32_t touch = r.B & neighbours(from_cold | seeds);
-                if (__any_sync(FULL, (seeds & r.B) != 0u)) {
+                if (__any_sync(FULL, check && (seeds & r.B) != 0u)) {  // (`check`: the warp's other env may burn at its rim)
                     const uint32_t from_burning = flood(seeds & r.B);
                     // (two burning border points joined only through unburnt cells, with no other burning cell and no
                     //  cold border point in their pocket, would still count as contained here: not reproduced)
