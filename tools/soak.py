@@ -1,6 +1,6 @@
 """Randomised differential soak test: CUDA path vs the C oracle on random configurations.
 
-    python tools/soak.py [seconds] [seed]
+    python tools/soak.py [seconds] [seed] [rollout|api]
 
 Each round draws a configuration (grid size from both kernel families, wind fixed / random / directional,
 rivers, dig toggle, a_speed, extra ignitions, fuel / threshold, tile cluster geometry), runs a fused
@@ -93,11 +93,88 @@ def one_round(rng):
     return fam, cfg, N, K, policy, n_done
 
 
+def api_round(rng):
+    """The per-call API instead of fused rollouts: step / step_host with explicit actions, masked resets as soon as
+    envs finish, World.set_fire_to injections, and a checkpoint round trip (get_state -> set_state into a second
+    handle that then has to stay in lock-step)."""
+    fam, cfg = draw_config(rng)
+    if fam == "tile":
+        T, CS = rng.choice([(0, 0), (128, 1), (128, 2), (256, 2), (128, 4), (256, 8), (128, 16)])
+        os.environ["WF_TILE_T"], os.environ["WF_TILE_CS"] = str(int(T)), str(int(CS))
+    os.environ["WF_HOST_THREADS"] = str(int(rng.integers(1, 6)))
+    N = int(rng.integers(2, 20)) if fam == "warp" else int(rng.integers(2, 6))
+    K = int(rng.integers(40, 160)) if fam == "warp" else int(rng.integers(30, 80))
+    print(f"  next(api): {fam} {cfg} N={N} K={K} T={os.environ.get('WF_TILE_T')} CS={os.environ.get('WF_TILE_CS')}", flush=True)
+    W, H = cfg["width"], cfg["height"]
+    gpu = BatchedForestFire(N, **cfg)
+    twin = None
+    orc = [wo.OracleEnv(cfg, env_id=i) for i in range(N)]
+    obs = to_np(gpu.reset())
+    for i, e in enumerate(orc):
+        assert np.array_equal(obs[i], e.reset()), "reset obs"
+    a_speed = cfg.get("a_speed", 1)
+    a_iter = a_speed
+    n_act = cfg.get("n_actions", 4)
+    for k in range(K):
+        op = rng.random()
+        if op < 0.08:  # World.set_fire_to on a few envs
+            cells = np.full((N, 2), -1, np.int32)
+            for i in rng.choice(N, size=max(1, N // 3), replace=False):
+                cells[i] = (int(rng.integers(0, W)), int(rng.integers(0, H)))
+                orc[i].set_fire_to(int(cells[i, 0]), int(cells[i, 1]))
+            gpu.set_fire_to(torch.from_numpy(cells))
+            if twin is not None:
+                twin.set_fire_to(torch.from_numpy(cells))
+        if op > 0.95 and twin is None:  # checkpoint into a second handle
+            st = gpu.get_state()
+            twin = BatchedForestFire(N, **cfg)
+            twin.set_state(type=st["type"], burning=st["burning"], fm_inf=st["fm_inf"], fuel=st["fuel"], hits=st["hits"],
+                           scalars=st["scalars"])
+        acts = rng.integers(0, n_act + 1, size=N).astype(np.int32)
+        live = [bool(e.planes()["running"]) for e in orc]
+        for e in orc:
+            e.set_a_speed_iter(a_iter)
+        a_iter = a_speed if a_iter == 1 else a_iter - 1
+        if rng.random() < 0.5:
+            o_g, r_g, d_g, _ = gpu.step_host(acts)
+            o_g, r_g, d_g = np.array(o_g), np.array(r_g), np.array(d_g)
+        else:
+            o_g, r_g, d_g, _ = gpu.step(torch.from_numpy(acts).cuda())
+            o_g, r_g, d_g = to_np(o_g), to_np(r_g), to_np(d_g)
+        for i, e in enumerate(orc):
+            if not live[i]:
+                assert r_g[i] == 0.0 and d_g[i], (i, k, "frozen env")
+                continue
+            o, r, d, _ = e.step(int(acts[i]))
+            assert r_g[i] == r and bool(d_g[i]) == d, (i, k, r_g[i], r, d_g[i], d)
+            assert np.array_equal(o_g[i], o), (i, k, "obs")
+        if twin is not None and a_speed == 1:  # (a second handle has its own a_speed_iter: keep to a_speed 1)
+            o_t, r_t, d_t, _ = twin.step(torch.from_numpy(acts).cuda())
+            assert np.array_equal(to_np(o_t), o_g) and np.array_equal(to_np(r_t), r_g), (k, "twin diverged")
+        m = np.array([not e.planes()["running"] for e in orc], np.uint8)
+        if m.any() and rng.random() < 0.5:
+            o_r = to_np(gpu.reset(mask=torch.from_numpy(m).cuda()))
+            if twin is not None:
+                twin.reset(mask=torch.from_numpy(m).cuda())
+            for i in np.nonzero(m)[0]:
+                assert np.array_equal(o_r[i], orc[i].reset()), (i, k, "masked reset obs")
+    compare_states("end", gpu, orc)
+    gpu.close()
+    if twin is not None:
+        twin.close()
+    return N * K
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    mode = sys.argv[3] if len(sys.argv) > 3 else "rollout"
     t0, rounds, steps = time.time(), 0, 0
-    while time.time() - t0 < budget:
+    while mode == "api" and time.time() - t0 < budget:
+        steps += api_round(rng)
+        rounds += 1
+        print(f"round {rounds}: ok", flush=True)
+    while mode != "api" and time.time() - t0 < budget:
         fam, cfg, N, K, policy, n_done = one_round(rng)
         rounds += 1
         steps += N * K
