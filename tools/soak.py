@@ -1,6 +1,6 @@
 """Randomised differential soak test: CUDA path vs the C oracle on random configurations.
 
-    python tools/soak.py [seconds] [seed] [rollout|api]
+    python tools/soak.py [seconds] [seed] [rollout|api|mlp]
 
 Each round draws a configuration (grid size from both kernel families, wind fixed / random / directional,
 rivers, dig toggle, a_speed, extra ignitions, fuel / threshold, tile cluster geometry), runs a fused
@@ -165,16 +165,75 @@ def api_round(rng):
     return N * K
 
 
+def mlp_round(rng):
+    """WF_POLICY_MLP with random networks: hidden size, action count, grid size (both lane layouts of the warp family),
+    epsilon; every chosen action against a float64 evaluation, every transition against the oracle."""
+    from oracle import philox
+    size = int(rng.integers(10, 33))
+    n_act = int(rng.choice([4, 4, 5, 6]))
+    cfg = dict(width=size, height=size, seed=int(rng.integers(1, 1 << 30)), n_actions=n_act)
+    if n_act > 4 and rng.random() < 0.7:
+        cfg["allow_dig_toggle"] = True
+    if rng.random() < 0.4:
+        cfg["wind"] = "random"
+    if rng.random() < 0.3:
+        cfg["make_rivers"] = True
+    hid = int(rng.integers(1, 65))
+    eps = float(rng.choice([0.0, 0.05, 0.3, 1.0]))
+    N, K = int(rng.integers(2, 30)), int(rng.integers(40, 200))
+    print(f"  next(mlp): {cfg} hid={hid} eps={eps} N={N} K={K}", flush=True)
+    scale = float(rng.choice([0.1, 1.0, 10.0]))
+    w1 = (rng.standard_normal((size * size * 3, hid)) * scale / np.sqrt(size)).astype(np.float32)
+    b1 = (rng.standard_normal(hid) * scale).astype(np.float32)
+    w2 = (rng.standard_normal((hid, n_act)) * scale).astype(np.float32)
+    b2 = (rng.standard_normal(n_act) * scale).astype(np.float32)
+    gpu = BatchedForestFire(N, auto_reset=True, **cfg)
+    gpu.set_policy_mlp(w1, b1, w2, b2, eps=eps)
+    orc = [wo.OracleEnv(cfg, env_id=i) for i in range(N)]
+    obs0 = to_np(gpu.reset())
+    for e in orc:
+        e.reset()
+    obs, rew, done, acts = gpu.rollout(K, policy="mlp", return_actions=True)
+    obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+    eps_u32 = 0xFFFFFFFF if eps >= 1.0 else int(eps * 4294967296.0)
+    w1d, b1d, w2d, b2d = (a.astype(np.float64) for a in (w1, b1, w2, b2))
+    ties = 0
+    for i, e in enumerate(orc):
+        episode, t = 0, 0
+        for k in range(K):
+            seen = obs0[i] if k == 0 else obs[k - 1, i]
+            u0, u1 = philox.explore_draw(cfg["seed"], i, episode, t)
+            a = int(acts[k, i])
+            if u0 < eps_u32:
+                assert a == u1 % n_act, (i, k, "explore")
+            else:
+                h = seen.reshape(-1).astype(np.float64) @ w1d + b1d
+                q = (1.0 / (1.0 + np.exp(-np.clip(h, -80, 80)))) @ w2d + b2d
+                assert q[a] >= q.max() - 1e-3 * max(1.0, np.abs(q).max()), (i, k, a, q)
+                ties += int(a != int(np.argmax(q)))
+            o, r, d, _ = e.step(a)
+            assert rew[k, i] == r and bool(done[k, i]) == d, (i, k)
+            t += 1
+            if d:
+                o = e.reset()
+                episode, t = episode + 1, 0
+            assert np.array_equal(obs[k, i], o), (i, k, "obs")
+    assert ties <= max(2, N * K // 200), ("too many near-ties", ties)
+    compare_states("end", gpu, orc)
+    gpu.close()
+    return N * K
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     mode = sys.argv[3] if len(sys.argv) > 3 else "rollout"
     t0, rounds, steps = time.time(), 0, 0
-    while mode == "api" and time.time() - t0 < budget:
-        steps += api_round(rng)
+    while mode in ("api", "mlp") and time.time() - t0 < budget:
+        steps += api_round(rng) if mode == "api" else mlp_round(rng)
         rounds += 1
         print(f"round {rounds}: ok", flush=True)
-    while mode != "api" and time.time() - t0 < budget:
+    while mode not in ("api", "mlp") and time.time() - t0 < budget:
         fam, cfg, N, K, policy, n_done = one_round(rng)
         rounds += 1
         steps += N * K
