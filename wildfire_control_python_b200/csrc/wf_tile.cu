@@ -2,27 +2,29 @@
 //
 // Same bit-plane state as the warp family (wf_common.cuh) but resident in HBM: a row x of H cells is
 // HW = ceil(H/32) words.  ONE thread-block cluster (1..8 CTAs, chosen so that all envs together fill
-// the 148 SMs; 16 with the non-portable opt-in) owns one environment for a whole K-step rollout; CTA r of the cluster owns the r-th
-// contiguous slice of the env's words.  Everything the reference does in ForestFire.step happens in
-// this one kernel, per step:
+// the 148 SMs; 16 with the non-portable opt-in) owns one environment for a whole K-step rollout;
+// CTA r of the cluster owns the r-th contiguous slice of the env's words.  Everything the reference
+// does in ForestFire.step happens in this one kernel, per step:
 //
 //   agent phase   thread 0 of every CTA (redundantly, from identical inputs): action, Agent.move /
 //                 toggle_digging / is_dead (environment.py:116-171), local articulation test for the
 //                 reach plane.  Reads only; the dig is applied by the thread that owns the word.
 //                 (Runs while the other warps still emit the previous step's observation.)
 //   barrier X     (cluster)  nobody writes a plane before everybody has read the agent's surroundings
-//   tick          stream G, B and the heat-source mask S (1 bit/cell: burning and fuel >= 2) of the
-//                 slice; words that burn or are heated are queued in shared memory and handed one per
-//                 thread to the active path (fuel planes, hit counters, ignition, burn-out --
-//                 forest_fire.py:85-106, environment.py:278-307); S is ping-ponged so the in-place
-//                 update of every other plane is race-free across CTAs.
+//   tick          every warp on its own: stream G, B and the heat-source mask S (1 bit/cell: burning and
+//                 fuel >= 2) of 128 words; words that burn or are heated are compacted into the warp's
+//                 queue in shared memory and handed one per lane to the active path (fuel planes, hit
+//                 counters, ignition, burn-out -- forest_fire.py:85-106, environment.py:278-307); S is
+//                 ping-ponged (parity bit per env) so the in-place update of every other plane is
+//                 race-free across warps and CTAs.
 //   barrier Y     (cluster)  per-env reductions exchanged through distributed shared memory
-//   finish        RUNNING, World.get_reward (environment.py:342-390: containment = no burning cell in
-//                 or next to the border-connected reach plane R), done, statistics; auto-reset
+//   finish        RUNNING, World.get_reward (environment.py:342-390: containment = no burning cell next
+//                 to the border-connected reach plane R), done, statistics; auto-reset
 //   observation   World.get_state (environment.py:399-402): 2 plane words in, 96 bytes out per word
 //
 // The A* containment search (pyastar/astar.cpp) is the persistent reach plane R (cells with a finite
-// 4-connected path to a finite border point), re-flooded by the cluster only when a dig may disconnect it.
+// 4-connected path to a finite border point), re-flooded by the cluster only when a dig may disconnect
+// it; burning cells that are border points themselves (W > H maps) get a scratch flood (seed_cells_touch).
 #include <cstdlib>
 
 #include "wf_families.cuh"
