@@ -66,6 +66,8 @@ struct wf_env {
     bool packed_dma;
     size_t h_packed_words;
     HostPool* pool;
+    const void* alias_host[4];  // the caller's four host buffers of the previous wf_step_host call ...
+    void* alias_dev[4];         // ... and their device aliases (a caller steps with the same buffers every time)
     double t_launch, t_sync, t_expand;  // WF_HOST_TIMING=1: accumulated seconds of the packed path's three parts
     int64_t t_calls;
 };
@@ -536,10 +538,17 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
     // separate copy to launch.  Pageable buffers fall back to staged cudaMemcpyAsync.
-    void* a_d = e->host_direct ? mapped_alias(actions_host) : nullptr;
-    void* o_d = e->host_direct ? mapped_alias(obs_host) : nullptr;
-    void* r_d = e->host_direct ? mapped_alias(reward_host) : nullptr;
-    void* d_d = e->host_direct ? mapped_alias(done_host) : nullptr;
+    const void* hp[4] = {actions_host, obs_host, reward_host, done_host};
+    for (int i = 0; i < 4; ++i) {  // cudaPointerGetAttributes costs ~1 us per buffer: look each buffer up once
+        if (hp[i] != e->alias_host[i] || !hp[i]) {
+            e->alias_host[i] = hp[i];
+            e->alias_dev[i] = mapped_alias(hp[i]);
+        }
+    }
+    void* a_d = e->host_direct ? e->alias_dev[0] : nullptr;
+    void* o_d = e->host_direct ? e->alias_dev[1] : nullptr;
+    void* r_d = e->host_direct ? e->alias_dev[2] : nullptr;
+    void* d_d = e->host_direct ? e->alias_dev[3] : nullptr;
     const bool small_direct = a_d && (r_d || !reward_host) && (d_d || !done_host);
     if (small_direct && e->host_packed && !e->tile && obs_host && obs_dtype == WF_OBS_U8) {
         // Packed path (grids up to 32x32): the kernel stores the observation BIT STREAM straight into mapped
