@@ -68,6 +68,7 @@ struct wf_env {
     HostPool* pool;
     const void* alias_host[4];  // the caller's four host buffers of the previous wf_step_host call ...
     void* alias_dev[4];         // ... and their device aliases (a caller steps with the same buffers every time)
+    uint32_t alias_age;         // the cache is re-validated every 1024 calls (a buffer may have been re-allocated)
     double t_launch, t_sync, t_expand;  // WF_HOST_TIMING=1: accumulated seconds of the packed path's three parts
     int64_t t_calls;
 };
@@ -540,11 +541,12 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
     // separate copy to launch.  Pageable buffers fall back to staged cudaMemcpyAsync.
     const void* hp[4] = {actions_host, obs_host, reward_host, done_host};
     for (int i = 0; i < 4; ++i) {  // cudaPointerGetAttributes costs ~1 us per buffer: look each buffer up once
-        if (hp[i] != e->alias_host[i] || !hp[i]) {
+        if (hp[i] != e->alias_host[i] || !hp[i] || (e->alias_age & 1023u) == 0u) {
             e->alias_host[i] = hp[i];
             e->alias_dev[i] = mapped_alias(hp[i]);
         }
     }
+    e->alias_age += 1u;
     void* a_d = e->host_direct ? e->alias_dev[0] : nullptr;
     void* o_d = e->host_direct ? e->alias_dev[1] : nullptr;
     void* r_d = e->host_direct ? e->alias_dev[2] : nullptr;
