@@ -541,7 +541,7 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         e->host_packed = !(pk && pk[0] == '0');
         e->packed_dma = !(pk && std::string(pk) == "direct");  // default: stage in HBM, one DMA copy ("direct": zero-copy stores)
         const char* pl = getenv("WF_HOST_PIPELINE");
-        e->host_pipeline = pl && pl[0] == '1';  // opt-in until measured
+        e->host_pipeline = !(pl && pl[0] == '0');
         WF_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
         WF_CUDA(cudaEventCreateWithFlags(&e->ev_half, cudaEventDisableTiming));
     }
