@@ -64,9 +64,6 @@ struct wf_env {
     uint32_t* h_packed_dev;  // device alias
     uint32_t* d_packed;      // HBM staging (WF_HOST_PACKED=dma: kernel -> HBM -> one DMA copy)
     bool packed_dma;
-    bool host_pipeline;      // two half-batches: the copy + expansion of the first overlaps the kernel of the second
-    cudaStream_t cstream;    // copy stream of the first half
-    cudaEvent_t ev_half;
     size_t h_packed_words;
     HostPool* pool;
     const void* alias_host[4];  // the caller's four host buffers of the previous wf_step_host call ...
@@ -368,8 +365,6 @@ void wf_destroy(wf_env* e) {
     cudaFree(e->d_packed);
     if (e->pool) hostpool_destroy(e->pool);
     if (e->hstream) cudaStreamDestroy(e->hstream);
-    if (e->cstream) cudaStreamDestroy(e->cstream);
-    if (e->ev_half) cudaEventDestroy(e->ev_half);
     delete e;
 }
 
@@ -540,10 +535,6 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const char* pk = getenv("WF_HOST_PACKED");
         e->host_packed = !(pk && pk[0] == '0');
         e->packed_dma = !(pk && std::string(pk) == "direct");  // default: stage in HBM, one DMA copy ("direct": zero-copy stores)
-        const char* pl = getenv("WF_HOST_PIPELINE");
-        e->host_pipeline = !(pl && pl[0] == '0');
-        WF_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
-        WF_CUDA(cudaEventCreateWithFlags(&e->ev_half, cudaEventDisableTiming));
     }
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
@@ -580,42 +571,6 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
             e->h_packed_words = need;
         }
         if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
-        const int half = (s.N / 2) / 8 * 8;  // a multiple of the envs per CTA
-        if (e->packed_dma && e->host_pipeline && half >= 256) {
-            // Two half-batches: while the second half steps, the first half's bit stream crosses PCIe; while the
-            // second half's crosses, the host threads already expand the first.
-            const auto t0 = std::chrono::steady_clock::now();
-            const int64_t recA = half / epw;
-            WarpIO io{static_cast<const int32_t*>(a_d), e->d_packed, static_cast<double*>(r_d), static_cast<uint8_t*>(d_d), nullptr,
-                      nullptr, kObsPacked, 1, e->a_iter, 0, magic_for(s.H), WF_POLICY_STREAM, nullptr, MlpPolicy{}, 0, half};
-            WF_CUDA(launch_warp_family(e->st, e->sc, io, e->hstream));
-            WF_CUDA(cudaEventRecord(e->ev_half, e->hstream));
-            WF_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_half, 0));
-            WF_CUDA(cudaMemcpyAsync(e->h_packed, e->d_packed, (size_t)recA * rec_words * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                    e->cstream));
-            io.env_begin = half;
-            io.env_end = s.N;
-            WF_CUDA(launch_warp_family(e->st, e->sc, io, e->hstream));
-            WF_CUDA(cudaMemcpyAsync(e->h_packed + recA * rec_words, e->d_packed + recA * rec_words,
-                                    (size_t)(records - recA) * rec_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->hstream));
-            e->launches += 2;
-            e->a_iter = advance_a_iter(e, 1);
-            const auto t1 = std::chrono::steady_clock::now();
-            WF_CUDA(cudaStreamSynchronize(e->cstream));
-            const auto t2 = std::chrono::steady_clock::now();
-            hostpool_expand(e->pool, e->h_packed, static_cast<uint8_t*>(obs_host), recA, rec_words, env_bits, epw, half);
-            const auto t3 = std::chrono::steady_clock::now();
-            WF_CUDA(cudaStreamSynchronize(e->hstream));
-            const auto t4 = std::chrono::steady_clock::now();
-            hostpool_expand(e->pool, e->h_packed + recA * rec_words, static_cast<uint8_t*>(obs_host) + (size_t)half * env_bits,
-                            records - recA, rec_words, env_bits, epw, s.N - half);
-            const auto t5 = std::chrono::steady_clock::now();
-            e->t_launch += std::chrono::duration<double>(t1 - t0).count();
-            e->t_sync += std::chrono::duration<double>(t2 - t1).count() + std::chrono::duration<double>(t4 - t3).count();
-            e->t_expand += std::chrono::duration<double>(t3 - t2).count() + std::chrono::duration<double>(t5 - t4).count();
-            e->t_calls += 1;
-            return WF_OK;
-        }
         const auto t0 = std::chrono::steady_clock::now();
         int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->packed_dma ? e->d_packed : e->h_packed_dev, kObsPacked,
                          static_cast<double*>(r_d), static_cast<uint8_t*>(d_d), e->hstream);

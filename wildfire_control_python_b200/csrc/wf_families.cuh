@@ -26,8 +26,6 @@ struct WarpIO {
     int32_t policy;          // actions == nullptr: WF_POLICY_STREAM, WF_POLICY_WALK or WF_POLICY_MLP
     int32_t* actions_out;    // [K][N] or nullptr: the actions the policy chose
     MlpPolicy mlp;           // WF_POLICY_MLP only
-    int32_t env_begin, env_end;  // envs [env_begin, env_end) of the handle take part (env_end == 0: all); env_begin
-                                 // must be a multiple of the envs per CTA (wf_step_host pipelines two halves)
 };
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 

@@ -244,11 +244,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / L, x = lane % L;
-    const int env_end = io.env_end > 0 ? io.env_end : s.N;
-    const int env0 = io.env_begin + (blockIdx.x * kWarpsPerBlock + warp) * EPW;  // first env of this warp
+    const int env0 = (blockIdx.x * kWarpsPerBlock + warp) * EPW;  // first env of this warp
     const int env = env0 + sub;
-    const bool valid_env = env < env_end;
-    const int n_valid = min(EPW, env_end - env0);
+    const bool valid_env = env < s.N;
+    const int n_valid = min(EPW, s.N - env0);
     const int W = s.W, H = s.H;
     const uint32_t colmask = (H == 32) ? 0xffffffffu : ((1u << H) - 1u);
     const uint32_t validmask = (valid_env && x < W) ? colmask : 0u;
@@ -660,9 +659,7 @@ cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO
     const int L = s.RS;
     const int epw = 32 / L;
     const int envs_per_block = kWarpsPerBlock * epw;
-    const int n_range = (io.env_end > 0 ? io.env_end : s.N) - io.env_begin;
-    if (n_range <= 0 || io.env_begin % envs_per_block != 0) return cudaErrorInvalidValue;
-    const dim3 grid((n_range + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
+    const dim3 grid((s.N + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
     if (s.HB != 0 && (s.HB != kHitBits || s.FB != 5)) return cudaErrorInvalidValue;
     const bool mlp = io.policy == WF_POLICY_MLP && io.actions == nullptr && !io.reset_mode;
     if (mlp && (io.mlp.hid < 1 || io.mlp.hid > kHidMax || io.mlp.n_actions > kActMax)) return cudaErrorInvalidValue;
