@@ -240,8 +240,9 @@ def test_f32_observation_equals_u8():
 @pytest.mark.parametrize("cfg,n_envs,packed", [(dict(width=14, height=14, seed=501), 16, "1"), (dict(width=14, height=14, seed=502), 33, "1"),
                                                (dict(width=10, height=10, seed=503), 7, "1"), (dict(width=32, height=32, seed=504), 5, "1"),
                                                (dict(width=17, height=13, seed=505, wind="random"), 9, "1"),
-                                               (dict(width=14, height=14, seed=506), 16, "0"), (dict(width=40, height=36, seed=507), 6, "1")],
-                         ids=["14_even", "14_odd", "10", "32", "17x13", "14_unpacked", "tile_40x36"])
+                                               (dict(width=14, height=14, seed=506), 16, "0"), (dict(width=40, height=36, seed=507), 6, "1"),
+                                               (dict(width=14, height=14, seed=508), 601, "1"), (dict(width=20, height=20, seed=509), 530, "1")],
+                         ids=["14_even", "14_odd", "10", "32", "17x13", "14_unpacked", "tile_40x36", "14_n601", "20_n530"])
 def test_step_host_roundtrip(monkeypatch, cfg, n_envs, packed):
     """wf_step_host with page-locked host buffers: the packed path (observation bit stream into mapped host
     memory + host-thread expansion, grids up to 32x32), the plain uint8 path (WF_HOST_PACKED=0) and the tile family."""
