@@ -38,8 +38,9 @@ enum {
     WF_ERR_STATE = -3    /* call not valid in the handle's current state */
 };
 
-/* Observation element type written by wf_step / wf_rollout. */
-enum { WF_OBS_U8 = 0, WF_OBS_F32 = 1 };
+/* Observation element type written by wf_reset / wf_step / wf_rollout / wf_step_host / wf_get_obs: the 0 / 1 values of
+ * World.get_state (environment.py:399-402) as uint8, float32, or bfloat16 (1.0 = 0x3F80) for a bf16 learner. */
+enum { WF_OBS_U8 = 0, WF_OBS_F32 = 1, WF_OBS_BF16 = 2 };
 
 /* Cell types -- Simulation/utility.py:128-140. */
 enum { WF_GRASS = 0, WF_FIRE = 1, WF_BURNT = 2, WF_DIRT = 3, WF_WATER = 4 };

@@ -224,17 +224,33 @@ def test_rollout_equals_repeated_step():
         assert torch.equal(o, obs_a[k]) and torch.equal(r, rew_a[k]) and torch.equal(d, done_a[k]), k
 
 
-def test_f32_observation_equals_u8():
-    cfg = dict(width=14, height=14, seed=401)
-    a, _ = make_pair(9, cfg, auto_reset=True)
-    b, _ = make_pair(9, cfg, auto_reset=True, obs_dtype=torch.float32)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("cfg,n_envs", [(dict(width=14, height=14, seed=401), 9), (dict(width=13, height=11, seed=402), 7),
+                                        (dict(width=32, height=32, seed=403), 3), (dict(width=40, height=36, seed=404), 5),
+                                        (dict(width=64, height=64, seed=405), 4)],
+                         ids=["14", "13x11_odd", "32", "tile_40x36", "tile_64"])
+def test_float_observation_equals_u8(cfg, n_envs, dtype):
+    """WF_OBS_F32 / WF_OBS_BF16 (obs delivered as f32 / bf16 directly for the learner) hold exactly the
+    0 / 1 values of the uint8 observation, through reset, step, rollout, observe and step_host."""
+    a, _ = make_pair(n_envs, cfg, auto_reset=True)
+    b, _ = make_pair(n_envs, cfg, auto_reset=True, obs_dtype=dtype)
     oa, ob = a.reset(), b.reset()
-    assert torch.equal(oa.float(), ob)
-    for _ in range(50):
-        acts = torch.randint(0, 4, (9,), dtype=torch.int32, device="cuda")
+    assert ob.dtype == dtype and torch.equal(oa.to(dtype), ob)
+    gen = torch.Generator("cuda").manual_seed(cfg["seed"])
+    for _ in range(30):
+        acts = torch.randint(0, 4, (n_envs,), dtype=torch.int32, device="cuda", generator=gen)
         oa, ra, da, _ = a.step(acts)
         ob, rb, db, _ = b.step(acts)
-        assert ob.dtype == torch.float32 and torch.equal(oa.float(), ob) and torch.equal(ra, rb) and torch.equal(da, db)
+        assert ob.dtype == dtype and torch.equal(oa.to(dtype), ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    assert torch.equal(a.observe().to(dtype), b.observe())
+    acts = torch.randint(0, 4, (8, n_envs), dtype=torch.int32, device="cuda", generator=gen)
+    (oa, ra, da), (ob, rb, db) = a.rollout(8, actions=acts), b.rollout(8, actions=acts)
+    assert ob.dtype == dtype and torch.equal(oa.to(dtype), ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    for _ in range(5):
+        h = torch.randint(0, 4, (n_envs,), dtype=torch.int32, generator=torch.Generator().manual_seed(5)).numpy()
+        oa, ra, da, _ = a.step_host(h)
+        ob, rb, db, _ = b.step_host(h)
+        assert torch.equal(torch.as_tensor(oa).to(dtype), torch.as_tensor(ob)) and (ra == rb).all() and (da == db).all()
 
 
 @pytest.mark.parametrize("cfg,n_envs,packed", [(dict(width=14, height=14, seed=501), 16, "1"), (dict(width=14, height=14, seed=502), 33, "1"),

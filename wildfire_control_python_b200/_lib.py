@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("WILDFIRE_B200_LIB") or os.path.join(HERE, "libwildfir
 CSRC = os.path.join(HERE, "csrc")
 
 WF_OK, WF_ERR_INVALID, WF_ERR_CUDA, WF_ERR_STATE = 0, -1, -2, -3
-WF_OBS_U8, WF_OBS_F32 = 0, 1
+WF_OBS_U8, WF_OBS_F32, WF_OBS_BF16 = 0, 1, 2
 WF_POLICY_STREAM, WF_POLICY_WALK, WF_POLICY_MLP = 0, 1, 2
 WF_NSCALARS = 16
 (S_ALIVE, S_AX, S_AY, S_DEAD, S_DIGGING, S_VISIBLE, S_RUNNING, S_FIRE_AT_BORDER, S_LATCHED, S_EPISODE, S_T,

@@ -76,10 +76,11 @@ class BatchedForestFire:
         self.device = dev
         self.width, self.height = int(m["width"]), int(m["height"])
         self.n_actions = int(m["n_actions"])
-        if obs_dtype not in (torch.uint8, torch.float32):
-            raise ValueError("obs_dtype must be torch.uint8 or torch.float32")
+        codes = {torch.uint8: _lib.WF_OBS_U8, torch.float32: _lib.WF_OBS_F32, torch.bfloat16: _lib.WF_OBS_BF16}
+        if obs_dtype not in codes:
+            raise ValueError("obs_dtype must be torch.uint8, torch.float32 or torch.bfloat16")
         self.obs_dtype = obs_dtype
-        self._obs_code = _lib.WF_OBS_U8 if obs_dtype == torch.uint8 else _lib.WF_OBS_F32
+        self._obs_code = codes[obs_dtype]
 
         L = _lib.lib()
         self._cfg = config_from_metadata(m)
@@ -210,7 +211,8 @@ class BatchedForestFire:
     def step_host(self, actions):
         """Host-buffer step through ``wf_step_host``: H2D actions, step, D2H obs/reward/done, sync.
 
-        Uses page-locked staging arrays owned by this object; returns numpy views of them.
+        Uses page-locked staging arrays owned by this object; returns numpy views of them (numpy has no
+        bfloat16: with ``obs_dtype=torch.bfloat16`` the observation is the pinned torch tensor itself).
         """
         if self._host is None:
             N, W, H = self.n_envs, self.width, self.height
@@ -218,7 +220,7 @@ class BatchedForestFire:
                      obs=torch.empty((N, W, H, 3), dtype=self.obs_dtype).pin_memory(),
                      reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
                      done=torch.empty((N,), dtype=torch.uint8).pin_memory())
-            self._host = dict(tensors=t, np_actions=t["actions"].numpy(), np_obs=t["obs"].numpy(),
+            self._host = dict(tensors=t, np_actions=t["actions"].numpy(), np_obs=t["obs"] if self.obs_dtype == torch.bfloat16 else t["obs"].numpy(),
                               np_reward=t["reward"].numpy(), np_done=t["done"].numpy().view(np.bool_),
                               ptrs=tuple(t[k].data_ptr() for k in ("actions", "obs", "reward", "done")),
                               fn=_lib.lib().wf_step_host)

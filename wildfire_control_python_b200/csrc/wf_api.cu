@@ -197,6 +197,9 @@ __global__ void get_obs_kernel(DevState s, void* obs, int dtype) {
         if (dtype == WF_OBS_U8) {
             uint8_t* o = static_cast<uint8_t*>(obs) + 3 * i;
             o[0] = (uint8_t)a; o[1] = (uint8_t)f; o[2] = (uint8_t)d;
+        } else if (dtype == WF_OBS_BF16) {
+            uint16_t* o = static_cast<uint16_t*>(obs) + 3 * i;
+            o[0] = a ? kBf16One : 0; o[1] = f ? kBf16One : 0; o[2] = d ? kBf16One : 0;
         } else {
             float* o = static_cast<float*>(obs) + 3 * i;
             o[0] = (float)a; o[1] = (float)f; o[2] = (float)d;
@@ -390,8 +393,8 @@ int64_t wf_state_bytes_per_env(const wf_env* e) {
 }
 
 static int check_obs(const void* obs, int32_t dtype) {
-    if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32 && dtype != kObsPacked)
-        return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8 or WF_OBS_F32");
+    if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32 && dtype != WF_OBS_BF16 && dtype != kObsPacked)
+        return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8, WF_OBS_F32 or WF_OBS_BF16");
     if (obs && (reinterpret_cast<uintptr_t>(obs) & 15u)) return fail(WF_ERR_INVALID, "obs pointer must be 16-byte aligned");
     return WF_OK;
 }
@@ -519,10 +522,10 @@ static void* mapped_alias(const void* host_ptr) {
 int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
                  uint8_t* done_host) {
     if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
-    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32) return fail(WF_ERR_INVALID, "bad obs_dtype");
+    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32 && obs_dtype != WF_OBS_BF16) return fail(WF_ERR_INVALID, "bad obs_dtype");
     WF_CUDA(cudaSetDevice(e->device));
     const DevState& s = e->st;
-    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
+    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
     if (!e->hstream) {
         WF_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
         // WF_HOST_MODE: "hybrid" (default) = actions/reward/done zero-copy, obs staged + one DMA copy;

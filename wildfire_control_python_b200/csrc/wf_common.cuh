@@ -27,6 +27,10 @@ namespace wf {
 // ceil(envs_per_warp * W*H*3 / 32) words per warp; expanded to bytes by the host thread pool (wf_hostpool.cpp).
 constexpr int kObsPacked = 100;
 
+// Bytes per observation element of a public obs_dtype (WF_OBS_U8 / WF_OBS_F32 / WF_OBS_BF16).
+__host__ __device__ __forceinline__ int obs_elem_bytes(int dtype) { return dtype == WF_OBS_F32 ? 4 : dtype == WF_OBS_BF16 ? 2 : 1; }
+constexpr uint16_t kBf16One = 0x3F80u;  // 1.0 in bfloat16
+
 enum Plane : int { P_G = 0, P_F, P_BT, P_D, P_WT, P_B, P_I, P_FU0 };  // + FB fuel planes (+ S0, S1, R for tiles)
 
 constexpr int kMaxWind = 27;  // 3 speeds x 9 vectors (environment.py:189-190) or 1 fixed entry

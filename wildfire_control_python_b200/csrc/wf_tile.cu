@@ -775,6 +775,9 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
                 if (obs_dtype == WF_OBS_U8) {
                     uint8_t* o8 = static_cast<uint8_t*>(obs_step) + e0;
                     for (int b = 0; b < 3 * ncell; ++b) o8[b] = (uint8_t)((r[b >> 5] >> (b & 31)) & 1u);
+                } else if (obs_dtype == WF_OBS_BF16) {
+                    uint16_t* oh = static_cast<uint16_t*>(obs_step) + e0;
+                    for (int b = 0; b < 3 * ncell; ++b) oh[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? kBf16One : (uint16_t)0;
                 } else {
                     float* of = static_cast<float*>(obs_step) + e0;
                     for (int b = 0; b < 3 * ncell; ++b) of[b] = ((r[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
@@ -1220,7 +1223,7 @@ static TilePar make_par(const TileState* t, const DevState& s, int obs_dtype) {
     p.cells = s.W * s.H;
     p.pstride = (size_t)s.N * s.RS * s.HW;
     p.env_words = (size_t)s.RS * s.HW;
-    p.step_bytes = (size_t)s.N * s.W * s.H * 3 * (obs_dtype == WF_OBS_F32 ? 4 : 1);
+    p.step_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
     return p;
 }
 

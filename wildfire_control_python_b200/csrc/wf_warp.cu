@@ -209,6 +209,17 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         } else {
             for (int b = lane; b < tbits; b += 32) o8[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
         }
+    } else if (dtype == WF_OBS_BF16) {  // 1.0 = 0x3F80: two elements per 32-bit store where the block allows it
+        uint16_t* oh = static_cast<uint16_t*>(obs_step) + (size_t)env0 * nbits;
+        if ((tbits & 1) == 0 && (reinterpret_cast<uintptr_t>(oh) & 3u) == 0) {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(oh);
+            for (int j = lane; j < (tbits >> 1); j += 32) {
+                const uint32_t two = (stream[j >> 4] >> ((j & 15) * 2)) & 3u;
+                o32[j] = ((two & 1u) ? (uint32_t)kBf16One : 0u) | ((two & 2u) ? (uint32_t)kBf16One << 16 : 0u);
+            }
+        } else {
+            for (int b = lane; b < tbits; b += 32) oh[b] = ((stream[b >> 5] >> (b & 31)) & 1u) ? kBf16One : (uint16_t)0;
+        }
     } else {
         float* of = static_cast<float*>(obs_step) + (size_t)env0 * nbits;
         for (int b = lane; b < tbits; b += 32) of[b] = ((stream[b >> 5] >> (b & 31)) & 1u) ? 1.0f : 0.0f;
@@ -624,7 +635,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             if (io.obs != nullptr) {
                 const size_t step_bytes =
                     io.obs_dtype == kObsPacked ? (size_t)((s.N + EPW - 1) / EPW) * ((EPW * W * H * 3 + 31) >> 5) * 4
-                                               : (size_t)s.N * W * H * 3 * (io.obs_dtype == WF_OBS_F32 ? 4 : 1);
+                                               : (size_t)s.N * W * H * 3 * obs_elem_bytes(io.obs_dtype);
                 emit_obs<L>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
                             (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, tab8,
                             lane, sub, x, W, H, env0, n_valid);
