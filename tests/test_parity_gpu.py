@@ -227,8 +227,9 @@ def test_rollout_equals_repeated_step():
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("cfg,n_envs", [(dict(width=14, height=14, seed=401), 9), (dict(width=13, height=11, seed=402), 7),
                                         (dict(width=32, height=32, seed=403), 3), (dict(width=40, height=36, seed=404), 5),
-                                        (dict(width=64, height=64, seed=405), 4)],
-                         ids=["14", "13x11_odd", "32", "tile_40x36", "tile_64"])
+                                        (dict(width=64, height=64, seed=405), 4), (dict(width=128, height=128, seed=406), 3),
+                                        (dict(width=130, height=128, seed=407, extra_ignitions=8), 2)],
+                         ids=["14", "13x11_odd", "32", "tile_40x36", "tile_64", "tile_128_wide", "tile_130x128_wide_tail"])
 def test_float_observation_equals_u8(cfg, n_envs, dtype):
     """WF_OBS_F32 / WF_OBS_BF16 (obs delivered as f32 / bf16 directly for the learner) hold exactly the
     0 / 1 values of the uint8 observation, through reset, step, rollout, observe and step_host."""

@@ -29,6 +29,8 @@
 
 #include "wf_families.cuh"
 
+#include <type_traits>
+
 namespace wf {
 
 struct TileState {
@@ -677,6 +679,33 @@ __device__ bool seed_cells_touch(const Env& e, const TilePar& t, int scratch_pla
 }
 
 // ---------------------------------------------------------------------------------------------
+// Float observations (WF_OBS_BF16 / WF_OBS_F32) of a staged bit stream: `nelem` (a multiple of 512) stream bits
+// become `nelem` elements starting at element `elem0` of the step's block, 16 bytes per lane and store.
+__device__ __forceinline__ uint32_t bf16_pair(uint32_t bytes01, uint32_t sel) {  // two 0/1 bytes -> two bfloat16
+    return __byte_perm(bytes01, 0u, sel) * (uint32_t)kBf16One;
+}
+__device__ __forceinline__ void expand_stream_float(void* obs_step, int obs_dtype, size_t elem0, const uint32_t* stage,
+                                                    int nelem, const uint2* tab8, int lane) {
+    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(stage);
+    if (obs_dtype == WF_OBS_BF16) {
+        uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(obs_step) + elem0);
+#pragma unroll 4
+        for (int c = lane; c < (nelem >> 3); c += 32) {  // 8 stream bits -> 8 x bf16
+            const uint2 t = tab8[s8[c]];
+            __stcs(&o[c], make_uint4(bf16_pair(t.x, 0x4140u), bf16_pair(t.x, 0x4342u), bf16_pair(t.y, 0x4140u),
+                                     bf16_pair(t.y, 0x4342u)));
+        }
+    } else {
+        uint4* o = reinterpret_cast<uint4*>(static_cast<float*>(obs_step) + elem0);
+        constexpr uint32_t ONE = 0x3F800000u;
+#pragma unroll 4
+        for (int c = lane; c < (nelem >> 2); c += 32) {  // 4 stream bits -> 4 x float32
+            const uint32_t nib = ((uint32_t)s8[c >> 1] >> ((c & 1) * 4)) & 15u;
+            __stcs(&o[c], make_uint4((nib & 1u) ? ONE : 0u, (nib & 2u) ? ONE : 0u, (nib & 4u) ? ONE : 0u, (nib & 8u) ? ONE : 0u));
+        }
+    }
+}
+
 // World.get_state :399-402 of this CTA's slice: [agent_pos, type == fire, fire_mobility != inf].
 // Output element (x*H + y)*3 + ch is ONE BIT, so a word's 32 cells are a 96-bit stream (its three masks
 // interleaved bit by bit, via a 256-entry "spread by 3" table).  A warp stages the streams of 32
@@ -698,62 +727,70 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
     uint32_t* stage = stage_all + warp * ((HW & 3) == 0 ? 384 : 96);  // 32 words x 96 bits
     const uint16_t* stage16 = reinterpret_cast<const uint16_t*>(stage);
     int g_first = e.lo;
-    if (obs_dtype == WF_OBS_U8 && (H & 31) == 0 && (HW & 3) == 0) {
-        // Wide path: a warp takes 128 consecutive words (12 KB of output) per iteration with two 128-bit
-        // loads per lane, issued one iteration ahead so that the expansion never waits on HBM.
-        uint32_t* stage4 = stage_all + warp * 384;  // 128 words x 96 bits
-        const uint16_t* stage4_16 = reinterpret_cast<const uint16_t*>(stage4);
-        const int n128 = (e.hi - e.lo) >> 7;  // full 128-word groups of this slice
-        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        uint4 F4 = z4, I4 = z4;
-        auto next_group = [&](int prev) -> int {  // warp-uniform
-            if (ctr == nullptr) return prev < 0 ? warp : prev + nwarps;
-            int v = 0;
-            if (lane == 0) v = atomicAdd(ctr, 1);
-            return __shfl_sync(0xffffffffu, v, 0);
-        };
-        int gi = next_group(-1);
-        if (gi < n128) {
-            F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gi * 128 + 4 * lane);
-            I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gi * 128 + 4 * lane);
-        }
-        while (gi < n128) {
-            const int g = e.lo + gi * 128;
-            const uint4 Fc = F4, Ic = I4;
-            const int gn = next_group(gi);
-            if (gn < n128) {
-                F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gn * 128 + 4 * lane);
-                I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gn * 128 + 4 * lane);
+    if ((H & 31) == 0 && (HW & 3) == 0) {
+        // Two instantiations, so that the uint8 loop carries no per-iteration test of the element type.
+        auto wide = [&](auto is_u8) {
+            // Wide path: a warp takes 128 consecutive words (12 KB of output) per iteration with two 128-bit
+            // loads per lane, issued one iteration ahead so that the expansion never waits on HBM.
+            uint32_t* stage4 = stage_all + warp * 384;  // 128 words x 96 bits
+            const uint16_t* stage4_16 = reinterpret_cast<const uint16_t*>(stage4);
+            const int n128 = (e.hi - e.lo) >> 7;  // full 128-word groups of this slice
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            uint4 F4 = z4, I4 = z4;
+            auto next_group = [&](int prev) -> int {  // warp-uniform
+                if (ctr == nullptr) return prev < 0 ? warp : prev + nwarps;
+                int v = 0;
+                if (lane == 0) v = atomicAdd(ctr, 1);
+                return __shfl_sync(0xffffffffu, v, 0);
+            };
+            int gi = next_group(-1);
+            if (gi < n128) {
+                F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gi * 128 + 4 * lane);
+                I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gi * 128 + 4 * lane);
             }
-            const uint32_t Fw[4] = {Fc.x, Fc.y, Fc.z, Fc.w}, Iw[4] = {Ic.x, Ic.y, Ic.z, Ic.w};
+            while (gi < n128) {
+                const int g = e.lo + gi * 128;
+                const uint4 Fc = F4, Ic = I4;
+                const int gn = next_group(gi);
+                if (gn < n128) {
+                    F4 = *reinterpret_cast<const uint4*>(PF + e.lo + gn * 128 + 4 * lane);
+                    I4 = *reinterpret_cast<const uint4*>(PI + e.lo + gn * 128 + 4 * lane);
+                }
+                const uint32_t Fw[4] = {Fc.x, Fc.y, Fc.z, Fc.w}, Iw[4] = {Ic.x, Ic.y, Ic.z, Ic.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t F = Fw[j], freerow = ~Iw[j];
-                uint32_t p[4];
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t F = Fw[j], freerow = ~Iw[j];
+                    uint32_t p[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    p[k] = (spread3[(F >> (8 * k)) & 255u] << 1) | (spread3[(freerow >> (8 * k)) & 255u] << 2);
-                if (g + 4 * lane + j == aw) p[(ay & 31) >> 3] |= 1u << (3 * (ay & 7));
-                uint32_t* st = stage4 + (4 * lane + j) * 3;
-                st[0] = p[0] | (p[1] << 24);
-                st[1] = (p[1] >> 8) | (p[2] << 16);
-                st[2] = (p[2] >> 16) | (p[3] << 8);
-            }
-            __syncwarp();
-            uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
+                    for (int k = 0; k < 4; ++k)
+                        p[k] = (spread3[(F >> (8 * k)) & 255u] << 1) | (spread3[(freerow >> (8 * k)) & 255u] << 2);
+                    if (g + 4 * lane + j == aw) p[(ay & 31) >> 3] |= 1u << (3 * (ay & 7));
+                    uint32_t* st = stage4 + (4 * lane + j) * 3;
+                    st[0] = p[0] | (p[1] << 24);
+                    st[1] = (p[1] >> 8) | (p[2] << 16);
+                    st[2] = (p[2] >> 16) | (p[3] << 8);
+                }
+                __syncwarp();
+                if constexpr (decltype(is_u8)::value) {
+                    uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
 #pragma unroll 8
-            for (int it = 0; it < 24; ++it) {
-                const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 12288 bytes = 16 stream bits
-                const uint32_t bits = stage4_16[cidx];
-                const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
-                __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+                    for (int it = 0; it < 24; ++it) {
+                        const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 12288 bytes = 16 stream bits
+                        const uint32_t bits = stage4_16[cidx];
+                        const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
+                        __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+                    }
+                } else {
+                    expand_stream_float(obs_step, obs_dtype, (((size_t)e.env * W) * H + (size_t)32 * g) * 3, stage4, 128 * 96, tab8, lane);
+                }
+                __syncwarp();
+                gi = gn;
             }
-            __syncwarp();
-            gi = gn;
-        }
-        g_first = e.lo + n128 * 128;  // the slice's tail (< 128 words) takes the narrow path
+            g_first = e.lo + n128 * 128;  // the slice's tail (< 128 words) takes the narrow path
+        };
+        if (obs_dtype == WF_OBS_U8) wide(std::true_type{}); else wide(std::false_type{});
     }
-    const bool fast_ok = obs_dtype == WF_OBS_U8 && (H & 31) == 0;
+    const bool fast_ok = (H & 31) == 0;
     for (int g = g_first + warp * 32; g < e.hi; g += nwarps * 32) {
         const int i = g + lane;
         if (i < e.hi) {
@@ -786,13 +823,17 @@ __device__ __forceinline__ void emit_obs_slice(const Env& e, void* obs_step, int
         }
         if (fast_ok && g + 31 < e.hi) {  // warp-uniform
             __syncwarp();
-            uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
+            if (obs_dtype == WF_OBS_U8) {
+                uint4* o = reinterpret_cast<uint4*>(static_cast<uint8_t*>(obs_step) + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
 #pragma unroll
-            for (int it = 0; it < 6; ++it) {
-                const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 3072 bytes = 16 stream bits
-                const uint32_t bits = stage16[cidx];
-                const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
-                __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+                for (int it = 0; it < 6; ++it) {
+                    const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 3072 bytes = 16 stream bits
+                    const uint32_t bits = stage16[cidx];
+                    const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
+                    __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+                }
+            } else {
+                expand_stream_float(obs_step, obs_dtype, (((size_t)e.env * W) * H + (size_t)32 * g) * 3, stage, 32 * 96, tab8, lane);
             }
             __syncwarp();
         }
