@@ -42,7 +42,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 14x14 (Logs/14-sized constants) batched 4096 envs, random actions
-    "c2": dict(n_envs=4096, meta=dict(width=14, height=14), chunk=64,
+    # 256 steps per launch: the ~15 us a launch costs beyond its steps (launch gap, state load/store, table set-up,
+    # the tail of the slowest warp) falls from 9 % of a 64-step launch to 2.5 % (tools/ab_rollout.py, r01)
+    "c2": dict(n_envs=4096, meta=dict(width=14, height=14), chunk=256,
                desc="14x14 Logs/14-sized constants, 4096 envs/GPU, ACTION-stream random actions, auto-reset"),
     # configs[2]: 14x14 batched 65536 envs (8192 per GPU on 8 GPUs) with a DQN-policy rollout via torch:
     # Flatten -> Dense(50, sigmoid) -> Dense(4) (DQN.py:209-233), fixed-seed weights, epsilon-greedy 0.1
@@ -429,9 +431,10 @@ def run_ours(args, wl):
         if wl.get("policy"):
             res = measure_policy(D, args.workload, args.steps, args.warmup)
         else:
-            res = measure(D, args.workload, args.steps, args.warmup, args.chunk, args.no_graph, True, True)
+            res = measure(D, args.workload, args.steps, args.warmup, args.chunk, args.no_graph, not args.only_value,
+                          not args.only_value)
         sec = None
-        if args.workload == "c2" and not args.no_secondary:
+        if args.workload == "c2" and not args.no_secondary and not args.only_value:
             sec = measure(D, "c4", 160, 32, 0, args.no_graph, False, False)
     clocks = clk.summary()
     if D.rank != 0:
@@ -440,7 +443,7 @@ def run_ours(args, wl):
     world, N, W, H, K = D.world, res["N"], res["W"], res["H"], res["K"]
 
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and not args.only_value:
         from oracle import wf_oracle as wo  # the checker, timed as the CPU baseline (allowed use)
         ob = wo.OracleBatch(oracle_cfg(wl["meta"]), min(N, 1024), 1)
         t0 = time.perf_counter(); n = ob.step(2); rate = n / (time.perf_counter() - t0)
@@ -492,6 +495,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="steps per fused launch / graph replay (default: workload's)")
     ap.add_argument("--no-graph", action="store_true", help="tile family: plain launches instead of CUDA-graph replay")
     ap.add_argument("--no-secondary", action="store_true", help="skip the c4 stencil measurement in the default line")
+    ap.add_argument("--only-value", action="store_true",
+                    help="profiling runs: only the fused-rollout measurement (no per-step, e2e, CPU baseline legs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

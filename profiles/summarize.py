@@ -4,7 +4,7 @@
 usage: python profiles/summarize.py r01
 Reads (whatever exists):
   gpurun_out/launches_c2.csv, launches_c4.csv     `ncu --metrics gpu__time_duration.sum ...` launch lists
-  gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 64 steps/launch)
+  gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 256 steps/launch; WF_C2_KEY names the ncu_traffic key)
   gpurun_out/prof_c4.ncu-rep, prof_c5.ncu-rep     captures of wf::tile_rollout_kernel (c4 / c5, 16 steps/launch)
 Writes profiles/<round>_*.{csv,txt,json} and profiles/ncu_traffic.json (read by bench.py).
 """
@@ -85,7 +85,7 @@ def main(rnd):
         ls = launch_summary(name, rnd)
         if ls:
             summary[f"{name}_launch_list"] = ls
-    for rep, tag, key in (("prof_c2.ncu-rep", "c2_warp_kernel", "c2_chunk64"), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4_chunk16"),
+    for rep, tag, key in (("prof_c2.ncu-rep", "c2_warp_kernel", os.environ.get("WF_C2_KEY", "c2_chunk256")), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4_chunk16"),
                           ("prof_c5.ncu-rep", "c5_tile_rollout", "c5_chunk16")):
         ks = rep_summary(rep, rnd, tag)
         if ks:

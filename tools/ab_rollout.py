@@ -1,5 +1,5 @@
 """A/B helper: us/step of wf_rollout on one workload with the library named by WILDFIRE_B200_LIB.
-    WILDFIRE_B200_LIB=build_ab/libold.so python tools/ab_rollout.py c4|c5|c2"""
+    WILDFIRE_B200_LIB=build_ab/libold.so python tools/ab_rollout.py c4|c5|c2 [steps_per_launch]"""
 import os
 import sys
 
@@ -11,7 +11,7 @@ from wildfire_control_python_b200 import BatchedForestFire  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 wl = WORKLOADS[name]
-N, K = wl["n_envs"], wl["chunk"]
+N, K = wl["n_envs"], (int(sys.argv[2]) if len(sys.argv) > 2 else wl["chunk"])
 W, H = wl["meta"]["width"], wl["meta"]["height"]
 env = BatchedForestFire(N, auto_reset=True, seed=0, **wl["meta"])
 env.reset()
@@ -24,10 +24,10 @@ for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    n = 20 if name != "c2" else 100
+    n = max(2, (20 if name != "c2" else 100) * wl["chunk"] // K)
     for _ in range(n):
         env.rollout(K, out=out)
     e1.record()
     torch.cuda.synchronize()
     res.append(e0.elapsed_time(e1) * 1e3 / (n * K))
-print(name, os.environ.get("WILDFIRE_B200_LIB", "in-tree"), " ".join(f"{r:.2f}" for r in res), "us/step", flush=True)
+print(name, f"K={K}", os.environ.get("WILDFIRE_B200_LIB", "in-tree"), " ".join(f"{r:.2f}" for r in res), "us/step", flush=True)
