@@ -2,6 +2,7 @@
 
 TEST INFRASTRUCTURE; needs /root/reference (build container only).  Run as
     python -m oracle.validate_oracle [--steps N]
+    python -m oracle.validate_oracle --random 200 --seed 1 [--steps N]   # randomised scenarios instead of the list
 Every step compares type / burning / fm_inf / fuel / agent_pos planes, agent
 xy + alive, fire_at_border, obs, reward (float64 ==) and done bit-exactly, and
 temp on grass cells to 1e-12.
@@ -44,6 +45,34 @@ SCENARIOS = [
     dict(name="walk_14", width=14, height=14, seed=41, policy="walk"),
     dict(name="walk_20_rivers_wind", width=20, height=20, seed=42, policy="walk", make_rivers=True, wind="random"),
 ]
+
+
+def random_scenario(rng, i):
+    """A random configuration of everything the step reads (square maps: Q6 is history-dependent on W > H)."""
+    size = int(rng.choice([10, 11, 12, 13, 14, 16, 18, 20, 24, 28]))
+    sc = dict(name=f"rand{i}_{size}", width=size, height=size, seed=int(rng.integers(1, 1 << 30)))
+    w = rng.integers(0, 4)
+    if w == 1:
+        sc["wind"] = "random"
+    elif w == 2:
+        sc["wind"] = [float(rng.choice([0.7, 0.85, 1.0])), (int(rng.integers(-1, 2)), int(rng.integers(-1, 2)))]
+    if rng.random() < 0.3:
+        sc["make_rivers"] = True
+    if rng.random() < 0.3:
+        sc["allow_dig_toggle"] = True
+        sc["n_actions"] = int(rng.choice([5, 6]))
+    elif rng.random() < 0.2:
+        sc["n_actions"] = 5  # action 4 is a no-op without the toggle
+    if rng.random() < 0.3:
+        sc["a_speed"] = int(rng.choice([2, 3]))
+    if rng.random() < 0.4:
+        sc["extra_ignitions"] = int(rng.integers(1, 7))
+    pol = rng.random()
+    if pol < 0.25:
+        sc["policy"] = f"ring{int(rng.integers(2, min(5, size // 2 - 1)))}"
+    elif pol < 0.5 and "n_actions" not in sc:
+        sc["policy"] = "walk"
+    return sc
 
 
 def compare(tag, ref: RefEnv, orc: wo.OracleEnv, obs_r, obs_o, rew=None, done=None):
@@ -112,9 +141,15 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--random", type=int, default=0, help="number of randomised scenarios to run instead of the list")
+    ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args(argv)
     total = 0
-    for sc in SCENARIOS:
+    scenarios = SCENARIOS
+    if args.random:
+        rng = np.random.default_rng(args.seed)
+        scenarios = [random_scenario(rng, i) for i in range(args.random)]
+    for sc in scenarios:
         if args.only and args.only != sc["name"]:
             continue
         st = run(sc, args.steps)

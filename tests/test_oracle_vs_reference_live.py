@@ -29,3 +29,23 @@ def test_oracle_equals_python_reference(sc):
     assert st["steps"] == 350 and st["maxerr"] <= 1e-12
     if sc.get("policy", "").startswith(("ring", "walk")):
         assert st["contained"] >= 1  # the scripted / heuristic walks do contain the fire
+
+
+def _random_scenarios(n=12, seed=2026):
+    try:
+        import numpy as np
+
+        from oracle.validate_oracle import random_scenario
+        rng = np.random.default_rng(seed)
+        return [random_scenario(rng, i) for i in range(n)]
+    except Exception:
+        return []
+
+
+@pytest.mark.parametrize("sc", _random_scenarios(), ids=lambda s: s["name"])
+def test_oracle_equals_python_reference_random_configs(sc):
+    """Randomised configurations (size, wind, rivers, dig toggle, a_speed, extra ignitions, policy): the pytest face of
+    `python -m oracle.validate_oracle --random N` (DESIGN.md section 4 records the last long run)."""
+    from oracle.validate_oracle import run
+    st = run(sc, 250)
+    assert st["steps"] == 250 and st["maxerr"] <= 1e-12
