@@ -461,7 +461,7 @@ def run_ours(args, wl):
                    "steps_per_launch": res["chunk"] if res["fused"] else None,
                    "steps_per_graph_replay": res["chunk"] if res["graph"] else None, "kernel_family": res["family"],
                    "l2": f"outputs of one launch/replay ({res['obs_mb']:.0f} MB obs) exceed the 126 MB L2; "
-                         + ("state is register/L2 resident by design" if res["family"] == "warp" else "state (385 MB) exceeds L2 too")},
+                         + ("state is register/L2 resident by design" if res["family"] == "warp" else f"state ({res['state_bytes'] * res['N'] / 1e6:.0f} MB) exceeds L2 too")},
         "cell_updates_per_sec": res["value"] * W * H,
         "cell_updates_per_sec_per_gpu": res["value"] * W * H / world,
         "e2e": res.get("e2e"), "per_step_launch": res.get("per_step"),

@@ -87,7 +87,7 @@ __global__ void get_state_kernel(DevState s, uint8_t* type, uint8_t* burning, ui
         if (fm_inf) fm_inf[i] = (uint8_t)bit(P_I);
         if (fuel) {
             uint32_t f = 0;
-            for (int q = 0; q < s.FB; ++q) f |= bit(P_FU0 + q) << q;
+            for (int q = 0; q < s.FB; ++q) f |= ((*fuel_slice(s, q, env, x, w) >> b) & 1u) << q;
             fuel[i] = (uint8_t)f;
         }
         if (hits) {
@@ -140,7 +140,7 @@ __global__ void set_state_kernel(DevState s, const uint8_t* type, const uint8_t*
             for (int q = 0; q < s.FB; ++q) {
                 uint32_t m = 0;
                 for (int b = 0; b < ny; ++b) m |= ((uint32_t)(fuel[cell0 + b] >> q) & 1u) << b;
-                s.planes[word_index(s, P_FU0 + q, env, x, w)] = m;
+                *fuel_slice(s, q, env, x, w) = m;
             }
         }
         if (hits && s.HB) {
@@ -319,7 +319,7 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
         for (int i = 0; i < e->n_wind; ++i) all_uniform = all_uniform && e->wind_host.uniform[i];
         if (!e->tile && all_uniform && s.FB == 5 && !getenv("WF_WARP_NO_BITSLICED_HITS")) s.HB = 7;
     }
-    s.NP = 7 + s.FB + s.HB + (e->tile ? tile_extra_planes() : 0);
+    s.NP = e->tile ? 7 + tile_extra_planes() : 7 + s.FB + s.HB;  // tile family: fuel lives in its own records (s.fuel)
 
     const size_t plane_words = (size_t)s.NP * s.N * s.RS * s.HW;
     const size_t cells = (size_t)s.N * s.W * s.H;
@@ -331,6 +331,11 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
     } while (0)
     WF_CUDA_C(cudaMalloc(&s.planes, plane_words * sizeof(uint32_t)));
     WF_CUDA_C(cudaMemset(s.planes, 0, plane_words * sizeof(uint32_t)));
+    if (e->tile) {
+        const size_t fuel_words = (size_t)s.N * s.RS * s.HW * kFuelRec;
+        WF_CUDA_C(cudaMalloc(&s.fuel, fuel_words * sizeof(uint32_t)));
+        WF_CUDA_C(cudaMemset(s.fuel, 0, fuel_words * sizeof(uint32_t)));
+    }
     WF_CUDA_C(cudaMalloc(&s.hits, cells * sizeof(uint32_t)));
     WF_CUDA_C(cudaMemset(s.hits, 0, cells * sizeof(uint32_t)));
     WF_CUDA_C(cudaMalloc(&s.scal, (size_t)s.N * WF_NSCALARS * sizeof(int32_t)));
@@ -357,7 +362,7 @@ void wf_destroy(wf_env* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->tstate) tile_destroy(e->tstate);
-    cudaFree(e->st.planes); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
+    cudaFree(e->st.planes); cudaFree(e->st.fuel); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
     cudaFree(e->wind_dev);
     cudaFree(e->mlp_dev);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
@@ -389,7 +394,7 @@ int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t
 int64_t wf_state_bytes_per_env(const wf_env* e) {
     if (!e) return 0;
     const DevState& s = e->st;
-    return (int64_t)s.NP * s.RS * s.HW * 4 + (s.HB ? 0 : (int64_t)s.W * s.H * 4) + WF_NSCALARS * 4;
+    return (int64_t)(s.NP + (s.fuel ? kFuelRec : 0)) * s.RS * s.HW * 4 + (s.HB ? 0 : (int64_t)s.W * s.H * 4) + WF_NSCALARS * 4;
 }
 
 static int check_obs(const void* obs, int32_t dtype) {

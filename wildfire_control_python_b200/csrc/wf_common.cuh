@@ -56,7 +56,11 @@ struct DevState {
     int32_t N, W, H, RS, HW, FB, NP;
     int32_t HB;         // warp family, every wind of the handle uniform: total hit count per cell kept as HB bit planes
                         // (planes P_FU0 + FB ...) instead of the `hits` array; 0 otherwise
+    uint32_t* fuel;     // tile family: [N][RS * HW][kFuelRec] -- the FB fuel bit-slices of ONE word side by side, so that
+                        // a burning word's fuel is one 32-byte sector in and out instead of FB sectors in FB planes
+                        // (`planes` then has no fuel planes).  nullptr: fuel lives in planes P_FU0 .. P_FU0 + FB - 1
 };
+constexpr int kFuelRec = 8;  // words per fuel record (FB = 5 or 8 used)
 
 struct StepCfg {
     int32_t n_actions, a_speed, allow_dig_toggle, make_rivers, wind_random, fuel, extra_ignitions, auto_reset;
@@ -67,6 +71,10 @@ struct StepCfg {
 
 __device__ __forceinline__ size_t word_index(const DevState& s, int plane, int env, int x, int w) {
     return (((size_t)plane * s.N + env) * s.RS + x) * s.HW + w;
+}
+// Bit-slice q of the fuel of word (env, x, w), whichever layout the family uses.
+__device__ __forceinline__ uint32_t* fuel_slice(const DevState& s, int q, int env, int x, int w) {
+    return s.fuel ? s.fuel + ((((size_t)env * s.RS + x) * s.HW + w) * kFuelRec + q) : s.planes + word_index(s, P_FU0 + q, env, x, w);
 }
 
 // circle_points(0, 0, r) for r = 1, 2, 3 -- Simulation/utility.py:8-52, in the reference's

@@ -146,6 +146,7 @@ struct Env {
     uint32_t* P0;    // word 0 of plane 0 of this env
     size_t pstride;  // words between consecutive planes
     uint32_t* hits;  // hit counters of this env
+    uint32_t* FU;    // fuel records of this env: kFuelRec words per plane word
     int env, W, H, HW, nwords, hw_shift;
     uint32_t hw_magic;
     int lo, hi;      // this CTA's slice of the env's words
@@ -378,23 +379,39 @@ __device__ void agent_phase(const Env& e, const StepCfg& c, const TilePar& t, co
     }
 }
 
+// Fuel record of one plane word: its FB bit-slices side by side (one 32-byte sector).
+template <int FB>
+__device__ __forceinline__ void load_fuel(const uint32_t* rec, uint32_t (&FU)[FB]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(rec);
+    FU[0] = a.x; FU[1] = a.y; FU[2] = a.z; FU[3] = a.w;
+    if (FB == 5) {
+        FU[4] = rec[4];
+    } else {
+        const uint4 b = *reinterpret_cast<const uint4*>(rec + 4);
+        FU[4] = b.x; FU[FB > 5 ? 5 : 4] = b.y; FU[FB > 6 ? 6 : 4] = b.z; FU[FB > 7 ? 7 : 4] = b.w;
+    }
+}
+template <int FB>
+__device__ __forceinline__ void store_fuel(uint32_t* rec, const uint32_t (&FU)[FB]) {
+    *reinterpret_cast<uint4*>(rec) = make_uint4(FU[0], FU[1], FU[2], FU[3]);
+    if (FB == 5) rec[4] = FU[4];
+    else *reinterpret_cast<uint4*>(rec + 4) = make_uint4(FU[4], FU[FB > 5 ? 5 : 4], FU[FB > 6 ? 6 : 4], FU[FB > 7 ? 7 : 4]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The stencil.
 // Active word (it burns or is heated): reduce_fuel :297-307, burn-out, apply_heat_from_to :278-294,
 // set_fire_to :233-246.  Returns the word's heat sources for the next tick.  Planes this thread does
 // not hold in registers are patched with fire-and-forget reductions (RED), so nothing waits on them.
 template <int FB>
-__device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride, uint32_t& G, uint32_t& B, uint32_t h0,
-                                                     uint32_t h1, uint32_t h2, uint32_t h3, const DevState& s,
+__device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride, uint32_t* Frec, uint32_t& G, uint32_t& B,
+                                                     uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3, const DevState& s,
                                                      const StepCfg& c, uint32_t* hrow, int wid, int kmin,
                                                      uint32_t edge, int& my_edge) {
     uint32_t m = h0 | h1 | h2 | h3;
     // issue the loads of this word together: fuel planes (only if it burns) and the first heated cells
     uint32_t FU[FB];
-    if (B) {
-#pragma unroll
-        for (int q = 0; q < FB; ++q) FU[q] = P[(P_FU0 + q) * pstride];
-    }
+    if (B) load_fuel<FB>(Frec, FU);
     int y[4];
     uint32_t v[4];
     uint32_t mm = m;
@@ -423,8 +440,7 @@ __device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride
             nz |= FU[q];
         }
         out = B & ~nz;
-#pragma unroll
-        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = FU[q];
+        store_fuel<FB>(Frec, FU);
 #pragma unroll
         for (int q = 1; q < FB; ++q) ge2 |= FU[q];  // fuel >= 2, for every cell of the word
     }
@@ -454,9 +470,10 @@ __device__ __forceinline__ uint32_t tick_active_word(uint32_t* P, size_t pstride
     if (ign) {
         atomicOr(&P[P_F * pstride], ign);
         G &= ~ign; B |= ign;
-        if (!burning_word) {  // heated-only word that ignites (rare): now its fuel planes are needed
+        if (!burning_word) {  // heated-only word that ignites (rare): now its fuel is needed
+            load_fuel<FB>(Frec, FU);
 #pragma unroll
-            for (int q = 1; q < FB; ++q) ge2 |= P[(P_FU0 + q) * pstride];
+            for (int q = 1; q < FB; ++q) ge2 |= FU[q];
         }
     }
     if (ign | out) {
@@ -614,9 +631,9 @@ __device__ __forceinline__ void tick_slice(const Env& e, const DevState& s, cons
             const int x = e.row_of(wi), w = wi - x * HW;
             uint32_t Gq = q_G[it], Bq = q_B[it];
             uint32_t* P = e.P0 + wi;
-            const uint32_t sn = tick_active_word<FB>(P, pstride, Gq, Bq, q_h[it], q_h[QW + it], q_h[2 * QW + it],
-                                                     q_h[3 * QW + it], s, c, e.hits + ((size_t)x * H + 32 * w), wid, kmin,
-                                                     edge_word(W, H, x, w), my_edge);
+            const uint32_t sn = tick_active_word<FB>(P, pstride, e.FU + (size_t)wi * kFuelRec, Gq, Bq, q_h[it], q_h[QW + it],
+                                                     q_h[2 * QW + it], q_h[3 * QW + it], s, c,
+                                                     e.hits + ((size_t)x * H + 32 * w), wid, kmin, edge_word(W, H, x, w), my_edge);
             P[(size_t)snxt * pstride] = sn;
             my_nb += __popc(Bq);
             my_ng += __popc(Gq);
@@ -859,8 +876,12 @@ __device__ void reset_env(const Env& e, const DevState& s, const StepCfg& c, con
         P[P_G * pstride] = valid;
         P[P_F * pstride] = 0u; P[P_BT * pstride] = 0u; P[P_D * pstride] = 0u; P[P_WT * pstride] = 0u;
         P[P_B * pstride] = 0u; P[P_I * pstride] = 0u;
+        {
+            uint32_t FU[FB];
 #pragma unroll
-        for (int q = 0; q < FB; ++q) P[(P_FU0 + q) * pstride] = ((c.fuel >> q) & 1) ? valid : 0u;
+            for (int q = 0; q < FB; ++q) FU[q] = ((c.fuel >> q) & 1) ? valid : 0u;
+            store_fuel<FB>(e.FU + (size_t)i * kFuelRec, FU);
+        }
         P[(size_t)t.P_S0 * pstride] = 0u;
         P[(size_t)t.P_S1 * pstride] = 0u;
         P[(size_t)t.P_R * pstride] = valid;  // open field: every cell reaches the border (re-flooded if rivers)
@@ -1017,6 +1038,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
     e.pstride = t.pstride;
     e.P0 = s.planes + (size_t)e.env * t.env_words;
     e.hits = s.hits + (size_t)e.env * t.cells;
+    e.FU = s.fuel + (size_t)e.env * t.env_words * kFuelRec;
     const int tid = e.tid;
 
     for (int v = tid; v < 256; v += e.T) {
@@ -1169,6 +1191,7 @@ __global__ void rebuild_kernel(DevState s, TilePar t) {
     e.pstride = t.pstride;
     e.P0 = s.planes + (size_t)e.env * t.env_words;
     e.hits = s.hits + (size_t)e.env * t.cells;
+    e.FU = s.fuel + (size_t)e.env * t.env_words * kFuelRec;
     int32_t* sc = s.scal + (size_t)e.env * WF_NSCALARS;
     const int cur = sc[WF_S_RESERVED] & 1;
     if (e.tid < kRed) red[e.tid] = 0;
@@ -1177,7 +1200,7 @@ __global__ void rebuild_kernel(DevState s, TilePar t) {
     for (int i = e.tid; i < e.nwords; i += e.T) {
         uint32_t* P = e.P0 + i;
         uint32_t ge2 = 0u;
-        for (int q = 1; q < s.FB; ++q) ge2 |= P[(size_t)(P_FU0 + q) * e.pstride];
+        for (int q = 1; q < s.FB; ++q) ge2 |= e.FU[(size_t)i * kFuelRec + q];
         const uint32_t B = P[P_B * e.pstride];
         P[(size_t)(cur ? t.P_S1 : t.P_S0) * e.pstride] = B & ge2;
         n += __popc(B);
@@ -1230,9 +1253,9 @@ static cudaError_t set_smem_attr() {
 
 cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     TileState* t = new TileState();
-    t->P_S0 = 7 + s.FB;
-    t->P_S1 = 8 + s.FB;
-    t->P_R = 9 + s.FB;
+    t->P_S0 = P_FU0;  // no fuel planes in this family: the fuel has its own records (DevState::fuel)
+    t->P_S1 = P_FU0 + 1;
+    t->P_R = P_FU0 + 2;
     choose_geometry(s, t->T, t->CS);
     cudaError_t e;
     if ((e = set_smem_attr<5, 1, false>()) != cudaSuccess) return e;
