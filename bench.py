@@ -58,6 +58,7 @@ WORKLOADS = {
                desc="1024x1024, no wind, 256 extra ignitions, 64 envs/GPU, ACTION-stream actions, auto-reset"),
 }
 BYTES_PER_CELL_UPDATE = 15  # 6 B state read + 6 B state write + 3 B uint8 observation
+CPU_BASELINE_SECONDS = 12.0  # bounded sample of the cpu_baseline leg
 
 
 def load_peaks():
@@ -447,7 +448,7 @@ def run_ours(args, wl):
         from oracle import wf_oracle as wo  # the checker, timed as the CPU baseline (allowed use)
         ob = wo.OracleBatch(oracle_cfg(wl["meta"]), min(N, 1024), 1)
         t0 = time.perf_counter(); n = ob.step(2); rate = n / (time.perf_counter() - t0)
-        steps_cpu = max(1, int(rate * 12.0 / ob.n_envs))
+        steps_cpu = max(1, int(rate * CPU_BASELINE_SECONDS / ob.n_envs))
         t0 = time.perf_counter(); n = ob.step(steps_cpu); dt = time.perf_counter() - t0
         cpu_baseline = {"value": n / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
                         "sample": f"{ob.n_envs} envs x {steps_cpu} steps of the same workload, 1 thread, {dt:.1f} s",
@@ -461,7 +462,8 @@ def run_ours(args, wl):
                    "steps_per_launch": res["chunk"] if res["fused"] else None,
                    "steps_per_graph_replay": res["chunk"] if res["graph"] else None, "kernel_family": res["family"],
                    "l2": f"outputs of one launch/replay ({res['obs_mb']:.0f} MB obs) exceed the 126 MB L2; "
-                         + ("state is register/L2 resident by design" if res["family"] == "warp" else f"state ({res['state_bytes'] * res['N'] / 1e6:.0f} MB) exceeds L2 too")},
+                         + ("state is register/L2 resident by design" if res["family"] == "warp"
+                            else f"state ({res['state_bytes'] * res['N'] / 1e6:.0f} MB) exceeds L2 too")},
         "cell_updates_per_sec": res["value"] * W * H,
         "cell_updates_per_sec_per_gpu": res["value"] * W * H / world,
         "e2e": res.get("e2e"), "per_step_launch": res.get("per_step"),
