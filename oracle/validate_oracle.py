@@ -47,10 +47,12 @@ SCENARIOS = [
 ]
 
 
-def random_scenario(rng, i):
-    """A random configuration of everything the step reads (square maps: Q6 is history-dependent on W > H)."""
+def random_scenario(rng, i, wide=False):
+    """A random configuration of everything the step reads.  wide: W > H maps, where the literal [HEIGHT-1, y] border
+    points of environment.py:222 are an interior column (the oracle keeps the reference's destructive deque there)."""
     size = int(rng.choice([10, 11, 12, 13, 14, 16, 18, 20, 24, 28]))
-    sc = dict(name=f"rand{i}_{size}", width=size, height=size, seed=int(rng.integers(1, 1 << 30)))
+    width = size + (int(rng.integers(1, 7)) if wide else 0)
+    sc = dict(name=f"rand{i}_{width}x{size}", width=width, height=size, seed=int(rng.integers(1, 1 << 30)))
     w = rng.integers(0, 4)
     if w == 1:
         sc["wind"] = "random"
@@ -142,13 +144,14 @@ def main(argv=None):
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--only", default=None)
     ap.add_argument("--random", type=int, default=0, help="number of randomised scenarios to run instead of the list")
+    ap.add_argument("--wide", action="store_true", help="with --random: W > H maps")
     ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args(argv)
     total = 0
     scenarios = SCENARIOS
     if args.random:
         rng = np.random.default_rng(args.seed)
-        scenarios = [random_scenario(rng, i) for i in range(args.random)]
+        scenarios = [random_scenario(rng, i, args.wide) for i in range(args.random)]
     for sc in scenarios:
         if args.only and args.only != sc["name"]:
             continue
