@@ -413,7 +413,9 @@ def roofline_of(res, world):
         own = W * H * (3 * 4 / 32 + 4 / 32 + 2 * 4 / 32 + 3)
         kernel = "wf::tile_rollout_kernel"
         note = ("HBM-bound: one cluster per env streams 6 plane words + 96 B of observation per 32 cells and step; "
-                "fuel planes / hit counters are touched only where the fire front is")
+                "fuel records / hit counters are touched only where the fire front is.  `achieved` uses SURVEY 8(d)'s 15 B per "
+                "cell-update (byte-per-cell state read + written, 3 B observation); the bit-plane layout moves 3.75 B, so "
+                "`frac` can exceed 1 -- `frac_own_layout` is the fraction of peak in bytes this layout really moves")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
