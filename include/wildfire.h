@@ -151,7 +151,8 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * bit stream and is expanded into obs_host by a small pool of host threads (WF_HOST_THREADS, default
  * min(12, 3/4 of the cores / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead,
  * WF_HOST_PACKED=direct stores the bit stream straight into mapped host memory instead of one DMA copy;
- * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed).
+ * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed; WF_HOST_GRAPH=1 (experimental,
+ * a_speed == 1 only) issues kernel + copy as one CUDA graph).
  * The device alias of each page-locked buffer is looked up once and re-validated every 1024 calls: a caller that
  * unpins or frees a buffer must not hand the same ADDRESS back as a different kind of memory within that window
  * (pass a new address, or destroy the handle). */

@@ -71,6 +71,11 @@ struct wf_env {
     uint32_t alias_age;         // the cache is re-validated every 1024 calls (a buffer may have been re-allocated)
     double t_launch, t_sync, t_expand;  // WF_HOST_TIMING=1: accumulated seconds of the packed path's three parts
     int64_t t_calls;
+    // WF_HOST_GRAPH=1 (experiment, off by default): the packed path's kernel + DMA copy as ONE instantiated CUDA graph,
+    // re-captured when the caller's buffers change.  Only with a_speed == 1 (then every launch has the same parameters).
+    bool host_graph;
+    cudaGraphExec_t hg_exec;
+    const void* hg_key[3];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -369,6 +374,7 @@ void wf_destroy(wf_env* e) {
     if (e->t_calls && getenv("WF_HOST_TIMING"))
         fprintf(stderr, "wf_step_host (packed path), %lld calls: launch %.2f us, sync %.2f us, expand %.2f us per call\n",
                 (long long)e->t_calls, 1e6 * e->t_launch / e->t_calls, 1e6 * e->t_sync / e->t_calls, 1e6 * e->t_expand / e->t_calls);
+    if (e->hg_exec) cudaGraphExecDestroy(e->hg_exec);
     if (e->h_packed) cudaFreeHost(e->h_packed);
     cudaFree(e->d_packed);
     if (e->pool) hostpool_destroy(e->pool);
@@ -543,6 +549,8 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const char* pk = getenv("WF_HOST_PACKED");
         e->host_packed = !(pk && pk[0] == '0');
         e->packed_dma = !(pk && std::string(pk) == "direct");  // default: stage in HBM, one DMA copy ("direct": zero-copy stores)
+        const char* hg = getenv("WF_HOST_GRAPH");
+        e->host_graph = hg && hg[0] == '1' && e->cfg.a_speed == 1;
     }
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
@@ -568,6 +576,7 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const int64_t env_bits = (int64_t)s.W * s.H * 3, records = (s.N + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
         const size_t need = (size_t)records * rec_words;
         if (e->h_packed_words < need) {
+            if (e->hg_exec) { cudaGraphExecDestroy(e->hg_exec); e->hg_exec = nullptr; }
             if (e->h_packed) cudaFreeHost(e->h_packed);
             cudaFree(e->d_packed);
             e->h_packed = nullptr;
@@ -580,11 +589,34 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         }
         if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
         const auto t0 = std::chrono::steady_clock::now();
-        int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->packed_dma ? e->d_packed : e->h_packed_dev, kObsPacked,
-                         static_cast<double*>(r_d), static_cast<uint8_t*>(d_d), e->hstream);
-        if (rc != WF_OK) return rc;
-        if (e->packed_dma)
-            WF_CUDA(cudaMemcpyAsync(e->h_packed, e->d_packed, need * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->hstream));
+        if (e->host_graph && e->packed_dma) {
+            if (!e->hg_exec || e->hg_key[0] != a_d || e->hg_key[1] != r_d || e->hg_key[2] != d_d) {
+                if (e->hg_exec) { cudaGraphExecDestroy(e->hg_exec); e->hg_exec = nullptr; }
+                const int64_t launches0 = e->launches;
+                cudaGraph_t g = nullptr;
+                WF_CUDA(cudaStreamBeginCapture(e->hstream, cudaStreamCaptureModeThreadLocal));
+                int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->d_packed, kObsPacked, static_cast<double*>(r_d),
+                                 static_cast<uint8_t*>(d_d), e->hstream);
+                cudaError_t ce = cudaMemcpyAsync(e->h_packed, e->d_packed, need * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->hstream);
+                cudaError_t ee = cudaStreamEndCapture(e->hstream, &g);
+                e->launches = launches0;  // nothing ran yet
+                if (rc != WF_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                WF_CUDA(ce);
+                WF_CUDA(ee);
+                cudaError_t ie = cudaGraphInstantiate(&e->hg_exec, g, 0);
+                cudaGraphDestroy(g);
+                WF_CUDA(ie);
+                e->hg_key[0] = a_d; e->hg_key[1] = r_d; e->hg_key[2] = d_d;
+            }
+            WF_CUDA(cudaGraphLaunch(e->hg_exec, e->hstream));
+            e->launches += 1;
+        } else {
+            int rc = wf_step(e, static_cast<const int32_t*>(a_d), e->packed_dma ? e->d_packed : e->h_packed_dev, kObsPacked,
+                             static_cast<double*>(r_d), static_cast<uint8_t*>(d_d), e->hstream);
+            if (rc != WF_OK) return rc;
+            if (e->packed_dma)
+                WF_CUDA(cudaMemcpyAsync(e->h_packed, e->d_packed, need * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->hstream));
+        }
         const auto t1 = std::chrono::steady_clock::now();
         WF_CUDA(cudaStreamSynchronize(e->hstream));
         const auto t2 = std::chrono::steady_clock::now();
