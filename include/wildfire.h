@@ -14,7 +14,11 @@
  *   - "dev" pointers are device pointers on the handle's GPU, owned by the caller
  *     (torch tensors); the library owns only the environments' internal planes.
  *   - All *_dev calls are asynchronous on `stream` (a cudaStream_t passed as void*;
- *     NULL = the legacy default stream).  A handle is not thread-safe.
+ *     NULL = the legacy default stream).  A handle is not thread-safe.  The *_host calls
+ *     (wf_step_host, wf_reset_host) run on a private stream of the handle and are ordered
+ *     behind every *_dev call made on the handle before them (an event on that call's stream);
+ *     they synchronise before returning, so later *_dev calls are ordered behind them too.
+ *   - Every call runs on the handle's device and restores the caller's current device.
  *   - Grid indexing follows the reference: cell (x, y) of env n lives at
  *     [n][x][y], x is the SLOW axis (environment.py: env[x, y, layer]).
  *   - Return value: WF_OK (0) or a negative error code; wf_last_error() gives text.
@@ -158,6 +162,10 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * (pass a new address, or destroy the handle). */
 int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32_t obs_dtype,
                  double* reward_host, uint8_t* done_host);
+/* Host-buffer variant of wf_reset (ForestFire.reset, forest_fire.py:52-54): mask_host / init_host as in wf_reset but in
+ * host memory (NULL = all envs / draw the start cell), obs_host [N][W][H][3] receives World.get_state() (NULL = skip).
+ * Synchronises.  Ordered behind every earlier call on the handle, like wf_step_host. */
+int wf_reset_host(wf_env* env, const uint8_t* mask_host, const wf_init* init_host, void* obs_host, int32_t obs_dtype);
 /* Host threads wf_step_host uses to expand observations (0: the packed path has not been used). */
 int wf_host_threads(const wf_env* env);
 /* The host half of that path on its own (no GPU needed): expand a packed observation buffer -- one record of
@@ -176,6 +184,11 @@ int wf_get_state(wf_env* env, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, 
                  uint8_t* hits, uint8_t* apos, int32_t* scalars, void* stream);
 int wf_set_state(wf_env* env, const uint8_t* type, const uint8_t* burning, const uint8_t* fm_inf,
                  const uint8_t* fuel, const uint8_t* hits, const int32_t* scalars, void* stream);
+/* METADATA['a_speed_iter'] (forest_fire.py:40-43; constants.py:38): steps left until the next fire tick, 1..a_speed.
+ * One counter per handle, NOT reset by wf_reset (quirk Q8) and not part of the per-env scalars: a checkpoint of a handle
+ * with a_speed > 1 is wf_get_state + wf_get_a_iter, restored by wf_set_state + wf_set_a_iter. */
+int wf_get_a_iter(const wf_env* env, int32_t* out);
+int wf_set_a_iter(wf_env* env, int32_t a_iter);
 /* World.set_fire_to(cell) on selected envs: cells_dev [N][2] int32 (x, y), x < 0 = skip. */
 int wf_set_fire_to(wf_env* env, const int32_t* cells_dev, void* stream);
 /* World.get_state() without stepping. */
@@ -195,6 +208,10 @@ int wf_stats_reset(wf_env* env, void* stream);
  * so the device generator can be pinned to the Random123 known-answer vectors. */
 int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_host[4]);
 
+/* Tile family: threads per CTA and CTAs per thread-block cluster (one cluster per env) the handle launches with; chosen
+ * from n_envs so that the batch fills the GPU (overridable for experiments and tests: WF_TILE_T, WF_TILE_CS, read by
+ * wf_create).  Warp family: both 0. */
+int wf_tile_geometry(const wf_env* env, int32_t* threads, int32_t* cluster);
 /* How many kernels of this library the handle has launched (bench.py's gpu_launches). */
 int64_t wf_launch_count(const wf_env* env);
 /* Introspection for DESIGN.md / bench roofline: bytes of internal state per env. */

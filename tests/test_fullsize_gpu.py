@@ -112,3 +112,94 @@ def test_free_burn_without_wind_is_mirror_symmetric_256():
     assert torch.equal(typ, typ.T) and torch.equal(fuel, fuel.T)
     total = hits.int().sum(-1)
     assert torch.equal(total, total.T)
+
+
+# ---------------------------------------------------------------------------------------------
+# The tile geometries bench.py really runs.  choose_geometry (wf_tile.cu) picks threads-per-CTA x CTAs-per-cluster from
+# the number of envs: C4's 1024 envs of 256x256 get (256, 1), C5's 64 envs of 1024x1024 get (256, 8).  A handful of envs
+# would get a different geometry, so the production one is forced (WF_TILE_T / WF_TILE_CS, read by wf_create) and the
+# test asserts that it is the one the full batch gets.
+def _production_geometry(monkeypatch, size, full_batch):
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    monkeypatch.delenv("WF_TILE_T", raising=False)
+    monkeypatch.delenv("WF_TILE_CS", raising=False)
+    probe = BatchedForestFire(full_batch, width=size, height=size)  # no reset: only asks which geometry the batch gets
+    geom = probe.tile_geometry
+    probe.close()
+    monkeypatch.setenv("WF_TILE_T", str(geom[0]))
+    monkeypatch.setenv("WF_TILE_CS", str(geom[1]))
+    return geom
+
+
+def _rollout_against_oracle(gpu, orc, steps, chunk, policy, check_state_every):
+    """`steps` steps in launches of `chunk` (what bench.py times), every action / reward / done / observation of every
+    env against the oracle, auto-reset included; full state every `check_state_every` steps."""
+    events = dict(contained=0, done=0, deaths=0)
+    s = 0
+    while s < steps:
+        c = min(chunk, steps - s)
+        obs, rew, done, acts = gpu.rollout(c, policy=policy, return_actions=True)
+        obs, rew, done, acts = to_np(obs), to_np(rew), to_np(done), to_np(acts)
+        for i, e in enumerate(orc):
+            for k in range(c):
+                a = e.walk_action() if policy == "walk" else e.random_action()
+                assert acts[k, i] == a, (s + k, i)
+                o, r, d, _ = e.step(a)
+                if r == 1000.0:
+                    events["contained"] += 1
+                if d:
+                    events["done"] += 1
+                    events["deaths"] += int(r == -1000.0)
+                    o = e.reset()
+                assert rew[k, i] == r and bool(done[k, i]) == d, (s + k, i, rew[k, i], r)
+                assert np.array_equal(obs[k, i], o), (s + k, i)
+        s += c
+        if s % check_state_every == 0 or s == steps:
+            compare_states(f"step {s}", gpu, orc)
+    return events
+
+
+def test_c4_production_geometry_matches_oracle(monkeypatch):
+    """C4 (256x256, wind [0.85,(1,0)], 32 extra ignitions) on the geometry its 1024-env batch runs with: 256 threads,
+    cluster of 1.  300 ticks in 16-step launches: several ignition generations, burn-outs, deaths and auto-resets."""
+    geom = _production_geometry(monkeypatch, 256, 1024)
+    assert geom == (256, 1)
+    cfg = dict(width=256, height=256, seed=6, wind=[0.85, (1, 0)], extra_ignitions=32)
+    gpu, orc = make_pair(6, cfg, auto_reset=True)
+    assert gpu.tile_geometry == geom
+    obs = gpu.reset()
+    for e in orc:
+        e.reset()
+    compare_states("reset", gpu, orc, obs=obs)
+    ev = _rollout_against_oracle(gpu, orc, 304, 16, "stream", 64)
+    assert ev["done"] >= 1  # at least one in-kernel reset happened
+
+
+def test_c5_production_geometry_matches_oracle(monkeypatch):
+    """C5 (1024x1024, no wind, 256 extra ignitions) on the geometry its 64-env batch runs with: 8 CTAs of 256 threads per
+    env.  272 ticks in 16-step launches (14 ignition generations of the 19-tick delay; the first fires burn out at tick 20)."""
+    geom = _production_geometry(monkeypatch, 1024, 64)
+    assert geom == (256, 8)
+    cfg = dict(width=1024, height=1024, seed=6, extra_ignitions=256)  # envs 0 and 2 start with no fire on the border
+    gpu, orc = make_pair(3, cfg, auto_reset=True)
+    assert gpu.tile_geometry == geom
+    obs = gpu.reset()
+    for e in orc:
+        e.reset()
+    compare_states("reset", gpu, orc, obs=obs)
+    _rollout_against_oracle(gpu, orc, 272, 16, "stream", 136)
+
+
+def test_c5_geometry_walk_policy_contains_burns_out_and_resets(monkeypatch):
+    """1024x1024 on the C5 geometry with the reference's heuristic walk policy (DQN.py:353-389): the bulldozer rings
+    the fire (containment bonus, environment.py:342-377 -- the reach plane is cut by the closing dig and re-flooded by
+    the whole cluster), the ring burns out (burn-out reward), the env resets inside the kernel and does it again."""
+    geom = _production_geometry(monkeypatch, 1024, 64)
+    cfg = dict(width=1024, height=1024, seed=6)
+    gpu, orc = make_pair(2, cfg, auto_reset=True)
+    assert gpu.tile_geometry == geom == (256, 8)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    ev = _rollout_against_oracle(gpu, orc, 256, 16, "walk", 128)
+    assert ev["contained"] >= 2 and ev["done"] >= 2 and ev["deaths"] == 0

@@ -1,0 +1,191 @@
+"""The host-buffer entry points (wf_step_host / wf_reset_host, include/wildfire.h) the way a maintainer of the
+reference would call them: plain pageable NumPy arrays through the ctypes binding of INTEGRATION.md section 3
+(kept verbatim in tools/reference_binding/forest_fire_b200.py), inside a stand-in ``Simulation`` package that
+holds only the two modules the binding imports (constants.METADATA, utility.grass).  Plus the ordering and
+bookkeeping contracts of the handle: *_host calls run behind earlier *_dev calls, the caller's current device is
+left alone, wf_stats counts fire ticks, a checkpoint carries the tick phase (a_speed > 1)."""
+import importlib
+import os
+import re
+import shutil
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wf_oracle as wo
+from tests.gpu_util import compare_states, make_pair, to_np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BINDING = os.path.join(ROOT, "tools", "reference_binding", "forest_fire_b200.py")
+
+
+def test_integration_md_snippet_is_the_tested_file():
+    """INTEGRATION.md section 3 shows exactly the file the GPU test below executes (CPU-only check)."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = md[md.index("## 3. The reference-side binding"):md.index("## 4.")]
+    code = re.search(r"```python\n(.*?)```", sec, re.S).group(1)
+    assert code == open(BINDING).read()
+
+
+def _stand_in_package(tmp_path, metadata, grass):
+    pkg = tmp_path / "Simulation"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "constants.py").write_text(f"METADATA = {metadata!r}\n")
+    (pkg / "utility.py").write_text(f"grass = {grass!r}\n")
+    shutil.copy(BINDING, pkg / "forest_fire_b200.py")
+    from wildfire_control_python_b200 import _lib
+    os.symlink(_lib.LIB_PATH, pkg / "libwildfire_b200.so")
+    for name in [m for m in sys.modules if m == "Simulation" or m.startswith("Simulation.")]:
+        del sys.modules[name]
+    sys.path.insert(0, str(tmp_path))
+    try:
+        return importlib.import_module("Simulation.forest_fire_b200")
+    finally:
+        sys.path.remove(str(tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,n_envs,wind,steps", [(14, 33, [0.54, (0, 0)], 80), (10, 5, [0.85, (1, 0)], 60), (40, 6, [0.54, (0, 0)], 50)],
+                         ids=["14x14_n33", "10x10_wind", "tile_40x40"])
+def test_integration_snippet_pageable_numpy_buffers_match_oracle(tmp_path, size, n_envs, wind, steps):
+    """The INTEGRATION.md binding, verbatim: pageable NumPy buffers land on wf_step_host's staged branch."""
+    from wildfire_control_python_b200.constants import make_metadata
+    meta = make_metadata(width=size, height=size, wind=wind)
+    metadata = {k: meta[k] for k in ("width", "height", "n_actions", "a_speed", "allow_dig_toggle", "make_rivers", "wind",
+                                     "death_penalty", "contained_bonus", "default_reward")}
+    metadata["wind"] = [wind[0], tuple(wind[1])]
+    grass = {"heat": meta["heat"], "fuel": meta["fuel"], "threshold": meta["threshold"], "radius": 1}
+    mod = _stand_in_package(tmp_path, metadata, grass)
+    sim = mod.ForestFire(n_envs=n_envs, seed=77)
+    cfg = dict(width=size, height=size, wind=wind, seed=77)
+    orc = [wo.OracleEnv(cfg, env_id=i) for i in range(n_envs)]
+    obs = sim.reset()
+    assert obs.dtype == np.float64 and obs.shape == (n_envs, size, size, 3)
+    for i, e in enumerate(orc):
+        assert np.array_equal(obs[i], e.reset()), i
+    assert not torch.as_tensor(sim.obs).is_pinned()  # really the pageable branch
+    for s in range(steps):
+        acts = [e.random_action() for e in orc]
+        live = [bool(e.planes()["running"]) for e in orc]
+        obs, rew, done, info = sim.step(acts)
+        for i, e in enumerate(orc):
+            if not live[i]:
+                assert rew[i] == 0.0 and done[i]
+                continue
+            o, r, d, _ = e.step(acts[i])
+            assert rew[i] == r and bool(done[i]) == d and np.array_equal(obs[i], o), (s, i)
+    # masked reset of the finished envs through the host entry point, start cells drawn from the stream
+    fin = np.array([0 if e.planes()["running"] else 1 for e in orc], np.uint8)
+    if fin.any():
+        rc = mod.lib.wf_reset_host(sim.h, fin.ctypes.data, None, sim.obs, 0)
+        assert rc == 0
+        for i, e in enumerate(orc):
+            if fin[i]:
+                assert np.array_equal(sim.obs[i], e.reset()), i
+            else:
+                assert np.array_equal(sim.obs[i], e.obs()), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n_envs", [(dict(width=256, height=256, seed=31, extra_ignitions=16), 96),
+                                        (dict(width=14, height=14, seed=32), 4096)], ids=["tile_256_n96", "warp_14_n4096"])
+def test_step_host_is_ordered_behind_device_calls(cfg, n_envs):
+    """reset() on the caller's stream, then step_host() at once (bench.py and every e2e loop do this): the step on
+    the handle's private stream must see the finished reset.  A long kernel is queued in front of the reset so that
+    an unordered step would certainly overtake it."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    gpu, twin = BatchedForestFire(n_envs, **cfg), BatchedForestFire(n_envs, **cfg)
+    twin.reset()
+    acts = np.random.default_rng(5).integers(0, 4, size=(4, n_envs), dtype=np.int32)
+    ref = []
+    for k in range(4):
+        o, r, d, _ = twin.step(torch.from_numpy(acts[k]).cuda())
+        ref.append((to_np(o).copy(), to_np(r).copy(), to_np(d).copy()))
+    big = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
+    for rep in range(3):
+        for _ in range(6):
+            big.normal_()  # ~ms of queued work on the current stream
+        gpu.reset()
+        for k in range(4):
+            o, r, d, _ = gpu.step_host(acts[k])
+            assert np.array_equal(o, ref[k][0]) and np.array_equal(r, ref[k][1]) and np.array_equal(d, ref[k][2]), (rep, k)
+    # and the other direction: device-side calls after a host step see its result
+    st_a, st_b = gpu.get_state(), twin.get_state()
+    for key in ("type", "burning", "fuel", "scalars"):
+        assert torch.equal(st_a[key][:, ...], st_b[key][:, ...]), key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [14, 48], ids=["warp", "tile"])
+def test_stats_count_fire_ticks(size):
+    """wf_stats[5] (include/wildfire.h): env fire ticks = env-steps on which ForestFire.update ran (every a_speed steps)."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    N, K = 7, 30
+    for a_speed in (1, 3):
+        env = BatchedForestFire(N, width=size, height=size, seed=3, a_speed=a_speed)
+        env.reset(starts=torch.tensor([[size // 2 + 3, size // 2]] * N, dtype=torch.int32))
+        env.rollout(K, actions=torch.full((K, N), 9, dtype=torch.int32, device="cuda"), obs=False)  # no-ops: nobody dies
+        st = env.stats()
+        assert st["env_steps"] == N * K
+        assert st["ticks"] == N * (K // a_speed), (a_speed, st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(width=14, height=14, seed=821, a_speed=3), dict(width=48, height=40, seed=822, a_speed=2)],
+                         ids=["warp_a3", "tile_a2"])
+def test_checkpoint_restores_the_tick_phase(cfg):
+    """a_speed > 1: METADATA['a_speed_iter'] (Q8) lives in the handle; get_state()/set_state() carry it, so a handle
+    restored MID-PHASE ticks the fire on the same steps as the original."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    N, K2 = 9, 60
+    for K1 in (cfg["a_speed"] + 1, 2 * cfg["a_speed"] + 2):  # both leave the counter away from its initial value
+        a = BatchedForestFire(N, auto_reset=True, **cfg)
+        a.reset()
+        gen = torch.Generator("cuda").manual_seed(cfg["seed"])
+        acts = torch.randint(0, 4, (K1 + K2, N), dtype=torch.int32, device="cuda", generator=gen)
+        a.rollout(K1, actions=acts[:K1], obs=False)
+        st = a.get_state()
+        assert st["a_iter"] == a.a_speed_iter and st["a_iter"] != cfg["a_speed"]
+        b = BatchedForestFire(N, auto_reset=True, **cfg)
+        b.set_state(**st)
+        assert b.a_speed_iter == st["a_iter"]
+        oa, ra, da = a.rollout(K2, actions=acts[K1:])
+        ob, rb, db = b.rollout(K2, actions=acts[K1:])
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(oa, ob)
+        sa, sb = a.get_state(), b.get_state()
+        for k in ("type", "burning", "fm_inf", "fuel", "apos"):
+            assert torch.equal(sa[k], sb[k]), k
+        assert sa["a_iter"] == sb["a_iter"]
+
+
+@pytest.mark.gpu
+def test_set_fire_to_twice_counts_one_burning_cell():
+    """World.set_fire_to adds to a SET (environment.py:236): re-igniting a burning cell leaves len(burning_cells) alone."""
+    cfg = dict(width=14, height=14, seed=9)
+    gpu, orc = make_pair(3, cfg)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    cells = torch.tensor([[2, 3], [-1, 0], [7, 7]], dtype=torch.int32)  # env 2: the centre already burns
+    for _ in range(2):
+        gpu.set_fire_to(cells)
+    orc[0].set_fire_to(2, 3)
+    orc[0].set_fire_to(2, 3)
+    orc[2].set_fire_to(7, 7)
+    compare_states("set_fire_to twice", gpu, orc, obs=gpu.observe())
+
+
+@pytest.mark.gpu
+def test_calls_leave_the_current_device_alone():
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    env = BatchedForestFire(8, device="cuda:1", width=14, height=14)
+    env.reset()
+    env.step(torch.zeros(8, dtype=torch.int32, device="cuda:1"))
+    env.step_host(np.zeros(8, np.int32))
+    assert torch.cuda.current_device() == 0

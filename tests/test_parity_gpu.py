@@ -258,11 +258,19 @@ def test_float_observation_equals_u8(cfg, n_envs, dtype):
                                                (dict(width=10, height=10, seed=503), 7, "1"), (dict(width=32, height=32, seed=504), 5, "1"),
                                                (dict(width=17, height=13, seed=505, wind="random"), 9, "1"),
                                                (dict(width=14, height=14, seed=506), 16, "0"), (dict(width=40, height=36, seed=507), 6, "1"),
-                                               (dict(width=14, height=14, seed=508), 601, "1"), (dict(width=20, height=20, seed=509), 530, "1")],
-                         ids=["14_even", "14_odd", "10", "32", "17x13", "14_unpacked", "tile_40x36", "14_n601", "20_n530"])
+                                               (dict(width=14, height=14, seed=508), 601, "1"), (dict(width=20, height=20, seed=509), 530, "1"),
+                                               (dict(width=14, height=14, seed=510), 77, "1+graph"), (dict(width=32, height=30, seed=511), 9, "1+graph"),
+                                               (dict(width=14, height=14, seed=512), 40, "direct")],
+                         ids=["14_even", "14_odd", "10", "32", "17x13", "14_unpacked", "tile_40x36", "14_n601", "20_n530",
+                              "14_graph", "32x30_graph", "14_direct"])
 def test_step_host_roundtrip(monkeypatch, cfg, n_envs, packed):
     """wf_step_host with page-locked host buffers: the packed path (observation bit stream into mapped host
-    memory + host-thread expansion, grids up to 32x32), the plain uint8 path (WF_HOST_PACKED=0) and the tile family."""
+    memory + host-thread expansion, grids up to 32x32; "+graph": kernel + copy as one CUDA graph, WF_HOST_GRAPH=1;
+    "direct": the kernel stores the stream straight into mapped host memory), the plain uint8 path (WF_HOST_PACKED=0)
+    and the tile family."""
+    if packed.endswith("+graph"):
+        packed = packed[:-6]
+        monkeypatch.setenv("WF_HOST_GRAPH", "1")
     monkeypatch.setenv("WF_HOST_PACKED", packed)
     monkeypatch.setenv("WF_HOST_THREADS", "3")
     gpu, orc = make_pair(n_envs, cfg)
@@ -277,7 +285,7 @@ def test_step_host_roundtrip(monkeypatch, cfg, n_envs, packed):
                 continue
             o, r, d, _ = e.step(int(acts[i]))
             assert rew[i] == r and bool(done[i]) == d and np.array_equal(obs[i], o), (s, i)
-    want_threads = 3 if (packed == "1" and max(cfg["width"], cfg["height"]) <= 32) else 0
+    want_threads = 3 if (packed != "0" and max(cfg["width"], cfg["height"]) <= 32) else 0
     assert gpu.host_threads == want_threads
 
 

@@ -84,9 +84,12 @@ def lib():
     L.wf_rollout_policy.argtypes = [vp, C.c_int32, C.c_int32, i32p, vp, C.c_int32, f64p, u8p, vp]
     L.wf_set_policy_mlp.argtypes = [vp, vp, vp, vp, vp, C.c_int32, C.c_double]
     L.wf_step_host.argtypes = [vp, i32p, vp, C.c_int32, f64p, u8p]
+    L.wf_reset_host.argtypes = [vp, u8p, vp, vp, C.c_int32]
     L.wf_get_state.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, u8p, i32p, vp]
     L.wf_set_state.argtypes = [vp, u8p, u8p, u8p, u8p, u8p, i32p, vp]
     L.wf_set_fire_to.argtypes = [vp, i32p, vp]
+    L.wf_get_a_iter.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.wf_set_a_iter.argtypes = [vp, C.c_int32]
     L.wf_get_obs.argtypes = [vp, vp, C.c_int32, vp]
     L.wf_get_wind_table.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32)]
@@ -94,6 +97,7 @@ def lib():
     L.wf_stats_reset.argtypes = [vp, vp]
     L.wf_philox_kat.argtypes = [C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.wf_philox_kat.restype = C.c_int
+    L.wf_tile_geometry.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.wf_launch_count.argtypes = [vp]
     L.wf_launch_count.restype = C.c_int64
     L.wf_host_threads.argtypes = [vp]
@@ -103,7 +107,7 @@ def lib():
     L.wf_state_bytes_per_env.argtypes = [vp]
     L.wf_state_bytes_per_env.restype = C.c_int64
     for name in ("wf_create", "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state",
-                 "wf_set_fire_to", "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset"):
+                 "wf_set_fire_to", "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset", "wf_get_a_iter", "wf_set_a_iter", "wf_reset_host", "wf_tile_geometry"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -118,5 +122,5 @@ EXPORTED_SYMBOLS = [
     "wf_default_config", "wf_create", "wf_destroy", "wf_last_error", "wf_abi_version", "wf_kernel_family",
     "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state", "wf_set_fire_to",
     "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset", "wf_philox_kat", "wf_launch_count",
-    "wf_state_bytes_per_env", "wf_host_threads", "wf_expand_packed_obs",
+    "wf_state_bytes_per_env", "wf_host_threads", "wf_expand_packed_obs", "wf_get_a_iter", "wf_set_a_iter", "wf_reset_host", "wf_tile_geometry",
 ]

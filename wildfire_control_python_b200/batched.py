@@ -258,11 +258,26 @@ class BatchedForestFire:
                                                _ptr(out["scalars"]), self._stream()))
         coef = torch.as_tensor(self.wind_coef, device=dev)[out["scalars"][:, _lib.S_WIND_ID].long()]  # [N, 4]
         out["temp"] = (out["hits"].double() * coef[:, None, None, :]).sum(-1)
+        out["a_iter"] = self.a_speed_iter  # METADATA['a_speed_iter'] (Q8): one counter per handle, part of a checkpoint
         return out
 
-    def set_state(self, type=None, burning=None, fm_inf=None, fuel=None, hits=None, scalars=None):
-        """Overwrite planes / scalars (parity injection, checkpoint restore).  ``None`` = keep."""
+    @property
+    def a_speed_iter(self) -> int:
+        """``METADATA['a_speed_iter']`` (forest_fire.py:40-43): steps left until the next fire tick, 1..a_speed."""
+        v = C.c_int32()
+        _lib.check(_lib.lib().wf_get_a_iter(self._h, C.byref(v)))
+        return int(v.value)
+
+    @a_speed_iter.setter
+    def a_speed_iter(self, value: int):
+        _lib.check(_lib.lib().wf_set_a_iter(self._h, int(value)))
+
+    def set_state(self, type=None, burning=None, fm_inf=None, fuel=None, hits=None, scalars=None, a_iter=None, **_ignored):
+        """Overwrite planes / scalars / the tick phase counter (parity injection, checkpoint restore).  ``None`` = keep.
+        ``set_state(**get_state())`` restores a checkpoint (derived entries such as ``temp`` / ``apos`` are ignored)."""
         N, W, H = self.n_envs, self.width, self.height
+        if a_iter is not None:
+            self.a_speed_iter = int(a_iter)
 
         def u8(t, shape):
             if t is None:
@@ -295,6 +310,13 @@ class BatchedForestFire:
     def reset_stats(self):
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().wf_stats_reset(self._h, self._stream()))
+
+    @property
+    def tile_geometry(self):
+        """Tile family: ``(threads per CTA, CTAs per cluster)`` of this handle's launches; warp family: ``(0, 0)``."""
+        t, c = C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().wf_tile_geometry(self._h, C.byref(t), C.byref(c)))
+        return int(t.value), int(c.value)
 
     @property
     def launch_count(self) -> int:

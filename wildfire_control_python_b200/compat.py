@@ -160,7 +160,12 @@ class ForestFire:
 
     def __init__(self, batch: BatchedForestFire = None, index: int = 0, **metadata):
         self._batch = batch if batch is not None else BatchedForestFire(1, **metadata)
-        self._i = index
+        if self._batch.n_envs != 1 or index != 0:
+            # step() acts on the whole batch: a no-op action still ages the other envs (t, the shared a_speed_iter, the
+            # fire tick, auto-reset), so a view into a larger batch would change its neighbours' trajectories.
+            raise ValueError("ForestFire is a single-env facade: pass a BatchedForestFire with n_envs == 1 "
+                             "(step whole batches through BatchedForestFire itself)")
+        self._i = 0
         self.METADATA = self._batch.METADATA
         self.DEBUG = self.METADATA.get("debug", 1)
         self.layer = layer

@@ -36,6 +36,22 @@ static int fail(int code, const std::string& msg) {
             return fail(WF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
     } while (0)
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+#define WF_ON_DEVICE(e)               \
+    DeviceGuard _guard((e)->device);  \
+    WF_CUDA(_guard.err)
+
 struct wf_env {
     wf_config cfg;
     int32_t N, device;
@@ -52,8 +68,15 @@ struct wf_env {
     MlpPolicy mlp;       // device pointers into mlp_dev (hid == 0: not set)
     // wf_step_host staging
     cudaStream_t hstream;
+    // wf_step_host runs on its own stream: it is ordered behind everything the caller queued through the *_dev entry
+    // points (reset, set_state, set_fire_to, step ...) by an event recorded on the stream of the last such call.
+    cudaStream_t dev_stream;
+    bool dev_pending;
+    cudaEvent_t dev_event;
     bool host_direct, host_obs_direct;
     int32_t* h_actions;
+    uint8_t* h_mask;   // wf_reset_host staging
+    wf_init* h_init;
     void* h_obs;
     size_t h_obs_bytes;
     double* h_reward;
@@ -178,6 +201,7 @@ __global__ void set_fire_kernel(DevState s, const int32_t* cells) {
     if (x < 0 || x >= s.W || y < 0 || y >= s.H) return;
     const int w = y >> 5;
     const uint32_t bit = 1u << (y & 31);
+    const bool was_burning = (s.planes[word_index(s, P_B, env, x, w)] & bit) != 0u;  // burning_cells is a set
     s.planes[word_index(s, P_G, env, x, w)] &= ~bit;
     s.planes[word_index(s, P_BT, env, x, w)] &= ~bit;
     s.planes[word_index(s, P_D, env, x, w)] &= ~bit;
@@ -186,7 +210,7 @@ __global__ void set_fire_kernel(DevState s, const int32_t* cells) {
     s.planes[word_index(s, P_B, env, x, w)] |= bit;
     int32_t* sc = s.scal + (size_t)env * WF_NSCALARS;
     if (x == 0 || x == s.W - 1 || y == 0 || y == s.H - 1) sc[WF_S_FIRE_AT_BORDER] = 1;
-    sc[WF_S_N_BURNING] += 1;
+    if (!was_burning) sc[WF_S_N_BURNING] += 1;
 }
 
 // World.get_state() without stepping, generic layout (used by wf_get_obs).
@@ -292,7 +316,8 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(WF_ERR_CUDA, "no CUDA device: libwildfire_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(WF_ERR_INVALID, "bad device index");
-    WF_CUDA(cudaSetDevice(device));
+    DeviceGuard _guard(device);
+    WF_CUDA(_guard.err);
 
     wf_env* e = new (std::nothrow) wf_env();
     if (!e) return fail(WF_ERR_INVALID, "out of host memory");
@@ -365,12 +390,13 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
 
 void wf_destroy(wf_env* e) {
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceGuard _guard(e->device);
     if (e->tstate) tile_destroy(e->tstate);
     cudaFree(e->st.planes); cudaFree(e->st.fuel); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
     cudaFree(e->wind_dev);
     cudaFree(e->mlp_dev);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
+    cudaFree(e->h_mask); cudaFree(e->h_init);
     if (e->t_calls && getenv("WF_HOST_TIMING"))
         fprintf(stderr, "wf_step_host (packed path), %lld calls: launch %.2f us, sync %.2f us, expand %.2f us per call\n",
                 (long long)e->t_calls, 1e6 * e->t_launch / e->t_calls, 1e6 * e->t_sync / e->t_calls, 1e6 * e->t_expand / e->t_calls);
@@ -379,11 +405,18 @@ void wf_destroy(wf_env* e) {
     cudaFree(e->d_packed);
     if (e->pool) hostpool_destroy(e->pool);
     if (e->hstream) cudaStreamDestroy(e->hstream);
+    if (e->dev_event) cudaEventDestroy(e->dev_event);
     delete e;
 }
 
 const char* wf_kernel_family(const wf_env* e) { return e ? (e->tile ? "tile" : "warp") : ""; }
 int64_t wf_launch_count(const wf_env* e) { return e ? e->launches : 0; }
+int wf_tile_geometry(const wf_env* e, int32_t* threads, int32_t* cluster) {
+    if (!e || !threads || !cluster) return fail(WF_ERR_INVALID, "null argument");
+    *threads = *cluster = 0;
+    if (e->tstate) tile_geometry(e->tstate, threads, cluster);
+    return WF_OK;
+}
 int wf_host_threads(const wf_env* e) { return (e && e->pool) ? hostpool_threads(e->pool) : 0; }
 
 int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t n_envs, int32_t width, int32_t height,
@@ -403,6 +436,13 @@ int64_t wf_state_bytes_per_env(const wf_env* e) {
     return (int64_t)(s.NP + (s.fuel ? kFuelRec : 0)) * s.RS * s.HW * 4 + (s.HB ? 0 : (int64_t)s.W * s.H * 4) + WF_NSCALARS * 4;
 }
 
+// A *_dev entry point queued work on `st`: the next wf_step_host must wait for it (see wf_env::dev_stream).
+static void note_dev_call(wf_env* e, cudaStream_t st) {
+    if (st == e->hstream && e->hstream) return;  // wf_step_host's own launches
+    e->dev_stream = st;
+    e->dev_pending = true;
+}
+
 static int check_obs(const void* obs, int32_t dtype) {
     if (dtype != WF_OBS_U8 && dtype != WF_OBS_F32 && dtype != WF_OBS_BF16 && dtype != kObsPacked)
         return fail(WF_ERR_INVALID, "obs_dtype must be WF_OBS_U8, WF_OBS_F32 or WF_OBS_BF16");
@@ -416,8 +456,9 @@ int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* 
              void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    note_dev_call(e, st);
     if (e->tile) {
         TileIO io{nullptr, obs_dev, nullptr, nullptr, mask_dev, init_dev, obs_dtype, 0, e->a_iter, 1, 0, nullptr};
         WF_CUDA(launch_tile_family(e->tstate, e->st, e->sc, io, st, &e->launches));
@@ -450,8 +491,9 @@ static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, 
         if (e->mlp.hid == 0) return fail(WF_ERR_STATE, "WF_POLICY_MLP: call wf_set_policy_mlp first");
     }
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    note_dev_call(e, st);
     if (e->tile) {  // one thread-block cluster per env runs all K steps in one launch
         TileIO io{actions_dev, obs_dev, reward_dev, done_dev, nullptr, nullptr, obs_dtype, k_steps, e->a_iter, 0, policy,
                   actions_out};
@@ -483,7 +525,7 @@ int wf_set_policy_mlp(wf_env* e, const float* k1, const float* b1, const float* 
     if (hidden < 1 || hidden > 64) return fail(WF_ERR_INVALID, "hidden must be in 1..64");
     if (e->cfg.n_actions > 8) return fail(WF_ERR_INVALID, "WF_POLICY_MLP supports at most 8 actions");
     if (!(eps >= 0.0 && eps <= 1.0)) return fail(WF_ERR_INVALID, "eps must be in [0, 1]");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     const DevState& s = e->st;
     const int n_in = s.W * s.H * 3, A = e->cfg.n_actions;
     const size_t n_w1 = (size_t)n_in * hidden, total = n_w1 + hidden + (size_t)hidden * A + A;
@@ -530,13 +572,9 @@ static void* mapped_alias(const void* host_ptr) {
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
-int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
-                 uint8_t* done_host) {
-    if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
-    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32 && obs_dtype != WF_OBS_BF16) return fail(WF_ERR_INVALID, "bad obs_dtype");
-    WF_CUDA(cudaSetDevice(e->device));
-    const DevState& s = e->st;
-    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
+// Common start of the host-buffer entry points: the handle's private stream (first call: also the WF_HOST_* switches)
+// and its ordering behind the caller's earlier *_dev work.
+static int host_prologue(wf_env* e) {
     if (!e->hstream) {
         WF_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
         // WF_HOST_MODE: "hybrid" (default) = actions/reward/done zero-copy, obs staged + one DMA copy;
@@ -552,6 +590,60 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         const char* hg = getenv("WF_HOST_GRAPH");
         e->host_graph = hg && hg[0] == '1' && e->cfg.a_speed == 1;
     }
+    if (e->dev_pending) {  // order this call behind the caller's earlier *_dev work on its own stream
+        if (!e->dev_event) WF_CUDA(cudaEventCreateWithFlags(&e->dev_event, cudaEventDisableTiming));
+        WF_CUDA(cudaEventRecord(e->dev_event, e->dev_stream));
+        WF_CUDA(cudaStreamWaitEvent(e->hstream, e->dev_event, 0));
+        e->dev_pending = false;
+    }
+    return WF_OK;
+}
+
+static int ensure_obs_staging(wf_env* e, size_t obs_bytes) {
+    if (e->h_obs_bytes < obs_bytes) {
+        cudaFree(e->h_obs);
+        e->h_obs = nullptr;
+        e->h_obs_bytes = 0;
+        WF_CUDA(cudaMalloc(&e->h_obs, obs_bytes));
+        e->h_obs_bytes = obs_bytes;
+    }
+    return WF_OK;
+}
+
+// ForestFire.reset() for a caller that only has host memory.
+int wf_reset_host(wf_env* e, const uint8_t* mask_host, const wf_init* init_host, void* obs_host, int32_t obs_dtype) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32 && obs_dtype != WF_OBS_BF16) return fail(WF_ERR_INVALID, "bad obs_dtype");
+    WF_ON_DEVICE(e);
+    const DevState& s = e->st;
+    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
+    if (int rc = host_prologue(e)) return rc;
+    if ((mask_host || init_host) && !e->h_mask) {
+        WF_CUDA(cudaMalloc(&e->h_mask, (size_t)s.N));
+        WF_CUDA(cudaMalloc(&e->h_init, (size_t)s.N * sizeof(wf_init)));
+    }
+    if (mask_host) WF_CUDA(cudaMemcpyAsync(e->h_mask, mask_host, (size_t)s.N, cudaMemcpyHostToDevice, e->hstream));
+    if (init_host) WF_CUDA(cudaMemcpyAsync(e->h_init, init_host, (size_t)s.N * sizeof(wf_init), cudaMemcpyHostToDevice, e->hstream));
+    if (obs_host) {
+        if (int rc = ensure_obs_staging(e, obs_bytes)) return rc;
+    }
+    if (int rc = wf_reset(e, mask_host ? e->h_mask : nullptr, init_host ? e->h_init : nullptr, obs_host ? e->h_obs : nullptr,
+                          obs_dtype, e->hstream))
+        return rc;
+    if (obs_host) WF_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, obs_bytes, cudaMemcpyDeviceToHost, e->hstream));
+    WF_CUDA(cudaStreamSynchronize(e->hstream));
+    return WF_OK;
+}
+
+int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
+                 uint8_t* done_host) {
+    if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
+    if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32 && obs_dtype != WF_OBS_BF16) return fail(WF_ERR_INVALID, "bad obs_dtype");
+    WF_ON_DEVICE(e);
+    const DevState& s = e->st;
+    const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
+    if (int rc = host_prologue(e)) return rc;
+
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
     // obs/reward/done stores stream over PCIe while the step is still computing and there is no
     // separate copy to launch.  Pageable buffers fall back to staged cudaMemcpyAsync.
@@ -638,12 +730,7 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
             if (obs_direct) {
                 obs_target = o_d;
             } else {
-                if (e->h_obs_bytes < obs_bytes) {
-                    cudaFree(e->h_obs);
-                    e->h_obs = nullptr;
-                    WF_CUDA(cudaMalloc(&e->h_obs, obs_bytes));
-                    e->h_obs_bytes = obs_bytes;
-                }
+                if (int rc = ensure_obs_staging(e, obs_bytes)) return rc;
                 obs_target = e->h_obs;
             }
         }
@@ -660,11 +747,8 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         WF_CUDA(cudaMalloc(&e->h_reward, (size_t)s.N * sizeof(double)));
         WF_CUDA(cudaMalloc(&e->h_done, (size_t)s.N));
     }
-    if (obs_host && e->h_obs_bytes < obs_bytes) {
-        cudaFree(e->h_obs);
-        e->h_obs = nullptr;
-        WF_CUDA(cudaMalloc(&e->h_obs, obs_bytes));
-        e->h_obs_bytes = obs_bytes;
+    if (obs_host) {
+        if (int rc = ensure_obs_staging(e, obs_bytes)) return rc;
     }
     WF_CUDA(cudaMemcpyAsync(e->h_actions, actions_host, (size_t)s.N * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
     int rc = wf_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, obs_dtype, e->h_reward, e->h_done, e->hstream);
@@ -681,10 +765,11 @@ static int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 14
 int wf_get_state(wf_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, uint8_t* fuel, uint8_t* hits,
                  uint8_t* apos, int32_t* scalars, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevState& s = e->st;
     if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
+    note_dev_call(e, st);
     if (type || burning || fm_inf || fuel || hits || apos) {
         get_state_kernel<<<grid_for((size_t)s.N * s.W * s.H), 256, 0, st>>>(s, type, burning, fm_inf, fuel, hits, apos);
         WF_CUDA(cudaGetLastError());
@@ -698,10 +783,11 @@ int wf_get_state(wf_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, ui
 int wf_set_state(wf_env* e, const uint8_t* type, const uint8_t* burning, const uint8_t* fm_inf, const uint8_t* fuel,
                  const uint8_t* hits, const int32_t* scalars, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevState& s = e->st;
     if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
+    note_dev_call(e, st);
     if (type || burning || fm_inf || fuel || hits) {
         set_state_kernel<<<grid_for((size_t)s.N * s.W * s.HW), 256, 0, st>>>(s, type, burning, fm_inf, fuel, hits);
         WF_CUDA(cudaGetLastError());
@@ -716,10 +802,24 @@ int wf_set_state(wf_env* e, const uint8_t* type, const uint8_t* burning, const u
     return WF_OK;
 }
 
+int wf_get_a_iter(const wf_env* e, int32_t* out) {
+    if (!e || !out) return fail(WF_ERR_INVALID, "null argument");
+    *out = e->a_iter;
+    return WF_OK;
+}
+
+int wf_set_a_iter(wf_env* e, int32_t a_iter) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    if (a_iter < 1 || a_iter > e->cfg.a_speed) return fail(WF_ERR_INVALID, "a_iter must be in 1..a_speed");
+    e->a_iter = a_iter;
+    return WF_OK;
+}
+
 int wf_set_fire_to(wf_env* e, const int32_t* cells_dev, void* stream) {
     if (!e || !cells_dev) return fail(WF_ERR_INVALID, "null argument");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    note_dev_call(e, st);
     set_fire_kernel<<<(e->N + 127) / 128, 128, 0, st>>>(e->st, cells_dev);
     WF_CUDA(cudaGetLastError());
     e->launches += 1;
@@ -730,8 +830,9 @@ int wf_set_fire_to(wf_env* e, const int32_t* cells_dev, void* stream) {
 int wf_get_obs(wf_env* e, void* obs_dev, int32_t obs_dtype, void* stream) {
     if (!e || !obs_dev) return fail(WF_ERR_INVALID, "null argument");
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     const DevState& s = e->st;
+    note_dev_call(e, static_cast<cudaStream_t>(stream));
     get_obs_kernel<<<grid_for((size_t)s.N * s.W * s.H), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, obs_dev, obs_dtype);
     WF_CUDA(cudaGetLastError());
     e->launches += 1;
@@ -751,7 +852,8 @@ int wf_get_wind_table(const wf_env* e, double* coef_host, double* speed_host, in
 
 int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_host[4]) {
     if (!ctr_key_host || !out_host) return fail(WF_ERR_INVALID, "null argument");
-    WF_CUDA(cudaSetDevice(device));
+    DeviceGuard _guard(device);
+    WF_CUDA(_guard.err);
     uint32_t* buf = nullptr;
     WF_CUDA(cudaMalloc(&buf, 10 * sizeof(uint32_t)));
     WF_CUDA(cudaMemcpy(buf, ctr_key_host, 6 * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -764,7 +866,7 @@ int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_h
 
 int wf_stats(wf_env* e, int64_t out_host[8], void* stream) {
     if (!e || !out_host) return fail(WF_ERR_INVALID, "null argument");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     WF_CUDA(cudaMemcpyAsync(out_host, e->st.stats, ST_N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     WF_CUDA(cudaStreamSynchronize(st));
@@ -773,7 +875,7 @@ int wf_stats(wf_env* e, int64_t out_host[8], void* stream) {
 
 int wf_stats_reset(wf_env* e, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
-    WF_CUDA(cudaSetDevice(e->device));
+    WF_ON_DEVICE(e);
     WF_CUDA(cudaMemsetAsync(e->st.stats, 0, ST_N * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
     return WF_OK;
 }

@@ -44,6 +44,7 @@ struct TileState;
 int tile_extra_planes();
 cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg& c);
 void tile_destroy(TileState* t);
+void tile_geometry(const TileState* t, int32_t* threads, int32_t* cluster);
 cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c, const TileIO& io,
                                cudaStream_t stream, int64_t* launches);
 cudaError_t tile_after_set_state(TileState* t, const DevState& s, const StepCfg& c, cudaStream_t stream,

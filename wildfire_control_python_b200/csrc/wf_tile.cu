@@ -1134,6 +1134,7 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                     sc[WF_S_T] += 1;
                     const bool is_done = !sc[WF_S_RUNNING];
                     ss.stat[ST_STEPS] += 1u;
+                    if (do_tick) ss.stat[ST_TICKS] += 1u;
                     if (is_done) {
                         ss.stat[ST_EPISODES] += 1u;
                         if (sc[WF_S_ALIVE]) ss.stat[ST_BURNOUTS] += 1u;
@@ -1257,20 +1258,28 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     t->P_S1 = P_FU0 + 1;
     t->P_R = P_FU0 + 2;
     choose_geometry(s, t->T, t->CS);
-    cudaError_t e;
-    if ((e = set_smem_attr<5, 1, false>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<5, 4, false>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<8, 1, false>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<8, 4, false>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<5, 1, true>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<5, 4, true>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<8, 1, true>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<8, 4, true>()) != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = set_smem_attr<5, 1, false>();
+    if (e == cudaSuccess) e = set_smem_attr<5, 4, false>();
+    if (e == cudaSuccess) e = set_smem_attr<8, 1, false>();
+    if (e == cudaSuccess) e = set_smem_attr<8, 4, false>();
+    if (e == cudaSuccess) e = set_smem_attr<5, 1, true>();
+    if (e == cudaSuccess) e = set_smem_attr<5, 4, true>();
+    if (e == cudaSuccess) e = set_smem_attr<8, 1, true>();
+    if (e == cudaSuccess) e = set_smem_attr<8, 4, true>();
+    if (e != cudaSuccess) {
+        delete t;
+        return e;
+    }
     *out = t;
     return cudaSuccess;
 }
 
 void tile_destroy(TileState* t) { delete t; }
+void tile_geometry(const TileState* t, int32_t* threads, int32_t* cluster) {
+    *threads = t->T;
+    *cluster = t->CS;
+}
 
 static TilePar make_par(const TileState* t, const DevState& s, int obs_dtype) {
     TilePar p;

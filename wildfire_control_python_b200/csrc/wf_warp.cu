@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
     if (!valid_env) { a.running = 0; a.alive = 0; a.ax = a.ay = 0; a.wid = 0; }
     a.refresh_wind(s.wind);
 
-    long long n_steps_done = 0;
+    long long n_steps_done = 0, n_ticks_done = 0;
 
     // WF_POLICY_MLP: hidden pre-activations of units j = x + L*i, and the observation they were computed from
     constexpr int HPL = kHidMax / L;
@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             if (act) {
                 a.t += 1u;
                 n_steps_done += 1;
+                n_ticks_done += do_tick ? 1 : 0;
                 if (done && x == 0) {
                     atomicAdd(&s.stats[ST_EPISODES], 1ull);
                     if (a.alive) atomicAdd(&s.stats[ST_BURNOUTS], 1ull);
@@ -660,6 +661,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             sp[2] = make_int4(a.latched, (int)a.episode, (int)a.t, a.wid);
             sp[3] = make_int4(s.wind->wx[a.wid], s.wind->wy[a.wid], a.nburn, 0);
             if (n_steps_done) atomicAdd(&s.stats[ST_STEPS], (unsigned long long)n_steps_done);
+            if (n_ticks_done) atomicAdd(&s.stats[ST_TICKS], (unsigned long long)n_ticks_done);
         }
     }
 }
