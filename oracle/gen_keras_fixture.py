@@ -44,4 +44,10 @@ for size, name in PICKS:
                                                              "contained_bonus", "death_penalty", "default_reward")}},
     }
 json.dump(kat, open(os.path.join(OUT, "kat.json"), "w"), indent=1)
+# bench.py --workload c3 rolls the 14-sized network out as its policy: the four arrays as a plain .npz (a benchmark INPUT,
+# kept outside tests/)
+w = read_keras_weights(os.path.join(OUT, PICKS[1][1]))
+os.makedirs(os.path.join(ROOT, "bench_inputs"), exist_ok=True)
+np.savez(os.path.join(ROOT, "bench_inputs", "c3_policy_sarsa9_14s.npz"), kernel1=w["dense_1/kernel:0"], bias1=w["dense_1/bias:0"],
+         kernel2=w["dense_2/kernel:0"], bias2=w["dense_2/bias:0"])
 print(json.dumps({k: v["log"] for k, v in kat.items()}, indent=1))

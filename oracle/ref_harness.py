@@ -29,9 +29,13 @@ import numpy as np
 
 from . import philox
 
-REF_ROOT = os.environ.get("WF_REFERENCE_ROOT", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BUILD = os.path.join(HERE, "_ref")
+REF_ROOT = os.environ.get("WF_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "Simulation", "forest_fire.py")):
+    # the GPU box: no reference tree, but `make -C oracle ref` (run by build() in the build container) left a snapshot of
+    # the unmodified Simulation/ package in the git-ignored oracle/_ref/, which travels with the working tree
+    REF_ROOT = REF_BUILD
 
 
 def reference_available() -> bool:
@@ -47,10 +51,10 @@ def build_ref() -> str:
 def _install_shims():
     """Make ``from pyastar import pyastar`` and ``from colour import Color`` resolvable."""
     so = os.path.join(REF_BUILD, "pyastar", "astar.so")
-    if not os.path.isfile(so):
+    if not os.path.isfile(so) or not os.path.isfile(os.path.join(REF_BUILD, "pyastar", "pyastar.py")):
         build_ref()
-    # oracle/_ref/pyastar/pyastar.py is a SYMLINK to the reference's own binding;
-    # it looks for astar.so beside its (unresolved) path, i.e. in oracle/_ref/pyastar.
+    # oracle/_ref/pyastar/pyastar.py is the reference's own binding (copied there by `make ref`);
+    # it looks for astar.so beside its own path, i.e. in oracle/_ref/pyastar.
     if REF_BUILD not in sys.path:
         sys.path.insert(0, REF_BUILD)
     if "colour" not in sys.modules:
@@ -70,7 +74,7 @@ def load_reference():
     """Import the reference's Simulation package (from REF_ROOT) and return its modules."""
     _install_shims()
     if REF_ROOT not in sys.path:
-        sys.path.insert(sys.path.index(REF_BUILD) + 1, REF_ROOT)  # after oracle/_ref
+        sys.path.insert(sys.path.index(REF_BUILD) + 1, REF_ROOT)  # after oracle/_ref (the reference's pyastar has no astar.so)
     import Simulation.constants as constants  # noqa: E402
     import Simulation.utility as utility  # noqa: E402
     import Simulation.environment as environment  # noqa: E402
