@@ -189,3 +189,82 @@ def test_calls_leave_the_current_device_alone():
     env.step(torch.zeros(8, dtype=torch.int32, device="cuda:1"))
     env.step_host(np.zeros(8, np.int32))
     assert torch.cuda.current_device() == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# wf_host_session: the step kernel as a resident server driven through mapped host memory
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n_envs", [(dict(width=14, height=14, seed=601), 601), (dict(width=10, height=10, seed=602), 7),
+                                        (dict(width=20, height=20, seed=603), 530), (dict(width=17, height=13, seed=604, wind="random", make_rivers=True), 45),
+                                        (dict(width=32, height=32, seed=605, a_speed=2, allow_dig_toggle=True, n_actions=5), 19),
+                                        (dict(width=14, height=14, seed=606, fuel=40, extra_ignitions=2), 64)],
+                         ids=["14_n601", "10_n7", "20_n530", "17x13_rivers_windrandom", "32_aspeed2_toggle", "14_fuel40"])
+def test_host_session_matches_oracle(monkeypatch, cfg, n_envs):
+    """Every action / reward / done / observation of a session against the oracle, with auto-reset inside the resident
+    kernel, and with the session interrupted by other entry points (which park the kernel) and by idle periods (after
+    which it parks itself)."""
+    import time
+    monkeypatch.setenv("WF_HOST_THREADS", "5")
+    monkeypatch.setenv("WF_SESSION_IDLE_US", "300")
+    gpu, orc = make_pair(n_envs, cfg, auto_reset=True)
+    gpu.reset()
+    for e in orc:
+        e.reset()
+    assert gpu.host_session(True) and gpu.host_session_state == 1
+    for s in range(150):
+        acts = np.array([e.random_action() for e in orc], np.int32)
+        obs, rew, done, _ = gpu.step_host(acts)
+        assert gpu.host_session_state == 2
+        for i, e in enumerate(orc):
+            o, r, d, _ = e.step(int(acts[i]))
+            if d:
+                o = e.reset()
+            assert rew[i] == r and bool(done[i]) == d, (s, i, rew[i], r)
+            assert np.array_equal(obs[i], o), (s, i)
+        if s == 40:
+            time.sleep(0.02)  # longer than the idle limit: the kernel parks itself, the next step starts it again
+        if s == 70:
+            compare_states("mid-session", gpu, orc)  # wf_get_state parks the kernel; state is whole in HBM
+            assert gpu.host_session_state == 1
+        if s == 100:  # a device-side step in between (parks, steps, and the session resumes behind it)
+            acts = [e.random_action() for e in orc]
+            o_g, r_g, d_g, _ = gpu.step(torch.tensor(acts, dtype=torch.int32, device="cuda"))
+            o_g, r_g, d_g = to_np(o_g), to_np(r_g), to_np(d_g)
+            for i, e in enumerate(orc):
+                o, r, d, _ = e.step(acts[i])
+                if d:
+                    o = e.reset()
+                assert r_g[i] == r and bool(d_g[i]) == d and np.array_equal(o_g[i], o), i
+    assert gpu.host_threads == 5
+    st = gpu.stats()
+    assert st["env_steps"] == 151 * n_envs
+    assert gpu.host_session(False) is False and gpu.host_session_state == 0
+    compare_states("after the session", gpu, orc, obs=gpu.observe())
+
+
+@pytest.mark.gpu
+def test_host_session_pageable_buffers_and_plain_path_agree():
+    """The session needs no page-locked caller buffers, and gives exactly what the launch-per-step path gives."""
+    from wildfire_control_python_b200 import _lib
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    N, cfg = 300, dict(width=14, height=14, seed=611, auto_reset=True)
+    a, b = BatchedForestFire(N, **cfg), BatchedForestFire(N, **cfg)
+    a.reset(); b.reset()
+    L = _lib.lib()
+    assert L.wf_host_session(a._h, 1) == 0
+    obs = np.zeros((N, 14, 14, 3), np.uint8); rew = np.zeros(N); done = np.zeros(N, np.uint8)  # pageable
+    rng = np.random.default_rng(1)
+    for s in range(60):
+        acts = rng.integers(0, 4, N, dtype=np.int32)
+        assert L.wf_step_host(a._h, acts.ctypes.data, obs.ctypes.data, 0, rew.ctypes.data, done.ctypes.data) == 0
+        o2, r2, d2, _ = b.step_host(acts)
+        assert np.array_equal(obs, o2) and np.array_equal(rew, r2) and np.array_equal(done.astype(bool), d2), s
+
+
+@pytest.mark.gpu
+def test_host_session_is_refused_for_the_tile_family():
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    env = BatchedForestFire(4, width=48, height=48)
+    env.reset()
+    assert env.host_session(True) is False and env.host_session_state == 0
+    env.step_host(np.zeros(4, np.int32))  # the launch-per-step path still serves it

@@ -232,6 +232,22 @@ class BatchedForestFire:
             _lib.check(rc)
         return hb["np_obs"], hb["np_reward"], hb["np_done"], {}
 
+    def host_session(self, on: bool = True) -> bool:
+        """Turn the step-server session of ``step_host`` on / off (``wf_host_session``, include/wildfire.h): the step
+        kernel stays resident and is driven through mapped host memory -- no launch, copy call or synchronise per
+        step.  Returns whether a session is on afterwards (False for grids larger than 32x32: not supported there)."""
+        L = _lib.lib()
+        rc = L.wf_host_session(self._h, 1 if on else 0)
+        if rc == _lib.WF_ERR_INVALID and on:
+            return False
+        _lib.check(rc)
+        return bool(L.wf_host_session_active(self._h))
+
+    @property
+    def host_session_state(self) -> int:
+        """0: no session, 1: session on with the kernel parked, 2: step-server kernel resident."""
+        return int(_lib.lib().wf_host_session_active(self._h))
+
     def observe(self) -> torch.Tensor:
         """``World.get_state()`` (environment.py:399-402) without stepping."""
         with torch.cuda.device(self.device):

@@ -1,6 +1,7 @@
 // wf_api.cu -- the C ABI of libwildfire_b200.so (include/wildfire.h): handle lifetime, argument
 // checks, wind table, state import/export kernels and dispatch to the two kernel families.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,10 @@ void hostpool_destroy(HostPool* p);
 int hostpool_threads(const HostPool* p);
 void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words, int64_t env_bits,
                      int64_t envs_per_record, int64_t n_envs);
+bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
+                             int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
+                             uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns);
 int hostpool_default_threads();
 }  // namespace wf
 
@@ -99,7 +104,23 @@ struct wf_env {
     bool host_graph;
     cudaGraphExec_t hg_exec;
     const void* hg_key[3];
+    // wf_host_session: the warp kernel as a resident step server driven through mapped page-locked memory
+    struct Session {
+        bool wanted, running;
+        uint32_t seq, generation;   // last sequence number rung; id of the current / last launch
+        uint32_t* ctl;              // mapped host: doorbell @0, parked @16 (words), done flags @32 + 16 * slice
+        uint32_t* ctl_dev;
+        int32_t* actions;           // mapped host [N]
+        int32_t* actions_dev;
+        uint32_t* rec;              // mapped host [records][rec_words + 1]
+        uint32_t* rec_dev;
+        uint32_t* sync_dev;         // device: go @0, arrival counters @16 + slice
+        int slices, ctas_per_slice;
+        int64_t launches, steps, relaunch_races;
+    } sess;
 };
+constexpr int kSessMaxSlices = 64;
+static int session_park(wf_env* e);
 
 // ---------------------------------------------------------------------------------------------
 // canonical-plane export / import (parity injection, checkpoint) -- works for both layouts
@@ -391,6 +412,14 @@ int wf_create(const wf_config* cfg, int32_t n_envs, int32_t device, wf_env** out
 void wf_destroy(wf_env* e) {
     if (!e) return;
     DeviceGuard _guard(e->device);
+    session_park(e);
+    if (e->sess.ctl) cudaFreeHost(e->sess.ctl);
+    if (e->sess.actions) cudaFreeHost(e->sess.actions);
+    if (e->sess.rec) cudaFreeHost(e->sess.rec);
+    cudaFree(e->sess.sync_dev);
+    if (e->sess.steps && getenv("WF_HOST_TIMING"))
+        fprintf(stderr, "wf_host_session: %lld steps in %lld launches of the step server (%lld park/ring races)\n",
+                (long long)e->sess.steps, (long long)e->sess.launches, (long long)e->sess.relaunch_races);
     if (e->tstate) tile_destroy(e->tstate);
     cudaFree(e->st.planes); cudaFree(e->st.fuel); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
     cudaFree(e->wind_dev);
@@ -436,6 +465,20 @@ int64_t wf_state_bytes_per_env(const wf_env* e) {
     return (int64_t)(s.NP + (s.fuel ? kFuelRec : 0)) * s.RS * s.HW * 4 + (s.HB ? 0 : (int64_t)s.W * s.H * 4) + WF_NSCALARS * 4;
 }
 
+// Ask a running step server to park (it stores the envs back to HBM and exits) and wait for it.
+static int session_park(wf_env* e) {
+    if (!e->sess.running) return WF_OK;
+    *reinterpret_cast<volatile uint32_t*>(e->sess.ctl) = 0xffffffffu;  // doorbell: park
+    cudaError_t err = cudaStreamSynchronize(e->hstream);
+    e->sess.running = false;
+    if (err != cudaSuccess) return fail(WF_ERR_CUDA, std::string("step-server kernel: ") + cudaGetErrorString(err));
+    return WF_OK;
+}
+#define WF_QUIESCE(e)                            \
+    do {                                         \
+        if (int _rc = session_park(e)) return _rc; \
+    } while (0)
+
 // A *_dev entry point queued work on `st`: the next wf_step_host must wait for it (see wf_env::dev_stream).
 static void note_dev_call(wf_env* e, cudaStream_t st) {
     if (st == e->hstream && e->hstream) return;  // wf_step_host's own launches
@@ -457,6 +500,7 @@ int wf_reset(wf_env* e, const uint8_t* mask_dev, const wf_init* init_dev, void* 
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     note_dev_call(e, st);
     if (e->tile) {
@@ -492,6 +536,7 @@ static int rollout_impl(wf_env* e, int32_t k_steps, const int32_t* actions_dev, 
     }
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     note_dev_call(e, st);
     if (e->tile) {  // one thread-block cluster per env runs all K steps in one launch
@@ -526,6 +571,7 @@ int wf_set_policy_mlp(wf_env* e, const float* k1, const float* b1, const float* 
     if (e->cfg.n_actions > 8) return fail(WF_ERR_INVALID, "WF_POLICY_MLP supports at most 8 actions");
     if (!(eps >= 0.0 && eps <= 1.0)) return fail(WF_ERR_INVALID, "eps must be in [0, 1]");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     const DevState& s = e->st;
     const int n_in = s.W * s.H * 3, A = e->cfg.n_actions;
     const size_t n_w1 = (size_t)n_in * hidden, total = n_w1 + hidden + (size_t)hidden * A + A;
@@ -615,6 +661,7 @@ int wf_reset_host(wf_env* e, const uint8_t* mask_host, const wf_init* init_host,
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     if (obs_dtype != WF_OBS_U8 && obs_dtype != WF_OBS_F32 && obs_dtype != WF_OBS_BF16) return fail(WF_ERR_INVALID, "bad obs_dtype");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     const DevState& s = e->st;
     const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
     if (int rc = host_prologue(e)) return rc;
@@ -635,6 +682,121 @@ int wf_reset_host(wf_env* e, const uint8_t* mask_host, const wf_init* init_host,
     return WF_OK;
 }
 
+// ---- step-server session ------------------------------------------------------------------------
+static int session_launch(wf_env* e) {
+    wf_env::Session& ss = e->sess;
+    const DevState& s = e->st;
+    ss.generation += 1u;
+    WF_CUDA(cudaMemsetAsync(ss.sync_dev, 0, (16 + kSessMaxSlices) * sizeof(uint32_t), e->hstream));
+    WarpIO io{ss.actions_dev, ss.rec_dev, nullptr, nullptr, nullptr, nullptr, kObsPackedStatus, 1, e->a_iter, 0,
+              magic_for(s.H), WF_POLICY_STREAM, nullptr, MlpPolicy{}, SrvCtl{}};
+    io.srv.doorbell = ss.ctl_dev;
+    io.srv.parked = ss.ctl_dev + 16;
+    io.srv.done = ss.ctl_dev + 32;
+    io.srv.go = ss.sync_dev;
+    io.srv.count = ss.sync_dev + 16;
+    io.srv.seq0 = ss.seq;
+    io.srv.generation = ss.generation;
+    io.srv.ctas_per_slice = ss.ctas_per_slice;
+    const char* idle = getenv("WF_SESSION_IDLE_US");
+    io.srv.idle_ns = 1000ull * (unsigned long long)((idle && atoll(idle) > 0) ? atoll(idle) : 2000);
+    WF_CUDA(launch_warp_server(s, e->sc, io, e->hstream));
+    e->launches += 1;
+    ss.launches += 1;
+    ss.running = true;
+    return WF_OK;
+}
+
+static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, double* reward_host, uint8_t* done_host) {
+    wf_env::Session& ss = e->sess;
+    const DevState& s = e->st;
+    const int epw = 32 / s.RS;
+    const int64_t env_bits = (int64_t)s.W * s.H * 3, records = (s.N + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
+    volatile uint32_t* ctl = ss.ctl;
+    if (ss.seq >= 0xfffffff0u) {  // sequence numbers wrap: park and start over from 0
+        WF_QUIESCE(e);
+        ss.seq = 0u;
+    }
+    if (ss.running && ctl[16] == ss.generation) {  // the kernel parked itself (no doorbell for idle_ns)
+        WF_CUDA(cudaStreamSynchronize(e->hstream));
+        ss.running = false;
+    }
+    if (!ss.running) {
+        if (int rc = host_prologue(e)) return rc;  // behind the caller's earlier *_dev work
+        if (!ss.ctl) {
+            if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
+            constexpr int kRecordsPerCta = 4;  // WF_WARPS_PER_BLOCK warps, one record each
+            const int64_t ctas = (records + kRecordsPerCta - 1) / kRecordsPerCta;
+            int slices = std::min<int64_t>(std::min(hostpool_threads(e->pool), kSessMaxSlices), ctas);
+            ss.ctas_per_slice = (int)((ctas + slices - 1) / slices);
+            ss.slices = (int)((ctas + ss.ctas_per_slice - 1) / ss.ctas_per_slice);
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));
+            std::memset(ss.ctl, 0, (32 + 16 * kSessMaxSlices) * sizeof(uint32_t));
+            WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.ctl_dev), ss.ctl, 0));
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.actions), (size_t)s.N * sizeof(int32_t), cudaHostAllocMapped));
+            WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.actions_dev), ss.actions, 0));
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)records * (rec_words + 1) * sizeof(uint32_t), cudaHostAllocMapped));
+            WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
+            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
+        }
+        ctl[0] = ss.seq;  // doorbell: nothing requested yet
+        if (int rc = session_launch(e)) {
+            ss.wanted = false;  // e.g. the batch is too large for a cooperative launch: the launch-per-step path serves it
+            cudaGetLastError();
+            return wf_step_host(e, actions_host, obs_host, WF_OBS_U8, reward_host, done_host);
+        }
+    }
+    std::memcpy(ss.actions, actions_host, (size_t)s.N * sizeof(int32_t));
+    ss.seq += 1u;
+    std::atomic_thread_fence(std::memory_order_release);
+    ctl[0] = ss.seq;  // ring
+    e->a_iter = advance_a_iter(e, 1);
+    ss.steps += 1;
+    const int64_t rps = (int64_t)ss.ctas_per_slice * 4;
+    const auto t_start = std::chrono::steady_clock::now();
+    for (;;) {
+        const bool ok = hostpool_expand_session(e->pool, ss.rec, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw,
+                                                s.N, ss.ctl + 32, ss.seq, rps, reward_host, done_host, e->cfg.default_reward,
+                                                e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000);
+        if (ok) return WF_OK;
+        if (ctl[16] == ss.generation) {
+            // The kernel decided to park in the instant the doorbell was rung: it did not take this step.  Start it
+            // again behind the old launch; it finds the doorbell ahead of its seq0 and serves the step at once.
+            ss.relaunch_races += 1;
+            ss.seq -= 1u;  // seq0 of the new launch = the step before this one
+            int rc = session_launch(e);
+            ss.seq += 1u;
+            if (rc) return rc;
+            continue;
+        }
+        cudaError_t q = cudaStreamQuery(e->hstream);
+        if (q != cudaErrorNotReady) {  // the kernel is gone without having parked: a fault
+            ss.running = false;
+            return fail(WF_ERR_CUDA, std::string("step-server kernel ended unexpectedly: ") + cudaGetErrorString(q));
+        }
+        if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(20)) {
+            return fail(WF_ERR_CUDA, "step-server kernel did not answer within 20 s");
+        }
+    }
+}
+
+int wf_host_session(wf_env* e, int32_t on) {
+    if (!e) return fail(WF_ERR_INVALID, "null handle");
+    WF_ON_DEVICE(e);
+    if (on) {
+        if (e->tile) return fail(WF_ERR_INVALID, "wf_host_session: grids up to 32x32 (warp family) only");
+        int coop = 0;
+        WF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+        if (!coop) return fail(WF_ERR_INVALID, "wf_host_session: the device has no cooperative launch");
+        e->sess.wanted = true;
+        return WF_OK;
+    }
+    WF_QUIESCE(e);
+    e->sess.wanted = false;
+    return WF_OK;
+}
+int wf_host_session_active(const wf_env* e) { return e ? (e->sess.wanted ? (e->sess.running ? 2 : 1) : 0) : 0; }
+
 int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t obs_dtype, double* reward_host,
                  uint8_t* done_host) {
     if (!e || !actions_host) return fail(WF_ERR_INVALID, "null argument");
@@ -642,6 +804,8 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
     WF_ON_DEVICE(e);
     const DevState& s = e->st;
     const size_t obs_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
+    if (e->sess.wanted && !e->tile && obs_host && obs_dtype == WF_OBS_U8) return session_step(e, actions_host, obs_host, reward_host, done_host);
+    WF_QUIESCE(e);
     if (int rc = host_prologue(e)) return rc;
 
     // Zero-copy path: page-locked host buffers are addressed by the kernels themselves, so the
@@ -766,6 +930,7 @@ int wf_get_state(wf_env* e, uint8_t* type, uint8_t* burning, uint8_t* fm_inf, ui
                  uint8_t* apos, int32_t* scalars, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevState& s = e->st;
     if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
@@ -784,6 +949,7 @@ int wf_set_state(wf_env* e, const uint8_t* type, const uint8_t* burning, const u
                  const uint8_t* hits, const int32_t* scalars, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevState& s = e->st;
     if (hits && (reinterpret_cast<uintptr_t>(hits) & 3u)) return fail(WF_ERR_INVALID, "hits must be 4-byte aligned");
@@ -818,6 +984,7 @@ int wf_set_a_iter(wf_env* e, int32_t a_iter) {
 int wf_set_fire_to(wf_env* e, const int32_t* cells_dev, void* stream) {
     if (!e || !cells_dev) return fail(WF_ERR_INVALID, "null argument");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     note_dev_call(e, st);
     set_fire_kernel<<<(e->N + 127) / 128, 128, 0, st>>>(e->st, cells_dev);
@@ -831,6 +998,7 @@ int wf_get_obs(wf_env* e, void* obs_dev, int32_t obs_dtype, void* stream) {
     if (!e || !obs_dev) return fail(WF_ERR_INVALID, "null argument");
     if (int rc = check_obs(obs_dev, obs_dtype)) return rc;
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     const DevState& s = e->st;
     note_dev_call(e, static_cast<cudaStream_t>(stream));
     get_obs_kernel<<<grid_for((size_t)s.N * s.W * s.H), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, obs_dev, obs_dtype);
@@ -867,6 +1035,7 @@ int wf_philox_kat(int32_t device, const uint32_t ctr_key_host[6], uint32_t out_h
 int wf_stats(wf_env* e, int64_t out_host[8], void* stream) {
     if (!e || !out_host) return fail(WF_ERR_INVALID, "null argument");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     WF_CUDA(cudaMemcpyAsync(out_host, e->st.stats, ST_N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     WF_CUDA(cudaStreamSynchronize(st));
@@ -876,6 +1045,7 @@ int wf_stats(wf_env* e, int64_t out_host[8], void* stream) {
 int wf_stats_reset(wf_env* e, void* stream) {
     if (!e) return fail(WF_ERR_INVALID, "null handle");
     WF_ON_DEVICE(e);
+    WF_QUIESCE(e);
     WF_CUDA(cudaMemsetAsync(e->st.stats, 0, ST_N * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
     return WF_OK;
 }

@@ -26,6 +26,10 @@ namespace wf {
 // Internal observation format of wf_step_host: the bit stream itself (1 bit per element), one record of
 // ceil(envs_per_warp * W*H*3 / 32) words per warp; expanded to bytes by the host thread pool (wf_hostpool.cpp).
 constexpr int kObsPacked = 100;
+// The step-server session's format: every record is followed by ONE status word, 16 bits per env of the record
+// (env sub-index 0 in the low half): bits 0-2 reward kind, bit 3 done, bits 4-14 grass-cell count of a burn-out reward.
+constexpr int kObsPackedStatus = 101;
+enum RewardKind : uint32_t { RK_ZERO = 0, RK_DEFAULT = 1, RK_DEATH = 2, RK_CONTAINED = 3, RK_BURNOUT = 4 };
 
 // Bytes per observation element of a public obs_dtype (WF_OBS_U8 / WF_OBS_F32 / WF_OBS_BF16).
 __host__ __device__ __forceinline__ int obs_elem_bytes(int dtype) { return dtype == WF_OBS_F32 ? 4 : dtype == WF_OBS_BF16 ? 2 : 1; }

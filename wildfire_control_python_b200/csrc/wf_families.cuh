@@ -14,6 +14,19 @@ struct MlpPolicy {
     uint32_t eps_u32;   // explore iff a 32-bit draw is below this
 };
 
+// Step-server session (wf_host_session): the warp kernel stays resident and is driven from the host through
+// flags in mapped page-locked memory -- no launch and no stream synchronise per step.
+struct SrvCtl {
+    volatile uint32_t* doorbell;  // mapped host, host -> GPU: sequence number of the step requested (0xffffffff: park)
+    volatile uint32_t* parked;    // mapped host, GPU -> host: the launch's generation, once the kernel has decided to exit
+    volatile uint32_t* done;      // mapped host, GPU -> host: [slices] flags 16 words apart = sequence number completed
+    uint32_t* go;                 // device: master CTA -> every CTA: index of the step to run (1, 2, ...), 0xffffffff = exit
+    uint32_t* count;              // device: [slices] arrival counters
+    uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
+    int32_t ctas_per_slice;
+    unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)
+};
+
 struct WarpIO {
     const int32_t* actions;  // [K][N] or nullptr (ACTION stream)
     void* obs;               // [K][N][W][H][3] or nullptr
@@ -26,8 +39,12 @@ struct WarpIO {
     int32_t policy;          // actions == nullptr: WF_POLICY_STREAM, WF_POLICY_WALK or WF_POLICY_MLP
     int32_t* actions_out;    // [K][N] or nullptr: the actions the policy chose
     MlpPolicy mlp;           // WF_POLICY_MLP only
+    SrvCtl srv;              // step-server launches only (launch_warp_server)
 };
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
+// The same kernel as a cooperative launch (every CTA resident) that serves steps until told to park; io.actions / io.obs
+// are mapped host buffers (obs_dtype kObsPackedStatus).  cudaErrorCooperativeLaunchTooLarge if the batch does not fit.
+cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 
 struct TileIO {
     const int32_t* actions;  // [K][N] or nullptr (ACTION stream / policy)

@@ -22,9 +22,18 @@
 namespace wf {
 
 struct ExpandJob {
-    const uint32_t* packed;  // [records][rec_words]
+    const uint32_t* packed;  // [records][rec_stride]: rec_words of observation bits (+ one status word in session mode)
     uint8_t* out;            // [n_envs][env_bits] bytes
     int64_t records, rec_words, env_bits, envs_per_record, n_envs;
+    int64_t rec_stride;      // words between records (rec_words, or rec_words + 1 with a status word)
+    // step-server session (wf_host_session): the records of slice t are complete once flags[16 * t] == seq
+    const volatile uint32_t* flags;
+    uint32_t seq;
+    int64_t records_per_slice;  // session: slice t = records [t * records_per_slice, ...); 0: split evenly over the threads
+    double* reward;             // session: decoded from the status word (may be null)
+    uint8_t* done;
+    double default_reward, death_penalty, contained_bonus, cells;
+    int64_t timeout_ns;         // session: give up waiting for a flag after this long (the caller then checks the kernel)
 };
 
 static uint64_t g_tab[256];
@@ -67,10 +76,42 @@ __attribute__((target("avx2"))) static void expand_avx2(const uint8_t* in, uint8
 }
 #endif
 
+#if defined(__x86_64__)
+// 8 input bytes -> 64 output bytes per iteration: the input IS the byte mask of a masked broadcast of 1.
+__attribute__((target("avx512f,avx512bw"))) static void expand_avx512(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+    const __m512i one = _mm512_set1_epi8(1);
+    int64_t i = 0;
+    for (; i + 8 <= nbytes; i += 8) {
+        uint64_t v;
+        std::memcpy(&v, in + i, 8);
+        _mm512_storeu_si512(reinterpret_cast<void*>(out + 8 * i), _mm512_maskz_mov_epi8(_cvtu64_mask64(v), one));
+    }
+    if (i < nbytes) {  // 1..7 input bytes left: one masked store
+        uint64_t v = 0;
+        std::memcpy(&v, in + i, (size_t)(nbytes - i));
+        const __mmask64 live = _cvtu64_mask64((~0ull) >> (64 - 8 * (nbytes - i)));
+        _mm512_mask_storeu_epi8(reinterpret_cast<void*>(out + 8 * i), live, _mm512_maskz_mov_epi8(_cvtu64_mask64(v), one));
+    }
+}
+#endif
+
+// Reward of one env from its status bits: the expressions of World.get_reward (environment.py:379-390) in the
+// reference's operation order; the burn-out fraction is the same IEEE division and multiplication the kernel does.
+static inline double decode_reward(const ExpandJob& j, uint32_t st) {
+    switch (st & 7u) {
+        case 1: return j.default_reward;
+        case 2: return j.death_penalty;
+        case 3: return j.contained_bonus;
+        case 4: return j.contained_bonus * ((double)((st >> 4) & 0x7ffu) / j.cells);
+        default: return 0.0;
+    }
+}
+
 static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
 #if defined(__x86_64__)
     static const bool bmi2 = __builtin_cpu_supports("bmi2");
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
+    static const bool avx512 = __builtin_cpu_supports("avx512bw") && !getenv("WF_HOST_NO_AVX512") && !getenv("WF_HOST_NO_AVX2");
 #else
     static const bool bmi2 = false;
 #endif
@@ -78,15 +119,24 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
         const int64_t env0 = r * j.envs_per_record;
         const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
         const int64_t bits = nenv * j.env_bits;
-        const uint8_t* in = reinterpret_cast<const uint8_t*>(j.packed + r * j.rec_words);
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(j.packed + r * j.rec_stride);
         uint8_t* out = j.out + env0 * j.env_bits;
 #if defined(__x86_64__)
-        if (avx2) expand_avx2(in, out, bits >> 3);
+        if (avx512) expand_avx512(in, out, bits >> 3);
+        else if (avx2) expand_avx2(in, out, bits >> 3);
         else if (bmi2) expand_pdep(in, out, bits >> 3);
         else
 #endif
             expand_table(in, out, bits >> 3);
         for (int64_t b = bits & ~(int64_t)7; b < bits; ++b) out[b] = (in[b >> 3] >> (b & 7)) & 1;  // ragged tail
+        if (j.rec_stride > j.rec_words) {  // session records: reward / done of the record's envs
+            const uint32_t st = j.packed[r * j.rec_stride + j.rec_words];
+            for (int64_t k = 0; k < nenv; ++k) {
+                const uint32_t sk = (st >> (16 * k)) & 0xffffu;
+                if (j.reward) j.reward[env0 + k] = decode_reward(j, sk);
+                if (j.done) j.done[env0 + k] = (uint8_t)((sk >> 3) & 1u);
+            }
+        }
     }
 }
 
@@ -106,8 +156,10 @@ public:
         for (auto& th : workers_) th.join();
     }
     int threads() const { return n_; }
-    void run(const ExpandJob& job) {
+    // Returns false if a session slice timed out waiting for its completion flag (nothing of that slice was expanded).
+    bool run(const ExpandJob& job) {
         job_ = job;
+        failed_.store(0, std::memory_order_relaxed);
         pending_.store(n_ - 1, std::memory_order_relaxed);
         {
             std::lock_guard<std::mutex> lk(m_);  // pairs with the sleepers' predicate check
@@ -116,6 +168,7 @@ public:
         if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         slice(0);
         while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+        return failed_.load(std::memory_order_acquire) == 0;
     }
 
 private:
@@ -127,9 +180,24 @@ private:
 #endif
     }
     void slice(int t) {
-        const int64_t per = (job_.records + n_ - 1) / n_;
+        const int64_t per = job_.records_per_slice > 0 ? job_.records_per_slice : (job_.records + n_ - 1) / n_;
         const int64_t r0 = per * t, r1 = (r0 + per < job_.records) ? r0 + per : job_.records;
-        if (r0 < r1) expand_records(job_, r0, r1);
+        if (r0 >= r1) return;
+        if (job_.flags) {  // session: the GPU raises this slice's flag once all of its records are in host memory
+            const volatile uint32_t* f = job_.flags + 16 * t;
+            const auto t0 = std::chrono::steady_clock::now();
+            int spins = 0;
+            while (*f != job_.seq) {
+                cpu_relax();
+                if ((++spins & 255) == 0 &&
+                    std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(job_.timeout_ns)) {
+                    failed_.store(1, std::memory_order_release);
+                    return;
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        expand_records(job_, r0, r1);
     }
     void loop(int t) {
         uint64_t seen = 0;
@@ -158,7 +226,7 @@ private:
     std::vector<std::thread> workers_;
     ExpandJob job_{};
     std::atomic<uint64_t> seq_{0};
-    std::atomic<int> pending_{0}, sleepers_{0};
+    std::atomic<int> pending_{0}, sleepers_{0}, failed_{0};
     std::mutex m_;
     std::condition_variable cv_;
     bool stop_ = false;
@@ -170,8 +238,24 @@ void hostpool_destroy(HostPool* p) { delete p; }
 int hostpool_threads(const HostPool* p) { return p ? p->threads() : 0; }
 void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words, int64_t env_bits,
                      int64_t envs_per_record, int64_t n_envs) {
-    ExpandJob j{packed, out, records, rec_words, env_bits, envs_per_record, n_envs};
+    ExpandJob j{};
+    j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
+    j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words;
     p->run(j);
+}
+// Session step: thread t waits for flags[16 * t] == seq, then expands records [t * records_per_slice, ...) and decodes
+// their status words into reward / done.  false: a flag did not come within timeout_ns.
+bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
+                             int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
+                             uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns) {
+    ExpandJob j{};
+    j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
+    j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words + 1;
+    j.flags = flags; j.seq = seq; j.records_per_slice = records_per_slice; j.reward = reward; j.done = done;
+    j.default_reward = default_reward; j.death_penalty = death_penalty; j.contained_bonus = contained_bonus; j.cells = cells;
+    j.timeout_ns = timeout_ns;
+    return p->run(j);
 }
 int hostpool_default_threads() {
     if (const char* v = getenv("WF_HOST_THREADS")) {

@@ -157,7 +157,7 @@ constexpr int kStreamWords = 100;  // 3*32*32/32 = 96 words + spill-over of the 
 template <int L>
 __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
                                          uint32_t* stream, const uint32_t* spread3, const uint2* tab8, int lane, int sub,
-                                         int x, int W, int H, int env0, int n_valid) {
+                                         int x, int W, int H, int env0, int n_valid, uint32_t status16 = 0u) {
     // obs_step: start of this step's [N][W][H][3] block; env0: first env of the warp; n_valid: how many
     // of the warp's envs exist.  The warp's envs are adjacent in memory, so they share ONE bit stream.
     const int nbits = W * H * 3;
@@ -188,10 +188,19 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
     }
     __syncwarp();
     if (n_valid <= 0) return;
-    if (dtype == kObsPacked) {  // the stream as it is: 8x fewer bytes over PCIe, expanded on the host
+    if (dtype == kObsPacked || dtype == kObsPackedStatus) {  // the stream as it is: 8x fewer bytes over PCIe, expanded on the host
         constexpr int EPW = 32 / L;
-        uint32_t* rec = static_cast<uint32_t*>(obs_step) + (size_t)(env0 / EPW) * ((EPW * nbits + 31) >> 5);
-        for (int w = lane; w < nw; w += 32) rec[w] = stream[w];
+        const int rec_words = (EPW * nbits + 31) >> 5;
+        if (dtype == kObsPackedStatus) {  // + one status word per record: reward kind / done / burn-out count of each env
+            uint32_t st = __shfl_sync(0xffffffffu, status16, 0);
+            if (EPW == 2) st |= __shfl_sync(0xffffffffu, status16, L & 31) << 16;
+            uint32_t* rec = static_cast<uint32_t*>(obs_step) + (size_t)(env0 / EPW) * (rec_words + 1);
+            for (int w = lane; w < nw; w += 32) rec[w] = stream[w];
+            if (lane == 0) rec[rec_words] = st;
+        } else {
+            uint32_t* rec = static_cast<uint32_t*>(obs_step) + (size_t)(env0 / EPW) * rec_words;
+            for (int w = lane; w < nw; w += 32) rec[w] = stream[w];
+        }
         return;
     }
     if (dtype == WF_OBS_U8) {
@@ -236,14 +245,33 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
 // (agent cell, dug cell, ignitions, burn-outs; everything after a reset).
 constexpr int kHidMax = 64, kActMax = 8;
 
-template <int L, int FB, bool UNI, bool MLP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, StepCfg c, WarpIO io) {
+// SRV: step-server session (wf_host_session).  The kernel stays resident; per step, thread 0 of CTA 0 waits for the
+// host's doorbell in mapped page-locked memory and releases the other CTAs through a flag in HBM; every warp reads its
+// actions from the mapped buffer, steps, stores its packed observation record (+ status word) straight into mapped host
+// memory; the last CTA of every slice of the grid to finish tells the host thread that expands that slice.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int L, int FB, bool UNI, bool MLP, bool SRV>
+__device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, const WarpIO& io) {
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
     __shared__ uint32_t stream_all[kWarpsPerBlock][kStreamWords];
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
+    __shared__ uint32_t srv_cmd;
     for (int v = threadIdx.x; v < 256; v += blockDim.x) {
         uint32_t o = 0u;
 #pragma unroll
@@ -314,11 +342,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
         // ---------------- K x ForestFire.step(action) ----------------
         int it = io.a_iter0;
         uint32_t ablk[4] = {0u, 0u, 0u, 0u}, ablk_ep = 0xffffffffu, ablk_idx = 0xffffffffu;  // cached ACTION block
-        for (int k = 0; k < io.K; ++k) {
+        uint32_t srv_step = 0u;  // SRV: steps served by this launch
+        for (int kk = 0; SRV || kk < io.K; ++kk) {
+            const int k = SRV ? 0 : kk;  // row of the output arrays
+            if (SRV) {
+                if (threadIdx.x == 0) {
+                    uint32_t go;
+                    if (blockIdx.x == 0) {
+                        const uint32_t last = io.srv.seq0 + srv_step;
+                        const unsigned long long t0 = global_timer_ns();
+                        uint32_t cmd;
+                        for (;;) {
+                            cmd = *io.srv.doorbell;
+                            if (cmd != last || global_timer_ns() - t0 > io.srv.idle_ns) break;
+                        }
+                        if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
+                            *io.srv.parked = io.srv.generation;
+                            go = 0xffffffffu;
+                        } else {
+                            go = srv_step + 1u;
+                        }
+                        st_release_gpu(io.srv.go, go);
+                    } else {
+                        do { go = ld_acquire_gpu(io.srv.go); } while (go == srv_step);
+                    }
+                    srv_cmd = go;
+                }
+                __syncthreads();
+                if (srv_cmd == 0xffffffffu) break;
+            }
             const bool act = valid_env && a.running;  // finished envs are frozen (reward 0, done 1)
             int action;
             if (io.actions != nullptr) {
-                action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
+                if (SRV) action = valid_env ? __ldcv(&io.actions[env]) : -1;  // mapped host memory, rewritten every step
+                else action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else if (MLP) {
                 const int hid = io.mlp.hid, A = io.mlp.n_actions;
                 // ---- first layer, incrementally: rows of the observation bits that changed since the last evaluation
@@ -593,17 +650,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                 contained = !group_bits(__ballot_sync(FULL, touch != 0u));
             }
             double rew = 0.0;
+            uint32_t rkind = RK_ZERO, rcnt = 0u;  // SRV: the reward as a code (the host evaluates the same expressions)
             if (act) {
                 if (check && contained) {
                     a.latched = 1;  // border_points left empty: bonus is paid once (Q4)
                     rew = c.contained_bonus;
+                    rkind = RK_CONTAINED;
                     if (x == 0) atomicAdd(&s.stats[ST_CONTAINED], 1ull);
                 } else if (!a.alive) {
                     rew = c.death_penalty;
+                    rkind = RK_DEATH;
                 } else if (!anyB) {
                     rew = 1.0;  // placeholder: burn-out fraction computed below
+                    rkind = RK_BURNOUT;
                 } else {
                     rew = c.default_reward;
+                    rkind = RK_DEFAULT;
                 }
             }
             const bool burnout = act && !(check && contained) && a.alive && !anyB;
@@ -612,6 +674,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
 #pragma unroll
                 for (int o = L / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o, L);
                 if (burnout) rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)cnt, (double)(W * H)));
+                if (burnout) rcnt = (uint32_t)cnt;
             }
             const bool done = valid_env && !a.running;
             if (act) {
@@ -639,7 +702,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
                                                : (size_t)s.N * W * H * 3 * obs_elem_bytes(io.obs_dtype);
                 emit_obs<L>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
                             (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, tab8,
-                            lane, sub, x, W, H, env0, n_valid);
+                            lane, sub, x, W, H, env0, n_valid, SRV ? (rkind | (done ? 8u : 0u) | (rcnt << 4)) : 0u);
+            }
+            if (SRV) {
+                __threadfence_system();  // this thread's stores to mapped host memory are visible before the flag is
+                __syncthreads();
+                srv_step += 1u;
+                if (threadIdx.x == 0) {
+                    const uint32_t slice = blockIdx.x / (uint32_t)io.srv.ctas_per_slice;
+                    const uint32_t n_in = min((uint32_t)io.srv.ctas_per_slice, gridDim.x - slice * (uint32_t)io.srv.ctas_per_slice);
+                    const uint32_t old = atomicAdd(&io.srv.count[slice], 1u);
+                    if (old + 1u == n_in * srv_step) {  // the slice's last CTA of this step
+                        __threadfence_system();
+                        io.srv.done[slice * 16u] = io.srv.seq0 + srv_step;
+                    }
+                }
             }
         }
     }
@@ -664,6 +741,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) warp_kernel(DevState s, S
             if (n_ticks_done) atomicAdd(&s.stats[ST_TICKS], (unsigned long long)n_ticks_done);
         }
     }
+}
+
+// 128 registers (16 warps per SM: all 2048 warps of a 4096-env batch resident) measured faster than what ptxas picks
+// when left alone (164: 3.3 instead of 2.3 us per C2 step); the network variant with per-direction hit counters needs more.
+template <int L, int FB, bool UNI, bool MLP>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MLP && !UNI) ? 8 / kWarpsPerBlock : 16 / kWarpsPerBlock)
+warp_kernel(DevState s, StepCfg c, WarpIO io) {
+    warp_body<L, FB, UNI, MLP, false>(s, c, io);
+}
+// The step server must be resident as a whole (cooperative launch): 128 registers at most.
+template <int L, int FB, bool UNI>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock) warp_server_kernel(DevState s, StepCfg c, WarpIO io) {
+    warp_body<L, FB, UNI, false, true>(s, c, io);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -694,6 +784,25 @@ cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO
     else return cudaErrorInvalidValue;
 #undef WF_LAUNCH
     return cudaGetLastError();
+}
+
+// The step server: the same kernel, launched cooperatively (all CTAs resident, or the launch fails).
+cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream) {
+    const int L = s.RS;
+    const int epw = 32 / L;
+    const int envs_per_block = kWarpsPerBlock * epw;
+    const dim3 grid((s.N + envs_per_block - 1) / envs_per_block), block(kWarpsPerBlock * 32);
+    if (s.HB != 0 && (s.HB != kHitBits || s.FB != 5)) return cudaErrorInvalidValue;
+    const void* fn = nullptr;
+    if (L == 16 && s.FB == 5 && s.HB) fn = (const void*)warp_server_kernel<16, 5, true>;
+    else if (L == 32 && s.FB == 5 && s.HB) fn = (const void*)warp_server_kernel<32, 5, true>;
+    else if (L == 16 && s.FB == 5) fn = (const void*)warp_server_kernel<16, 5, false>;
+    else if (L == 16 && s.FB == 8) fn = (const void*)warp_server_kernel<16, 8, false>;
+    else if (L == 32 && s.FB == 5) fn = (const void*)warp_server_kernel<32, 5, false>;
+    else if (L == 32 && s.FB == 8) fn = (const void*)warp_server_kernel<32, 8, false>;
+    else return cudaErrorInvalidValue;
+    void* args[3] = {const_cast<DevState*>(&s), const_cast<StepCfg*>(&c), const_cast<WarpIO*>(&io)};
+    return cudaLaunchCooperativeKernel(fn, grid, block, args, 0, stream);
 }
 
 }  // namespace wf
