@@ -120,7 +120,9 @@ struct wf_env {
     } sess;
 };
 constexpr int kSessMaxSlices = 64;
+extern "C" {
 static int session_park(wf_env* e);
+}
 
 // ---------------------------------------------------------------------------------------------
 // canonical-plane export / import (parity injection, checkpoint) -- works for both layouts
@@ -885,7 +887,7 @@ int wf_step_host(wf_env* e, const int32_t* actions_host, void* obs_host, int32_t
         return WF_OK;
     }
     if (small_direct) {
-        // The SMs' stores over PCIe reach ~39 GB/s, a DMA copy ~48 GB/s (measured, tools/e2e_modes.py):
+        // The SMs' stores over PCIe reach ~39 GB/s, a DMA copy ~48 GB/s (measured, tools/e2e_ab.py):
         // the 16-36 KB of actions/reward/done go zero-copy (no per-copy latency), the observation block
         // is written to HBM and moved by ONE cudaMemcpyAsync unless WF_HOST_MODE=direct.
         const bool obs_direct = e->host_obs_direct && o_d && (reinterpret_cast<uintptr_t>(o_d) & 15u) == 0;
