@@ -274,7 +274,9 @@ class BatchedForestFire:
                                                _ptr(out["scalars"]), self._stream()))
         coef = torch.as_tensor(self.wind_coef, device=dev)[out["scalars"][:, _lib.S_WIND_ID].long()]  # [N, 4]
         out["temp"] = (out["hits"].double() * coef[:, None, None, :]).sum(-1)
-        out["a_iter"] = self.a_speed_iter  # METADATA['a_speed_iter'] (Q8): one counter per handle, part of a checkpoint
+        # METADATA['a_speed_iter'] (Q8): ONE counter per handle, part of a checkpoint; kept as an [N] tensor (the same
+        # value for every env) so that code that slices every entry of the dict per env keeps working
+        out["a_iter"] = torch.full((N,), self.a_speed_iter, dtype=torch.int32, device=dev)
         return out
 
     @property
@@ -293,7 +295,7 @@ class BatchedForestFire:
         ``set_state(**get_state())`` restores a checkpoint (derived entries such as ``temp`` / ``apos`` are ignored)."""
         N, W, H = self.n_envs, self.width, self.height
         if a_iter is not None:
-            self.a_speed_iter = int(a_iter)
+            self.a_speed_iter = int(a_iter.flatten()[0]) if torch.is_tensor(a_iter) else int(a_iter)
 
         def u8(t, shape):
             if t is None:

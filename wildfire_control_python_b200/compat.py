@@ -181,7 +181,7 @@ class ForestFire:
     def _state(self):
         if self._cache is None:
             st = self._batch.get_state()
-            self._cache = {k: v[self._i].cpu().numpy() for k, v in st.items() if torch.is_tensor(v)}
+            self._cache = {k: v[self._i].cpu().numpy() for k, v in st.items()}
         return self._cache
 
     def _obs_f64(self):

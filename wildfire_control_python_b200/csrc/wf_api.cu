@@ -714,12 +714,11 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
     const DevState& s = e->st;
     const int epw = 32 / s.RS;
     const int64_t env_bits = (int64_t)s.W * s.H * 3, records = (s.N + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
-    volatile uint32_t* ctl = ss.ctl;
     if (ss.seq >= 0xfffffff0u) {  // sequence numbers wrap: park and start over from 0
         WF_QUIESCE(e);
         ss.seq = 0u;
     }
-    if (ss.running && ctl[16] == ss.generation) {  // the kernel parked itself (no doorbell for idle_ns)
+    if (ss.running && reinterpret_cast<volatile uint32_t*>(ss.ctl)[16] == ss.generation) {  // the kernel parked itself (idle)
         WF_CUDA(cudaStreamSynchronize(e->hstream));
         ss.running = false;
     }
@@ -741,18 +740,18 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
         }
-        ctl[0] = ss.seq;  // doorbell: nothing requested yet
+        reinterpret_cast<volatile uint32_t*>(ss.ctl)[0] = ss.seq;  // doorbell: nothing requested yet
         if (int rc = session_launch(e)) {
             ss.wanted = false;  // e.g. the batch is too large for a cooperative launch: the launch-per-step path serves it
             cudaGetLastError();
             return wf_step_host(e, actions_host, obs_host, WF_OBS_U8, reward_host, done_host);
         }
     }
+    volatile uint32_t* ctl = ss.ctl;
     std::memcpy(ss.actions, actions_host, (size_t)s.N * sizeof(int32_t));
     ss.seq += 1u;
     std::atomic_thread_fence(std::memory_order_release);
     ctl[0] = ss.seq;  // ring
-    e->a_iter = advance_a_iter(e, 1);
     ss.steps += 1;
     const int64_t rps = (int64_t)ss.ctas_per_slice * 4;
     const auto t_start = std::chrono::steady_clock::now();
@@ -760,7 +759,10 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
         const bool ok = hostpool_expand_session(e->pool, ss.rec, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw,
                                                 s.N, ss.ctl + 32, ss.seq, rps, reward_host, done_host, e->cfg.default_reward,
                                                 e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000);
-        if (ok) return WF_OK;
+        if (ok) {
+            e->a_iter = advance_a_iter(e, 1);  // (after the step: a relaunch below must start from the phase before it)
+            return WF_OK;
+        }
         if (ctl[16] == ss.generation) {
             // The kernel decided to park in the instant the doorbell was rung: it did not take this step.  Start it
             // again behind the old launch; it finds the doorbell ahead of its seq0 and serves the step at once.
