@@ -97,7 +97,7 @@ def test_step_host_is_ordered_behind_device_calls(cfg, n_envs):
     the handle's private stream must see the finished reset.  A long kernel is queued in front of the reset so that
     an unordered step would certainly overtake it."""
     from wildfire_control_python_b200.batched import BatchedForestFire
-    gpu, twin = BatchedForestFire(n_envs, **cfg), BatchedForestFire(n_envs, **cfg)
+    twin = BatchedForestFire(n_envs, **cfg)
     twin.reset()
     acts = np.random.default_rng(5).integers(0, 4, size=(4, n_envs), dtype=np.int32)
     ref = []
@@ -106,6 +106,7 @@ def test_step_host_is_ordered_behind_device_calls(cfg, n_envs):
         ref.append((to_np(o).copy(), to_np(r).copy(), to_np(d).copy()))
     big = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
     for rep in range(3):
+        gpu = BatchedForestFire(n_envs, **cfg)  # a fresh handle: its reset() opens episode 0, like the twin's
         for _ in range(6):
             big.normal_()  # ~ms of queued work on the current stream
         gpu.reset()
@@ -141,7 +142,7 @@ def test_checkpoint_restores_the_tick_phase(cfg):
     restored MID-PHASE ticks the fire on the same steps as the original."""
     from wildfire_control_python_b200.batched import BatchedForestFire
     N, K2 = 9, 60
-    for K1 in (cfg["a_speed"] + 1, 2 * cfg["a_speed"] + 2):  # both leave the counter away from its initial value
+    for K1 in (cfg["a_speed"] + 1, 2 * cfg["a_speed"] + 1):  # both leave the counter away from its initial value
         a = BatchedForestFire(N, auto_reset=True, **cfg)
         a.reset()
         gen = torch.Generator("cuda").manual_seed(cfg["seed"])

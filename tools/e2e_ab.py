@@ -57,6 +57,10 @@ if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
     run("launch", {}, False, N, K)
+    if len(sys.argv) > 3 and sys.argv[3] == "quick":
+        for t in (12, 6, 3):
+            run(f"session/{t}", {"WF_HOST_THREADS": str(t)}, True, N, K)
+        sys.exit(0)
     run("graph", {"WF_HOST_GRAPH": "1"}, False, N, K)
     run("direct", {"WF_HOST_PACKED": "direct"}, False, N, K)
     run("u8", {"WF_HOST_PACKED": "0"}, False, N, K)

@@ -4,6 +4,7 @@ import os
 import sys
 os.environ["WILDFIRE_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_dbg", "libwf_timing.so")
 import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import WORKLOADS
 from wildfire_control_python_b200 import BatchedForestFire, _lib
 

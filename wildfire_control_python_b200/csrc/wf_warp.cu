@@ -705,10 +705,10 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                             lane, sub, x, W, H, env0, n_valid, SRV ? (rkind | (done ? 8u : 0u) | (rcnt << 4)) : 0u);
             }
             if (SRV) {
-                __threadfence_system();  // this thread's stores to mapped host memory are visible before the flag is
-                __syncthreads();
+                __syncthreads();  // every warp of the CTA has issued its stores to mapped host memory ...
                 srv_step += 1u;
                 if (threadIdx.x == 0) {
+                    __threadfence_system();  // ... and ONE system-scope fence per CTA orders them (cumulatively) before the flag
                     const uint32_t slice = blockIdx.x / (uint32_t)io.srv.ctas_per_slice;
                     const uint32_t n_in = min((uint32_t)io.srv.ctas_per_slice, gridDim.x - slice * (uint32_t)io.srv.ctas_per_slice);
                     const uint32_t old = atomicAdd(&io.srv.count[slice], 1u);
@@ -746,7 +746,11 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
 // 128 registers (16 warps per SM: all 2048 warps of a 4096-env batch resident) measured faster than what ptxas picks
 // when left alone (164: 3.3 instead of 2.3 us per C2 step); the network variant with per-direction hit counters needs more.
 template <int L, int FB, bool UNI, bool MLP>
+#ifdef WF_WARP_NO_MINBLOCKS  // A/B switch (tools/build_variant.sh): let ptxas pick the register count
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+#else
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MLP && !UNI) ? 8 / kWarpsPerBlock : 16 / kWarpsPerBlock)
+#endif
 warp_kernel(DevState s, StepCfg c, WarpIO io) {
     warp_body<L, FB, UNI, MLP, false>(s, c, io);
 }
