@@ -115,6 +115,8 @@ struct wf_env {
         uint32_t* rec;              // mapped host [records][rec_words + 1]
         uint32_t* rec_dev;
         uint32_t* sync_dev;         // device: go @0, arrival counters @16 + slice
+        unsigned long long* dbg_dev;  // device: the kernel's debug counters (SrvCtl::dbg)
+        double t_wait;              // WF_HOST_TIMING: seconds between ringing and the last slice expanded
         int slices, ctas_per_slice;
         int64_t launches, steps, relaunch_races;
     } sess;
@@ -419,9 +421,16 @@ void wf_destroy(wf_env* e) {
     if (e->sess.actions) cudaFreeHost(e->sess.actions);
     if (e->sess.rec) cudaFreeHost(e->sess.rec);
     cudaFree(e->sess.sync_dev);
-    if (e->sess.steps && getenv("WF_HOST_TIMING"))
-        fprintf(stderr, "wf_host_session: %lld steps in %lld launches of the step server (%lld park/ring races)\n",
-                (long long)e->sess.steps, (long long)e->sess.launches, (long long)e->sess.relaunch_races);
+    if (e->sess.steps && getenv("WF_HOST_TIMING")) {
+        unsigned long long d[8] = {0};
+        if (e->sess.dbg_dev) cudaMemcpy(d, e->sess.dbg_dev, sizeof(d), cudaMemcpyDeviceToHost);
+        const double n = d[3] ? (double)d[3] : 1.0;
+        fprintf(stderr, "wf_host_session: %lld steps in %lld launches of the step server (%lld park/ring races); host ring->expanded "
+                        "%.2f us; CTA 0 per step: doorbell wait %.2f us, step %.2f us, barrier+fence+arrive %.2f us\n",
+                (long long)e->sess.steps, (long long)e->sess.launches, (long long)e->sess.relaunch_races,
+                1e6 * e->sess.t_wait / (double)e->sess.steps, d[0] / n / 1e3, d[1] / n / 1e3, d[2] / n / 1e3);
+    }
+    cudaFree(e->sess.dbg_dev);
     if (e->tstate) tile_destroy(e->tstate);
     cudaFree(e->st.planes); cudaFree(e->st.fuel); cudaFree(e->st.hits); cudaFree(e->st.scal); cudaFree(e->st.stats);
     cudaFree(e->wind_dev);
@@ -691,18 +700,20 @@ static int session_launch(wf_env* e) {
     ss.generation += 1u;
     WF_CUDA(cudaMemsetAsync(ss.sync_dev, 0, (16 + kSessMaxSlices) * sizeof(uint32_t), e->hstream));
     WarpIO io{ss.actions_dev, ss.rec_dev, nullptr, nullptr, nullptr, nullptr, kObsPackedStatus, 1, e->a_iter, 0,
-              magic_for(s.H), WF_POLICY_STREAM, nullptr, MlpPolicy{}, SrvCtl{}};
-    io.srv.doorbell = ss.ctl_dev;
-    io.srv.parked = ss.ctl_dev + 16;
-    io.srv.done = ss.ctl_dev + 32;
-    io.srv.go = ss.sync_dev;
-    io.srv.count = ss.sync_dev + 16;
-    io.srv.seq0 = ss.seq;
-    io.srv.generation = ss.generation;
-    io.srv.ctas_per_slice = ss.ctas_per_slice;
+              magic_for(s.H), WF_POLICY_STREAM, nullptr, MlpPolicy{}};
+    SrvCtl srv{};
+    srv.doorbell = ss.ctl_dev;
+    srv.parked = ss.ctl_dev + 16;
+    srv.done = ss.ctl_dev + 32;
+    srv.go = ss.sync_dev;
+    srv.count = ss.sync_dev + 16;
+    srv.seq0 = ss.seq;
+    srv.generation = ss.generation;
+    srv.ctas_per_slice = ss.ctas_per_slice;
     const char* idle = getenv("WF_SESSION_IDLE_US");
-    io.srv.idle_ns = 1000ull * (unsigned long long)((idle && atoll(idle) > 0) ? atoll(idle) : 2000);
-    WF_CUDA(launch_warp_server(s, e->sc, io, e->hstream));
+    srv.dbg = ss.dbg_dev;
+    srv.idle_ns = 1000ull * (unsigned long long)((idle && atoll(idle) > 0) ? atoll(idle) : 2000);
+    WF_CUDA(launch_warp_server(s, e->sc, io, srv, e->hstream));
     e->launches += 1;
     ss.launches += 1;
     ss.running = true;
@@ -739,6 +750,8 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)records * (rec_words + 1) * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
+            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.dbg_dev), 8 * sizeof(unsigned long long)));
+            WF_CUDA(cudaMemset(ss.dbg_dev, 0, 8 * sizeof(unsigned long long)));
         }
         reinterpret_cast<volatile uint32_t*>(ss.ctl)[0] = ss.seq;  // doorbell: nothing requested yet
         if (int rc = session_launch(e)) {
@@ -760,6 +773,7 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
                                                 s.N, ss.ctl + 32, ss.seq, rps, reward_host, done_host, e->cfg.default_reward,
                                                 e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000);
         if (ok) {
+            ss.t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             e->a_iter = advance_a_iter(e, 1);  // (after the step: a relaunch below must start from the phase before it)
             return WF_OK;
         }

@@ -25,6 +25,9 @@ struct SrvCtl {
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
     unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)
+    unsigned long long* dbg;      // device, 8 counters of CTA 0 (ns, summed over steps; WF_HOST_TIMING prints them):
+                                  // 0 waiting for the doorbell, 1 go -> step computed and stored, 2 CTA barrier + system
+                                  // fence + arrival, 3 steps
 };
 
 struct WarpIO {
@@ -39,12 +42,11 @@ struct WarpIO {
     int32_t policy;          // actions == nullptr: WF_POLICY_STREAM, WF_POLICY_WALK or WF_POLICY_MLP
     int32_t* actions_out;    // [K][N] or nullptr: the actions the policy chose
     MlpPolicy mlp;           // WF_POLICY_MLP only
-    SrvCtl srv;              // step-server launches only (launch_warp_server)
 };
 cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
 // The same kernel as a cooperative launch (every CTA resident) that serves steps until told to park; io.actions / io.obs
 // are mapped host buffers (obs_dtype kObsPackedStatus).  cudaErrorCooperativeLaunchTooLarge if the batch does not fit.
-cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream);
+cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, const SrvCtl& srv, cudaStream_t stream);
 
 struct TileIO {
     const int32_t* actions;  // [K][N] or nullptr (ACTION stream / policy)

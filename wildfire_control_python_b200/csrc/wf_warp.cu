@@ -264,7 +264,7 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
 }
 
 template <int L, int FB, bool UNI, bool MLP, bool SRV>
-__device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, const WarpIO& io) {
+__device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, const WarpIO& io, const SrvCtl& srv) {
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
@@ -343,28 +343,31 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
         int it = io.a_iter0;
         uint32_t ablk[4] = {0u, 0u, 0u, 0u}, ablk_ep = 0xffffffffu, ablk_idx = 0xffffffffu;  // cached ACTION block
         uint32_t srv_step = 0u;  // SRV: steps served by this launch
+        unsigned long long srv_t0 = 0ull, srv_t1 = 0ull;  // CTA 0, thread 0: time stamps of the debug counters
         for (int kk = 0; SRV || kk < io.K; ++kk) {
             const int k = SRV ? 0 : kk;  // row of the output arrays
             if (SRV) {
                 if (threadIdx.x == 0) {
                     uint32_t go;
                     if (blockIdx.x == 0) {
-                        const uint32_t last = io.srv.seq0 + srv_step;
+                        const uint32_t last = srv.seq0 + srv_step;
                         const unsigned long long t0 = global_timer_ns();
+                        srv_t0 = t0;
                         uint32_t cmd;
                         for (;;) {
-                            cmd = *io.srv.doorbell;
-                            if (cmd != last || global_timer_ns() - t0 > io.srv.idle_ns) break;
+                            cmd = *srv.doorbell;
+                            if (cmd != last || global_timer_ns() - t0 > srv.idle_ns) break;
                         }
                         if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
-                            *io.srv.parked = io.srv.generation;
+                            *srv.parked = srv.generation;
                             go = 0xffffffffu;
                         } else {
                             go = srv_step + 1u;
                         }
-                        st_release_gpu(io.srv.go, go);
+                        srv_t1 = global_timer_ns();
+                        st_release_gpu(srv.go, go);
                     } else {
-                        do { go = ld_acquire_gpu(io.srv.go); } while (go == srv_step);
+                        do { go = ld_acquire_gpu(srv.go); } while (go == srv_step);
                     }
                     srv_cmd = go;
                 }
@@ -705,16 +708,25 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                             lane, sub, x, W, H, env0, n_valid, SRV ? (rkind | (done ? 8u : 0u) | (rcnt << 4)) : 0u);
             }
             if (SRV) {
+                unsigned long long srv_t2 = 0ull;
+                if (blockIdx.x == 0 && threadIdx.x == 0) srv_t2 = global_timer_ns();
                 __syncthreads();  // every warp of the CTA has issued its stores to mapped host memory ...
                 srv_step += 1u;
                 if (threadIdx.x == 0) {
                     __threadfence_system();  // ... and ONE system-scope fence per CTA orders them (cumulatively) before the flag
-                    const uint32_t slice = blockIdx.x / (uint32_t)io.srv.ctas_per_slice;
-                    const uint32_t n_in = min((uint32_t)io.srv.ctas_per_slice, gridDim.x - slice * (uint32_t)io.srv.ctas_per_slice);
-                    const uint32_t old = atomicAdd(&io.srv.count[slice], 1u);
+                    const uint32_t slice = blockIdx.x / (uint32_t)srv.ctas_per_slice;
+                    const uint32_t n_in = min((uint32_t)srv.ctas_per_slice, gridDim.x - slice * (uint32_t)srv.ctas_per_slice);
+                    const uint32_t old = atomicAdd(&srv.count[slice], 1u);
                     if (old + 1u == n_in * srv_step) {  // the slice's last CTA of this step
                         __threadfence_system();
-                        io.srv.done[slice * 16u] = io.srv.seq0 + srv_step;
+                        srv.done[slice * 16u] = srv.seq0 + srv_step;
+                    }
+                    if (blockIdx.x == 0 && srv.dbg != nullptr) {
+                        const unsigned long long t3 = global_timer_ns();
+                        srv.dbg[0] += srv_t1 - srv_t0;
+                        srv.dbg[1] += srv_t2 - srv_t1;
+                        srv.dbg[2] += t3 - srv_t2;
+                        srv.dbg[3] += 1ull;
                     }
                 }
             }
@@ -752,12 +764,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MLP && !UNI) ? 8 / kWarpsPerBlock : 16 / kWarpsPerBlock)
 #endif
 warp_kernel(DevState s, StepCfg c, WarpIO io) {
-    warp_body<L, FB, UNI, MLP, false>(s, c, io);
+    warp_body<L, FB, UNI, MLP, false>(s, c, io, SrvCtl{});
 }
 // The step server must be resident as a whole (cooperative launch): 128 registers at most.
 template <int L, int FB, bool UNI>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock) warp_server_kernel(DevState s, StepCfg c, WarpIO io) {
-    warp_body<L, FB, UNI, false, true>(s, c, io);
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock) warp_server_kernel(DevState s, StepCfg c, WarpIO io, SrvCtl srv) {
+    warp_body<L, FB, UNI, false, true>(s, c, io, srv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -791,7 +803,7 @@ cudaError_t launch_warp_family(const DevState& s, const StepCfg& c, const WarpIO
 }
 
 // The step server: the same kernel, launched cooperatively (all CTAs resident, or the launch fails).
-cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, cudaStream_t stream) {
+cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO& io, const SrvCtl& srv, cudaStream_t stream) {
     const int L = s.RS;
     const int epw = 32 / L;
     const int envs_per_block = kWarpsPerBlock * epw;
@@ -805,7 +817,7 @@ cudaError_t launch_warp_server(const DevState& s, const StepCfg& c, const WarpIO
     else if (L == 32 && s.FB == 5) fn = (const void*)warp_server_kernel<32, 5, false>;
     else if (L == 32 && s.FB == 8) fn = (const void*)warp_server_kernel<32, 8, false>;
     else return cudaErrorInvalidValue;
-    void* args[3] = {const_cast<DevState*>(&s), const_cast<StepCfg*>(&c), const_cast<WarpIO*>(&io)};
+    void* args[4] = {const_cast<DevState*>(&s), const_cast<StepCfg*>(&c), const_cast<WarpIO*>(&io), const_cast<SrvCtl*>(&srv)};
     return cudaLaunchCooperativeKernel(fn, grid, block, args, 0, stream);
 }
 
