@@ -740,6 +740,8 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             constexpr int kRecordsPerCta = 4;  // WF_WARPS_PER_BLOCK warps, one record each
             const int64_t ctas = (records + kRecordsPerCta - 1) / kRecordsPerCta;
             int slices = std::min<int64_t>(std::min(hostpool_threads(e->pool), kSessMaxSlices), ctas);
+            if (const char* v = getenv("WF_SESSION_SLICES"))  // experiments: fewer completion flags than host threads
+                if (atoi(v) >= 1) slices = std::min(slices, atoi(v));
             ss.ctas_per_slice = (int)((ctas + slices - 1) / slices);
             ss.slices = (int)((ctas + ss.ctas_per_slice - 1) / ss.ctas_per_slice);
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));

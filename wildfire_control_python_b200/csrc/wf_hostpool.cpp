@@ -29,7 +29,7 @@ struct ExpandJob {
     // step-server session (wf_host_session): the records of slice t are complete once flags[16 * t] == seq
     const volatile uint32_t* flags;
     uint32_t seq;
-    int64_t records_per_slice;  // session: slice t = records [t * records_per_slice, ...); 0: split evenly over the threads
+    int64_t records_per_slice;  // session: flag s covers records [s * records_per_slice, (s + 1) * records_per_slice)
     double* reward;             // session: decoded from the status word (may be null)
     uint8_t* done;
     double default_reward, death_penalty, contained_bonus, cells;
@@ -180,19 +180,23 @@ private:
 #endif
     }
     void slice(int t) {
-        const int64_t per = job_.records_per_slice > 0 ? job_.records_per_slice : (job_.records + n_ - 1) / n_;
+        const int64_t per = (job_.records + n_ - 1) / n_;
         const int64_t r0 = per * t, r1 = (r0 + per < job_.records) ? r0 + per : job_.records;
         if (r0 >= r1) return;
-        if (job_.flags) {  // session: the GPU raises this slice's flag once all of its records are in host memory
-            const volatile uint32_t* f = job_.flags + 16 * t;
+        if (job_.flags) {
+            // session: the GPU raises a slice's flag once all of the slice's records are in host memory; this thread's
+            // records may lie in more than one slice
             const auto t0 = std::chrono::steady_clock::now();
             int spins = 0;
-            while (*f != job_.seq) {
-                cpu_relax();
-                if ((++spins & 255) == 0 &&
-                    std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(job_.timeout_ns)) {
-                    failed_.store(1, std::memory_order_release);
-                    return;
+            for (int64_t sl = r0 / job_.records_per_slice; sl <= (r1 - 1) / job_.records_per_slice; ++sl) {
+                const volatile uint32_t* f = job_.flags + 16 * sl;
+                while (*f != job_.seq) {
+                    cpu_relax();
+                    if ((++spins & 255) == 0 &&
+                        std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(job_.timeout_ns)) {
+                        failed_.store(1, std::memory_order_release);
+                        return;
+                    }
                 }
             }
             std::atomic_thread_fence(std::memory_order_acquire);

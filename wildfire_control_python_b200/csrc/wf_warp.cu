@@ -713,7 +713,11 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 __syncthreads();  // every warp of the CTA has issued its stores to mapped host memory ...
                 srv_step += 1u;
                 if (threadIdx.x == 0) {
-                    __threadfence_system();  // ... and ONE system-scope fence per CTA orders them (cumulatively) before the flag
+                    // ... and are ordered before this CTA's arrival at GPU scope.  System-scope fences are expensive (each
+                    // one drains the GPU's writes to host memory: ~100 us per step when all 512 CTAs issued one), so only
+                    // the LAST CTA of a slice issues one -- it is cumulative over the stores it has observed through the
+                    // arrival counter -- before it raises the slice's flag.
+                    __threadfence();
                     const uint32_t slice = blockIdx.x / (uint32_t)srv.ctas_per_slice;
                     const uint32_t n_in = min((uint32_t)srv.ctas_per_slice, gridDim.x - slice * (uint32_t)srv.ctas_per_slice);
                     const uint32_t old = atomicAdd(&srv.count[slice], 1u);
