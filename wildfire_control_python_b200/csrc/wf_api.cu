@@ -110,8 +110,9 @@ struct wf_env {
         uint32_t seq, generation;   // last sequence number rung; id of the current / last launch
         uint32_t* ctl;              // mapped host: doorbell @0, parked @16 (words), done flags @32 + 16 * slice
         uint32_t* ctl_dev;
-        int32_t* actions;           // mapped host [N]
-        int32_t* actions_dev;
+        int32_t* actions;           // mapped host [N, padded to 4]
+        int32_t* actions_dev;       // its device alias
+        int32_t* actions_hbm;       // HBM copy made by the kernel's CTA 0 every step
         uint32_t* rec;              // mapped host [records][rec_words + 1]
         uint32_t* rec_dev;
         uint32_t* sync_dev;         // device: go @0, arrival counters @16 + slice
@@ -421,14 +422,15 @@ void wf_destroy(wf_env* e) {
     if (e->sess.actions) cudaFreeHost(e->sess.actions);
     if (e->sess.rec) cudaFreeHost(e->sess.rec);
     cudaFree(e->sess.sync_dev);
+    cudaFree(e->sess.actions_hbm);
     if (e->sess.steps && getenv("WF_HOST_TIMING")) {
         unsigned long long d[8] = {0};
         if (e->sess.dbg_dev) cudaMemcpy(d, e->sess.dbg_dev, sizeof(d), cudaMemcpyDeviceToHost);
         const double n = d[3] ? (double)d[3] : 1.0;
         fprintf(stderr, "wf_host_session: %lld steps in %lld launches of the step server (%lld park/ring races); host ring->expanded "
-                        "%.2f us; CTA 0 per step: doorbell wait %.2f us, step %.2f us, barrier+fence+arrive %.2f us\n",
+                        "%.2f us; CTA 0 per step: doorbell wait + action copy %.2f us, step %.2f us, CTA barrier %.2f us, fence + arrive %.2f us\n",
                 (long long)e->sess.steps, (long long)e->sess.launches, (long long)e->sess.relaunch_races,
-                1e6 * e->sess.t_wait / (double)e->sess.steps, d[0] / n / 1e3, d[1] / n / 1e3, d[2] / n / 1e3);
+                1e6 * e->sess.t_wait / (double)e->sess.steps, d[0] / n / 1e3, d[1] / n / 1e3, d[2] / n / 1e3, d[4] / n / 1e3);
     }
     cudaFree(e->sess.dbg_dev);
     if (e->tstate) tile_destroy(e->tstate);
@@ -699,12 +701,14 @@ static int session_launch(wf_env* e) {
     const DevState& s = e->st;
     ss.generation += 1u;
     WF_CUDA(cudaMemsetAsync(ss.sync_dev, 0, (16 + kSessMaxSlices) * sizeof(uint32_t), e->hstream));
-    WarpIO io{ss.actions_dev, ss.rec_dev, nullptr, nullptr, nullptr, nullptr, kObsPackedStatus, 1, e->a_iter, 0,
+    WarpIO io{ss.actions_hbm, ss.rec_dev, nullptr, nullptr, nullptr, nullptr, kObsPackedStatus, 1, e->a_iter, 0,
               magic_for(s.H), WF_POLICY_STREAM, nullptr, MlpPolicy{}};
     SrvCtl srv{};
     srv.doorbell = ss.ctl_dev;
     srv.parked = ss.ctl_dev + 16;
     srv.done = ss.ctl_dev + 32;
+    srv.actions_host = ss.actions_dev;
+    srv.actions_dev = ss.actions_hbm;
     srv.go = ss.sync_dev;
     srv.count = ss.sync_dev + 16;
     srv.seq0 = ss.seq;
@@ -747,7 +751,10 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));
             std::memset(ss.ctl, 0, (32 + 16 * kSessMaxSlices) * sizeof(uint32_t));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.ctl_dev), ss.ctl, 0));
-            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.actions), (size_t)s.N * sizeof(int32_t), cudaHostAllocMapped));
+            const size_t act_bytes = (size_t)((s.N + 3) / 4) * 4 * sizeof(int32_t);
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.actions), act_bytes, cudaHostAllocMapped));
+            std::memset(ss.actions, 0, act_bytes);
+            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), act_bytes));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.actions_dev), ss.actions, 0));
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)records * (rec_words + 1) * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));

@@ -20,14 +20,16 @@ struct SrvCtl {
     volatile uint32_t* doorbell;  // mapped host, host -> GPU: sequence number of the step requested (0xffffffff: park)
     volatile uint32_t* parked;    // mapped host, GPU -> host: the launch's generation, once the kernel has decided to exit
     volatile uint32_t* done;      // mapped host, GPU -> host: [slices] flags 16 words apart = sequence number completed
+    const int32_t* actions_host;  // mapped host [N, padded to 4]: written by wf_step_host before it rings
+    int32_t* actions_dev;         // HBM [N, padded to 4]: CTA 0's copy of it, what the warps read (WarpIO::actions)
     uint32_t* go;                 // device: master CTA -> every CTA: index of the step to run (1, 2, ...), 0xffffffff = exit
     uint32_t* count;              // device: [slices] arrival counters
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
     unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)
     unsigned long long* dbg;      // device, 8 counters of CTA 0 (ns, summed over steps; WF_HOST_TIMING prints them):
-                                  // 0 waiting for the doorbell, 1 go -> step computed and stored, 2 CTA barrier + system
-                                  // fence + arrival, 3 steps
+                                  // 0 doorbell wait + action copy, 1 go -> thread 0's warp has stepped and stored, 2 CTA
+                                  // barrier (the slowest warp), 3 steps, 4 fence + arrival
 };
 
 struct WarpIO {

@@ -154,7 +154,7 @@ __device__ void reset_rows(Rows<FB>& r, Agent& a, const DevState& s, const StepC
 // 4-byte words of the output (coalesced 64/128-byte stores, ~7 instructions per word).
 constexpr int kStreamWords = 100;  // 3*32*32/32 = 96 words + spill-over of the last row's funnel shift
 
-template <int L>
+template <int L, bool SRV = false>
 __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t arow, uint32_t frow, uint32_t freerow,
                                          uint32_t* stream, const uint32_t* spread3, const uint2* tab8, int lane, int sub,
                                          int x, int W, int H, int env0, int n_valid, uint32_t status16 = 0u) {
@@ -188,10 +188,10 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
     }
     __syncwarp();
     if (n_valid <= 0) return;
-    if (dtype == kObsPacked || dtype == kObsPackedStatus) {  // the stream as it is: 8x fewer bytes over PCIe, expanded on the host
+    if (SRV || dtype == kObsPacked) {  // the stream as it is: 8x fewer bytes over PCIe, expanded on the host
         constexpr int EPW = 32 / L;
         const int rec_words = (EPW * nbits + 31) >> 5;
-        if (dtype == kObsPackedStatus) {  // + one status word per record: reward kind / done / burn-out count of each env
+        if (SRV) {  // kObsPackedStatus: + one status word per record: reward kind / done / burn-out count of each env
             uint32_t st = __shfl_sync(0xffffffffu, status16, 0);
             if (EPW == 2) st |= __shfl_sync(0xffffffffu, status16, L & 31) << 16;
             uint32_t* rec = static_cast<uint32_t*>(obs_step) + (size_t)(env0 / EPW) * (rec_words + 1);
@@ -347,9 +347,12 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
         for (int kk = 0; SRV || kk < io.K; ++kk) {
             const int k = SRV ? 0 : kk;  // row of the output arrays
             if (SRV) {
-                if (threadIdx.x == 0) {
-                    uint32_t go;
-                    if (blockIdx.x == 0) {
+                if (blockIdx.x == 0) {
+                    // CTA 0: thread 0 waits for the doorbell, then the whole CTA brings the step's actions from the mapped
+                    // host buffer into HBM with coalesced 16-byte loads (one read over PCIe per 512 bytes; every warp
+                    // fetching its own action from host memory was 2048 small PCIe reads, ~80 us per step), and only
+                    // then are the other CTAs released.
+                    if (threadIdx.x == 0) {
                         const uint32_t last = srv.seq0 + srv_step;
                         const unsigned long long t0 = global_timer_ns();
                         srv_t0 = t0;
@@ -360,24 +363,38 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         }
                         if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
                             *srv.parked = srv.generation;
-                            go = 0xffffffffu;
+                            srv_cmd = 0xffffffffu;
                         } else {
-                            go = srv_step + 1u;
+                            srv_cmd = srv_step + 1u;
                         }
-                        srv_t1 = global_timer_ns();
-                        st_release_gpu(srv.go, go);
-                    } else {
-                        do { go = ld_acquire_gpu(srv.go); } while (go == srv_step);
                     }
-                    srv_cmd = go;
+                    __syncthreads();
+                    if (srv_cmd != 0xffffffffu) {
+                        const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
+                        const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
+                        int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
+                        for (int j = threadIdx.x; j < n16; j += blockDim.x) dst[j] = __ldcv(src + j);
+                        __threadfence();
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        srv_t1 = global_timer_ns();
+                        st_release_gpu(srv.go, srv_cmd);
+                    }
+                } else {
+                    if (threadIdx.x == 0) {
+                        uint32_t go;
+                        do { go = ld_acquire_gpu(srv.go); } while (go == srv_step);
+                        srv_cmd = go;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (srv_cmd == 0xffffffffu) break;
             }
             const bool act = valid_env && a.running;  // finished envs are frozen (reward 0, done 1)
             int action;
             if (io.actions != nullptr) {
-                if (SRV) action = valid_env ? __ldcv(&io.actions[env]) : -1;  // mapped host memory, rewritten every step
+                if (SRV) action = valid_env ? __ldcg(&io.actions[env]) : -1;  // HBM copy, rewritten every step (L2, not L1)
                 else action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else if (MLP) {
                 const int hid = io.mlp.hid, A = io.mlp.n_actions;
@@ -703,14 +720,15 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 const size_t step_bytes =
                     io.obs_dtype == kObsPacked ? (size_t)((s.N + EPW - 1) / EPW) * ((EPW * W * H * 3 + 31) >> 5) * 4
                                                : (size_t)s.N * W * H * 3 * obs_elem_bytes(io.obs_dtype);
-                emit_obs<L>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
-                            (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, tab8,
-                            lane, sub, x, W, H, env0, n_valid, SRV ? (rkind | (done ? 8u : 0u) | (rcnt << 4)) : 0u);
+                emit_obs<L, SRV>(static_cast<char*>(io.obs) + (size_t)k * step_bytes, io.obs_dtype,
+                                 (a.vis && x == a.ax) ? (1u << a.ay) : 0u, r.F, ~r.I & validmask, stream_warp, spread3, tab8,
+                                 lane, sub, x, W, H, env0, n_valid, SRV ? (rkind | (done ? 8u : 0u) | (rcnt << 4)) : 0u);
             }
             if (SRV) {
-                unsigned long long srv_t2 = 0ull;
+                unsigned long long srv_t2 = 0ull, srv_t2b = 0ull;
                 if (blockIdx.x == 0 && threadIdx.x == 0) srv_t2 = global_timer_ns();
                 __syncthreads();  // every warp of the CTA has issued its stores to mapped host memory ...
+                if (blockIdx.x == 0 && threadIdx.x == 0) srv_t2b = global_timer_ns();
                 srv_step += 1u;
                 if (threadIdx.x == 0) {
                     // ... and are ordered before this CTA's arrival at GPU scope.  System-scope fences are expensive (each
@@ -729,7 +747,8 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         const unsigned long long t3 = global_timer_ns();
                         srv.dbg[0] += srv_t1 - srv_t0;
                         srv.dbg[1] += srv_t2 - srv_t1;
-                        srv.dbg[2] += t3 - srv_t2;
+                        srv.dbg[2] += srv_t2b - srv_t2;
+                        srv.dbg[4] += t3 - srv_t2b;
                         srv.dbg[3] += 1ull;
                     }
                 }
@@ -759,13 +778,15 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     }
 }
 
-// 128 registers (16 warps per SM: all 2048 warps of a 4096-env batch resident) measured faster than what ptxas picks
-// when left alone (164: 3.3 instead of 2.3 us per C2 step); the network variant with per-direction hit counters needs more.
+// The C2 kernel must stay at 128 registers (16 warps per SM: all 2048 warps of a 4096-env batch resident; at 164
+// registers a step costs 3.3 instead of 2.3 us).  ptxas lands there by itself and schedules better that way than under an
+// explicit cap (__launch_bounds__(128, 4): 115 registers, 2.52 us per step; A/B on one box, tools/build_variant.sh
+// -DWF_WARP_MINBLOCKS); the build checks the register count (csrc/Makefile, `make check-regs`).
 template <int L, int FB, bool UNI, bool MLP>
-#ifdef WF_WARP_NO_MINBLOCKS  // A/B switch (tools/build_variant.sh): let ptxas pick the register count
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-#else
+#ifdef WF_WARP_MINBLOCKS
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (MLP && !UNI) ? 8 / kWarpsPerBlock : 16 / kWarpsPerBlock)
+#else
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
 #endif
 warp_kernel(DevState s, StepCfg c, WarpIO io) {
     warp_body<L, FB, UNI, MLP, false>(s, c, io, SrvCtl{});
