@@ -756,7 +756,8 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             std::memset(ss.actions, 0, act_bytes);
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), act_bytes));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.actions_dev), ss.actions, 0));
-            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)records * (rec_words + 1) * sizeof(uint32_t), cudaHostAllocMapped));
+            const size_t block_words = (size_t)(kRecordsPerCta * (rec_words + 1) + 31) / 32 * 32;  // one CTA's records, whole lines
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)ctas * block_words * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.dbg_dev), 8 * sizeof(unsigned long long)));

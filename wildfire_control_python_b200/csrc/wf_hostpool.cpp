@@ -26,6 +26,8 @@ struct ExpandJob {
     uint8_t* out;            // [n_envs][env_bits] bytes
     int64_t records, rec_words, env_bits, envs_per_record, n_envs;
     int64_t rec_stride;      // words between records (rec_words, or rec_words + 1 with a status word)
+    int64_t recs_per_block, block_stride;  // session: records come in blocks of recs_per_block (one CTA's), block_stride words
+                                           // apart (whole 128-byte lines); otherwise 1 and rec_stride
     // step-server session (wf_host_session): the records of slice t are complete once flags[16 * t] == seq
     const volatile uint32_t* flags;
     uint32_t seq;
@@ -119,7 +121,8 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
         const int64_t env0 = r * j.envs_per_record;
         const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
         const int64_t bits = nenv * j.env_bits;
-        const uint8_t* in = reinterpret_cast<const uint8_t*>(j.packed + r * j.rec_stride);
+        const uint32_t* rec = j.packed + (r / j.recs_per_block) * j.block_stride + (r % j.recs_per_block) * j.rec_stride;
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(rec);
         uint8_t* out = j.out + env0 * j.env_bits;
 #if defined(__x86_64__)
         if (avx512) expand_avx512(in, out, bits >> 3);
@@ -130,7 +133,7 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
             expand_table(in, out, bits >> 3);
         for (int64_t b = bits & ~(int64_t)7; b < bits; ++b) out[b] = (in[b >> 3] >> (b & 7)) & 1;  // ragged tail
         if (j.rec_stride > j.rec_words) {  // session records: reward / done of the record's envs
-            const uint32_t st = j.packed[r * j.rec_stride + j.rec_words];
+            const uint32_t st = rec[j.rec_words];
             for (int64_t k = 0; k < nenv; ++k) {
                 const uint32_t sk = (st >> (16 * k)) & 0xffffu;
                 if (j.reward) j.reward[env0 + k] = decode_reward(j, sk);
@@ -245,6 +248,7 @@ void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t 
     ExpandJob j{};
     j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
     j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words;
+    j.recs_per_block = 1; j.block_stride = rec_words;
     p->run(j);
 }
 // Session step: thread t waits for flags[16 * t] == seq, then expands records [t * records_per_slice, ...) and decodes
@@ -256,6 +260,7 @@ bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, 
     ExpandJob j{};
     j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
     j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words + 1;
+    j.recs_per_block = 4; j.block_stride = (4 * (rec_words + 1) + 31) / 32 * 32;  // wf_warp.cu: one CTA = 4 warps = 4 records
     j.flags = flags; j.seq = seq; j.records_per_slice = records_per_slice; j.reward = reward; j.done = done;
     j.default_reward = default_reward; j.death_penalty = death_penalty; j.contained_bonus = contained_bonus; j.cells = cells;
     j.timeout_ns = timeout_ns;
