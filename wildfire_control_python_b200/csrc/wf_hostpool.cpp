@@ -159,6 +159,7 @@ public:
         for (auto& th : workers_) th.join();
     }
     int threads() const { return n_; }
+    double first_flag_seconds() const { return first_flag_s_; }  // session jobs: thread 0's accumulated wait for its flag(s)
     // Returns false if a session slice timed out waiting for its completion flag (nothing of that slice was expanded).
     bool run(const ExpandJob& job) {
         job_ = job;
@@ -203,6 +204,7 @@ private:
                 }
             }
             std::atomic_thread_fence(std::memory_order_acquire);
+            if (t == 0) first_flag_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
         expand_records(job_, r0, r1);
     }
@@ -237,6 +239,7 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
     bool stop_ = false;
+    double first_flag_s_ = 0.0;
 };
 
 // C-level hooks used by wf_api.cu
@@ -266,6 +269,7 @@ bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, 
     j.timeout_ns = timeout_ns;
     return p->run(j);
 }
+double hostpool_first_flag_seconds(const HostPool* p) { return p ? p->first_flag_seconds() : 0.0; }
 int hostpool_default_threads() {
     if (const char* v = getenv("WF_HOST_THREADS")) {
         const int n = atoi(v);

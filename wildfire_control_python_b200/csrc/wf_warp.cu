@@ -347,7 +347,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
         int it = io.a_iter0;
         uint32_t ablk[4] = {0u, 0u, 0u, 0u}, ablk_ep = 0xffffffffu, ablk_idx = 0xffffffffu;  // cached ACTION block
         uint32_t srv_step = 0u;  // SRV: steps served by this launch
-        unsigned long long srv_t0 = 0ull, srv_t1 = 0ull;  // CTA 0, thread 0: time stamps of the debug counters
+        unsigned long long srv_t0 = 0ull, srv_t0b = 0ull, srv_t1 = 0ull;  // CTA 0, thread 0: time stamps of the debug counters
         for (int kk = 0; SRV || kk < io.K; ++kk) {
             const int k = SRV ? 0 : kk;  // row of the output arrays
             if (SRV) {
@@ -371,6 +371,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         } else {
                             srv_cmd = srv_step + 1u;
                         }
+                        srv_t0b = global_timer_ns();
                     }
                     __syncthreads();
                     if (srv_cmd != 0xffffffffu) {
@@ -753,12 +754,18 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                     const uint32_t n_in = min((uint32_t)srv.ctas_per_slice, gridDim.x - slice * (uint32_t)srv.ctas_per_slice);
                     const uint32_t old = atomicAdd(&srv.count[slice], 1u);
                     if (old + 1u == n_in * srv_step) {  // the slice's last CTA of this step
+                        const unsigned long long tf = global_timer_ns();
                         __threadfence_system();
                         srv.done[slice * 16u] = srv.seq0 + srv_step;
+                        if (srv.dbg != nullptr) {
+                            atomicAdd(&srv.dbg[5], global_timer_ns() - tf);
+                            atomicAdd(&srv.dbg[6], 1ull);
+                        }
                     }
                     if (blockIdx.x == 0 && srv.dbg != nullptr) {
                         const unsigned long long t3 = global_timer_ns();
-                        srv.dbg[0] += srv_t1 - srv_t0;
+                        srv.dbg[0] += srv_t0b - srv_t0;
+                        srv.dbg[7] += srv_t1 - srv_t0b;
                         srv.dbg[1] += srv_t2 - srv_t1;
                         srv.dbg[2] += srv_t2b - srv_t2;
                         srv.dbg[4] += t3 - srv_t2b;
