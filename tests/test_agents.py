@@ -281,3 +281,54 @@ def test_batched_demonstration_memories(name):
     assert bool((first[..., 1].flatten(1).sum(1) == 1).all()) and bool((first[:, 7, 7, 1] == 1).all())
     assert bool((first[..., 0].flatten(1).sum(1) == 1).all()) and bool(((first[..., 2] == 0).flatten(1).sum(1) == 1).all())
     ag.replay()  # and the memory feeds the learner
+
+
+# ---------------------------------------------------------------------------------------------
+# N1 pinned: the update rule against golden vectors restated from the reference's source and Keras 2's code paths
+# WITHOUT autograd (oracle/gen_n1_fixture.py: per-sample target loop, hand-written gradients, Keras' clipped Adam).
+def _load_n1(name):
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "n1_replay.npz"))
+    return {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+def _check_n1(name, device):
+    cls = getattr(A, name)
+    fx = _load_n1(name)
+    ag = cls(FakeSim(), verbose=False, device=device)
+    keys = sorted(k[3:] for k in fx if k.startswith("w0/"))
+    assert keys == sorted(ag.get_weights())  # dense_1..2 (plain) / dense_1..4 (dueling), Keras names
+    ag.set_weights({k: fx["w0/" + k] for k in keys})
+    with torch.no_grad():  # the target network is a different set of weights
+        for lname, m in ag.target.named_children():
+            m.weight.copy_(torch.as_tensor(fx[f"target/{lname}/kernel:0"]).t())
+            m.bias.copy_(torch.as_tensor(fx[f"target/{lname}/bias:0"]))
+    dev = ag.device
+    for t in (1, 2):
+        b = {k: fx[f"t{t}/batch_{k}"] for k in ("s", "a", "r", "sp", "ap", "d")}
+        batch = (torch.as_tensor(b["s"], dtype=torch.uint8, device=dev).view(-1, 10, 10, 3), torch.as_tensor(b["a"], device=dev).long(),
+                 torch.as_tensor(b["r"], dtype=torch.float32, device=dev), torch.as_tensor(b["sp"], dtype=torch.uint8, device=dev).view(-1, 10, 10, 3),
+                 torch.as_tensor(b["ap"], device=dev).long(), torch.as_tensor(b["d"], device=dev).bool())
+        targets = ag.replay_targets(batch).cpu().numpy()
+        assert np.allclose(targets, fx[f"t{t}/targets"], rtol=2e-5, atol=2e-3), (name, t, np.abs(targets - fx[f"t{t}/targets"]).max())
+        loss = ag.fit_batch(batch)
+        assert loss == pytest.approx(float(fx[f"t{t}/loss"]), rel=1e-4)
+        got = ag.get_weights()
+        for k in keys:
+            want = fx[f"t{t}/w/{k}"]
+            have = got[k][::16] if got[k].shape[0] == 300 else got[k]
+            # one step moves a weight by at most ~lr = 5e-3: 2e-6 absolute is 0.04 % of a step
+            assert np.allclose(have, want, rtol=0, atol=2e-6), (name, t, k, np.abs(have - want).max())
+
+
+@pytest.mark.parametrize("name", ["DQN", "DQN_SARSA", "DQN_DUEL", "DQN_BOTH"])
+def test_replay_matches_the_keras_restatement_fixture(name):
+    """DQN.replay / DQN_SARSA.replay on DQN.make_network / DQN_DUEL.make_network with Adam(lr, clipvalue=1), two
+    consecutive updates: targets, loss and every updated weight against tests/golden/n1_replay.npz (float32 CPU)."""
+    _check_n1(name, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["DQN", "DQN_SARSA", "DQN_DUEL", "DQN_BOTH"])
+def test_replay_matches_the_keras_restatement_fixture_on_cuda(name):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _check_n1(name, "cuda")

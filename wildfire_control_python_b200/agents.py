@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import json
 import os
+import math
 import random
 import time
 
@@ -132,6 +133,34 @@ class _DuelNet(nn.Module):
         return val + (adv - adv.mean(dim=1, keepdim=True))
 
 
+class KerasAdam(torch.optim.Optimizer):
+    """``keras.optimizers.Adam(lr, clipvalue)`` of Keras 2 (the reference's ``Adam(lr=self.alpha, clipvalue=1)``,
+    DQN.py:227-230), update for update: every gradient element is clipped to [-clipvalue, clipvalue], then
+    ``lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t)``, ``p -= lr_t * m / (sqrt(v) + epsilon)`` with
+    ``epsilon = K.epsilon() = 1e-7`` added to the UNCORRECTED second moment (``torch.optim.Adam`` adds its epsilon after
+    the bias correction, i.e. an effective epsilon sqrt(1 - beta_2^t) times smaller).  Pinned by tests/golden/n1_replay.npz."""
+
+    def __init__(self, params, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipvalue=None):
+        super().__init__(params, dict(lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, clipvalue=clipvalue))
+
+    @torch.no_grad()
+    def step(self):
+        for group in self.param_groups:
+            b1, b2 = group["beta_1"], group["beta_2"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["t"], st["m"], st["v"] = 0, torch.zeros_like(p), torch.zeros_like(p)
+                g = p.grad if group["clipvalue"] is None else p.grad.clamp(-group["clipvalue"], group["clipvalue"])
+                st["t"] += 1
+                st["m"].mul_(b1).add_(g, alpha=1.0 - b1)
+                st["v"].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+                lr_t = group["lr"] * math.sqrt(1.0 - b2 ** st["t"]) / (1.0 - b1 ** st["t"])
+                p.addcdiv_(st["m"], st["v"].sqrt().add_(group["epsilon"]), value=-lr_t)
+
+
 def _keras_init(net):
     """Keras Dense defaults: glorot_uniform kernel, zero bias."""
     for m in net.modules():
@@ -183,8 +212,8 @@ class DQN:
         self.model = self.make_network()
         self.target = self.make_network()
         self.target.load_state_dict(self.model.state_dict())
-        # Adam(lr=alpha, clipvalue=1) with Keras' epsilon; loss = mse (DQN.py:227-230)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.alpha, eps=1e-7)
+        # Adam(lr=alpha, clipvalue=1), Keras' update rule; loss = mse (DQN.py:227-230)
+        self.optimizer = KerasAdam(self.model.parameters(), lr=self.alpha, clipvalue=1.0)
 
         if self.verbose:
             width, height = self.METADATA["width"], self.METADATA["height"]
@@ -288,13 +317,16 @@ class DQN:
         return pred
 
     def replay(self):  # DQN.py:156-185
-        batch = self.memory.sample(self.METADATA["batch_size"])
+        return self.fit_batch(self.memory.sample(self.METADATA["batch_size"]))
+
+    def fit_batch(self, batch):
+        """``self.model.fit(states, predictions, epochs=1)`` on one batch of transitions (DQN.py:181-185): with the
+        reference's batch_size = 32 = Keras' default mini-batch that is exactly one clipped-Adam update on the MSE."""
         targets = self.replay_targets(batch)
         loss = nn.functional.mse_loss(self.model(batch[0].float()), targets)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        nn.utils.clip_grad_value_(self.model.parameters(), 1.0)  # Adam(clipvalue=1)
-        self.optimizer.step()
+        self.optimizer.step()  # clips every gradient element to [-1, 1] first (clipvalue=1)
         return float(loss.detach())
 
     def choose_action(self, state, eps=None):  # DQN.py:188-196

@@ -378,7 +378,16 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
                         const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
                         int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
-                        for (int j = threadIdx.x; j < n16; j += blockDim.x) dst[j] = __ldcv(src + j);
+                        // all of a thread's loads are issued before its first store: one PCIe round trip, not one per chunk
+                        for (int j0 = threadIdx.x; j0 < n16; j0 += 8 * blockDim.x) {
+                            int4 v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (j0 + u * (int)blockDim.x < n16) v[u] = __ldcv(src + j0 + u * blockDim.x);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (j0 + u * (int)blockDim.x < n16) dst[j0 + u * blockDim.x] = v[u];
+                        }
                         __threadfence();
                     }
                     __syncthreads();
