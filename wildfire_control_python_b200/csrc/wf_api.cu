@@ -746,9 +746,12 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             if (!e->pool) e->pool = hostpool_create(hostpool_default_threads());
             constexpr int kRecordsPerCta = 4;  // WF_WARPS_PER_BLOCK warps, one record each
             const int64_t ctas = (records + kRecordsPerCta - 1) / kRecordsPerCta;
-            int slices = std::min<int64_t>(std::min(hostpool_threads(e->pool), kSessMaxSlices), ctas);
-            if (const char* v = getenv("WF_SESSION_SLICES"))  // experiments: fewer completion flags than host threads
-                if (atoi(v) >= 1) slices = std::min(slices, atoi(v));
+            // Completion flags per step.  Every flag costs its slice's last CTA a system-scope fence (5-7 us: the GPU's
+            // writes to host memory are drained), and the fences do not overlap, so splitting the batch to start expanding
+            // early does not pay: ONE flag measured best (25.8 us per C2 step against 27.3 with 2 and 28.3 with 12).
+            int slices = 1;
+            if (const char* v = getenv("WF_SESSION_SLICES"))
+                if (atoi(v) >= 1) slices = (int)std::min<int64_t>(std::min(atoi(v), kSessMaxSlices), ctas);
             ss.ctas_per_slice = (int)((ctas + slices - 1) / slices);
             ss.slices = (int)((ctas + ss.ctas_per_slice - 1) / ss.ctas_per_slice);
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));

@@ -73,6 +73,7 @@ __device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gs
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(a), "l"(gsrc), "r"(valid ? 4 : 0) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -1048,6 +1049,12 @@ __device__ __forceinline__ void fused_slice(const Env& e, const DevState& s, con
             }
         } else if (lane < nq) {
             mine = read_entry(lane);
+#ifndef WF_FUSED_NO_PREFETCH
+            // the active path's inputs start their way from HBM now and are used after the observation block below
+            if (mine.B) prefetch_l2(e.FU + (size_t)mine.wi * kFuelRec);
+            prefetch_l2(e.hits + ((size_t)mine.x * H + 32 * mine.w));
+            prefetch_l2(e.hits + ((size_t)mine.x * H + 32 * mine.w) + 16);
+#endif
         }
         // ---- World.get_state of the previous step: bit streams of the group's 128 words
         if (do_obs) {
@@ -1070,17 +1077,27 @@ __device__ __forceinline__ void fused_slice(const Env& e, const DevState& s, con
         }
         __syncwarp();  // every lane is done with the staged inputs
         if (gi + nwarps < n128) issue(gi + nwarps);
+#ifdef WF_FUSED_NO_PREFETCH
         if (mine.wi >= 0) run_entry(mine);
+#endif
         if (do_obs) {
             uint4* o = reinterpret_cast<uint4*>(obs_step + (((size_t)e.env * W) * H + (size_t)32 * g) * 3);
 #pragma unroll 8
             for (int it = 0; it < 24; ++it) {
                 const int cidx = it * 32 + lane;  // 16-byte chunk of the warp's 12288 bytes = 16 stream bits
                 const uint32_t bits = stage16[cidx];
+#ifdef WF_OBS_ALU  // bits -> bytes with a multiply and a mask per 4 bytes instead of two 8-byte table look-ups
+                __stcs(&o[cidx], make_uint4(((bits & 15u) * 0x00204081u) & 0x01010101u, (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u,
+                                            (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u, ((bits >> 12) * 0x00204081u) & 0x01010101u));
+#else
                 const uint2 lo = tab8[bits & 255u], hi = tab8[bits >> 8];
                 __stcs(&o[cidx], make_uint4(lo.x, lo.y, hi.x, hi.y));  // streamed: not read again by this kernel
+#endif
             }
         }
+#ifndef WF_FUSED_NO_PREFETCH
+        if (mine.wi >= 0) run_entry(mine);
+#endif
         __syncwarp();
     }
     if (do_tick) {
