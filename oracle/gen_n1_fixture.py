@@ -2,7 +2,7 @@
 
 Keras / TensorFlow are not installable here, so the reference's `replay` cannot be run; this script restates, in plain
 NumPy float64 and WITHOUT autograd, exactly what one `replay()` of each reference learner computes, from the reference's
-source and from the Keras 2 code paths it calls, and writes the result as tests/golden/n1_replay.npz:
+source and from the Keras 2 code paths it calls, and writes the result as tests/golden/agents/n1_replay.npz:
 
   targets      DQN.replay, DQN.py:156-185 (max bootstrap) / DQN_SARSA.replay, DQN_SARSA.py:103-132 (Q(s', a')):
                per sample `prediction = target.predict(state)[0]; prediction[action] = reward if done else
@@ -145,7 +145,7 @@ def main():
             out[f"{name}/t{t}/loss"] = np.float64(loss)
             for k, x in w.items():  # the big first-layer kernels: every 16th input row (the fixture stays small)
                 out[f"{name}/t{t}/w/{k}"] = (x[::16] if x.shape[0] == N_IN else x).astype(np.float32)
-    path = os.path.join(ROOT, "tests", "golden", "n1_replay.npz")
+    path = os.path.join(ROOT, "tests", "golden", "agents", "n1_replay.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
 

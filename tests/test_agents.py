@@ -287,7 +287,7 @@ def test_batched_demonstration_memories(name):
 # N1 pinned: the update rule against golden vectors restated from the reference's source and Keras 2's code paths
 # WITHOUT autograd (oracle/gen_n1_fixture.py: per-sample target loop, hand-written gradients, Keras' clipped Adam).
 def _load_n1(name):
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "n1_replay.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "agents", "n1_replay.npz"))
     return {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
 
 
@@ -323,7 +323,7 @@ def _check_n1(name, device):
 @pytest.mark.parametrize("name", ["DQN", "DQN_SARSA", "DQN_DUEL", "DQN_BOTH"])
 def test_replay_matches_the_keras_restatement_fixture(name):
     """DQN.replay / DQN_SARSA.replay on DQN.make_network / DQN_DUEL.make_network with Adam(lr, clipvalue=1), two
-    consecutive updates: targets, loss and every updated weight against tests/golden/n1_replay.npz (float32 CPU)."""
+    consecutive updates: targets, loss and every updated weight against tests/golden/agents/n1_replay.npz (float32 CPU)."""
     _check_n1(name, "cpu")
 
 

@@ -338,15 +338,7 @@ def test_trajectories_do_not_depend_on_sharding():
     assert all(a[k] == b[k] + c[k] for k in a)
 
 
-@pytest.mark.parametrize("T,CS", [(128, 1), (128, 2), (256, 4), (128, 8), (512, 2)])
-@pytest.mark.parametrize("cfg", [dict(width=64, height=64, seed=701, make_rivers=True, wind="random", extra_ignitions=3),
-                                 dict(width=100, height=70, seed=702, wind=[0.85, (1, 0)], extra_ignitions=6, a_speed=2),
-                                 dict(width=128, height=128, seed=703, allow_dig_toggle=True, n_actions=6, extra_ignitions=4)],
-                         ids=["64_rivers", "100x70_aspeed2", "128_toggle"])
-def test_tile_cluster_geometries_match_oracle(monkeypatch, T, CS, cfg):
-    """The tile family splits one env over a thread-block cluster of CS CTAs x T threads (chosen from
-    the batch size in production): every split must give the oracle's trajectory -- walk-policy
-    rollout with auto-reset (containments, re-floods of the reach plane, in-kernel resets)."""
+def _tile_geometry_case(monkeypatch, T, CS, cfg):
     monkeypatch.setenv("WF_TILE_T", str(T))
     monkeypatch.setenv("WF_TILE_CS", str(CS))
     N, K = 5, 150
@@ -368,6 +360,30 @@ def test_tile_cluster_geometries_match_oracle(monkeypatch, T, CS, cfg):
                     o = e.reset()
                 assert np.array_equal(obs[k, i], o), f"{policy} env {i} step {k}: obs"
         compare_states(f"after {policy} rollout", gpu, orc)
+
+
+@pytest.mark.parametrize("T,CS", [(128, 1), (128, 2), (256, 4), (128, 8), (512, 2)])
+@pytest.mark.parametrize("cfg", [dict(width=64, height=64, seed=701, make_rivers=True, wind="random", extra_ignitions=3),
+                                 dict(width=100, height=70, seed=702, wind=[0.85, (1, 0)], extra_ignitions=6, a_speed=2),
+                                 dict(width=128, height=128, seed=703, allow_dig_toggle=True, n_actions=6, extra_ignitions=4)],
+                         ids=["64_rivers", "100x70_aspeed2", "128_toggle"])
+def test_tile_cluster_geometries_match_oracle(monkeypatch, T, CS, cfg):
+    """The tile family splits one env over a thread-block cluster of CS CTAs x T threads (chosen from
+    the batch size in production): every split must give the oracle's trajectory -- walk-policy
+    rollout with auto-reset (containments, re-floods of the reach plane, in-kernel resets)."""
+    _tile_geometry_case(monkeypatch, T, CS, cfg)
+
+
+@pytest.mark.parametrize("T,CS", [(128, 1), (128, 2), (256, 4), (256, 1)])
+@pytest.mark.parametrize("cfg", [dict(width=128, height=128, seed=711, allow_dig_toggle=True, n_actions=6, extra_ignitions=4),
+                                 dict(width=128, height=128, seed=712, make_rivers=True, wind="random", a_speed=2, extra_ignitions=3),
+                                 dict(width=256, height=128, seed=713, wind=[0.85, (1, 0)], extra_ignitions=9, fuel=40)],
+                         ids=["128_toggle", "128_rivers_aspeed2", "256x128_wide_fuel40"])
+def test_tile_fused_pass_matches_oracle(monkeypatch, T, CS, cfg):
+    """WF_TILE_FUSED=1: the tick of step k and the observation of step k-1 in one cp.async-staged sweep (grids whose
+    slices are whole 128-word groups).  Same check as the geometry sweep above."""
+    monkeypatch.setenv("WF_TILE_FUSED", "1")
+    _tile_geometry_case(monkeypatch, T, CS, cfg)
 
 
 def test_burning_border_point_is_not_its_own_goal():

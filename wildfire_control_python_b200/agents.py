@@ -138,7 +138,7 @@ class KerasAdam(torch.optim.Optimizer):
     DQN.py:227-230), update for update: every gradient element is clipped to [-clipvalue, clipvalue], then
     ``lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t)``, ``p -= lr_t * m / (sqrt(v) + epsilon)`` with
     ``epsilon = K.epsilon() = 1e-7`` added to the UNCORRECTED second moment (``torch.optim.Adam`` adds its epsilon after
-    the bias correction, i.e. an effective epsilon sqrt(1 - beta_2^t) times smaller).  Pinned by tests/golden/n1_replay.npz."""
+    the bias correction, i.e. an effective epsilon sqrt(1 - beta_2^t) times smaller).  Pinned by tests/golden/agents/n1_replay.npz."""
 
     def __init__(self, params, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipvalue=None):
         super().__init__(params, dict(lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, clipvalue=clipvalue))

@@ -36,7 +36,7 @@ namespace wf {
 struct TileState {
     int32_t P_S0, P_S1, P_R;
     int32_t T, CS;  // threads per CTA, CTAs per cluster (one cluster per env)
-    bool no_fused;  // WF_TILE_NO_FUSED=1 (read by wf_create)
+    bool fused;     // WF_TILE_FUSED=1 (read by wf_create): the fused pass for the shapes that allow it
 };
 
 struct TilePar {  // launch constants, precomputed on the host so the kernel re-reads them from the constant bank
@@ -1049,8 +1049,9 @@ __device__ __forceinline__ void fused_slice(const Env& e, const DevState& s, con
             }
         } else if (lane < nq) {
             mine = read_entry(lane);
-#ifndef WF_FUSED_NO_PREFETCH
-            // the active path's inputs start their way from HBM now and are used after the observation block below
+#ifdef WF_FUSED_PREFETCH
+            // (experiment, measured SLOWER on C4: 51.1 vs 47.5 us per step) the active path's inputs start their way from
+            // HBM now and are used after the observation block below
             if (mine.B) prefetch_l2(e.FU + (size_t)mine.wi * kFuelRec);
             prefetch_l2(e.hits + ((size_t)mine.x * H + 32 * mine.w));
             prefetch_l2(e.hits + ((size_t)mine.x * H + 32 * mine.w) + 16);
@@ -1077,7 +1078,7 @@ __device__ __forceinline__ void fused_slice(const Env& e, const DevState& s, con
         }
         __syncwarp();  // every lane is done with the staged inputs
         if (gi + nwarps < n128) issue(gi + nwarps);
-#ifdef WF_FUSED_NO_PREFETCH
+#ifndef WF_FUSED_PREFETCH
         if (mine.wi >= 0) run_entry(mine);
 #endif
         if (do_obs) {
@@ -1095,7 +1096,7 @@ __device__ __forceinline__ void fused_slice(const Env& e, const DevState& s, con
 #endif
             }
         }
-#ifndef WF_FUSED_NO_PREFETCH
+#ifdef WF_FUSED_PREFETCH
         if (mine.wi >= 0) run_entry(mine);
 #endif
         __syncwarp();
@@ -1533,7 +1534,7 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     t->P_S1 = P_FU0 + 1;
     t->P_R = P_FU0 + 2;
     choose_geometry(s, t->T, t->CS);
-    t->no_fused = env_int("WF_TILE_NO_FUSED", 0) != 0;
+    t->fused = env_int("WF_TILE_FUSED", 0) != 0;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = set_smem_attr<5, 1, false>();
     if (e == cudaSuccess) e = set_smem_attr<5, 4, false>();
@@ -1608,11 +1609,13 @@ cudaError_t launch_tile_family(TileState* t, const DevState& s, const StepCfg& c
                                cudaStream_t stream, int64_t* launches) {
     *launches += 1;
     const bool v4 = (s.HW % 4 == 0);
-    // The fused pass (tick of step k + observation of step k-1 in one sweep): rollouts on grids whose slices are
-    // whole 128-word groups of full-width words, uint8 observations.  WF_TILE_NO_FUSED=1: the two-phase path (A/B).
+    // The fused pass (tick of step k + observation of step k-1 in one cp.async-staged sweep): rollouts on grids whose
+    // slices are whole 128-word groups of full-width words, uint8 observations.  Opt-in (WF_TILE_FUSED=1): bit-exact
+    // (tests/test_fullsize_gpu.py runs the production geometries both ways) but not faster than the two-phase path --
+    // A/B on one box, r02: C4 47.5-49.5 vs 47.2-48.7 us per step, C5 76/91/94 vs 76/90/94 -- see DESIGN.md section 8.
     const int nwords = s.W * s.HW, per = (nwords + t->CS - 1) / t->CS, wpc = (per + 31) / 32 * 32;
     const bool fused = v4 && !io.reset_mode && (s.H % 32) == 0 && (wpc % 128) == 0 && (nwords % wpc) == 0 &&
-                       (io.obs == nullptr || io.obs_dtype == WF_OBS_U8) && !t->no_fused;
+                       (io.obs == nullptr || io.obs_dtype == WF_OBS_U8) && t->fused;
     if (fused) return s.FB == 5 ? launch<5, 4, true>(t, s, c, io, stream) : launch<8, 4, true>(t, s, c, io, stream);
     if (s.FB == 5) return v4 ? launch<5, 4>(t, s, c, io, stream) : launch<5, 1>(t, s, c, io, stream);
     return v4 ? launch<8, 4>(t, s, c, io, stream) : launch<8, 1>(t, s, c, io, stream);

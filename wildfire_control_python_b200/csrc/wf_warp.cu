@@ -346,6 +346,8 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
         // ---------------- K x ForestFire.step(action) ----------------
         int it = io.a_iter0;
         uint32_t ablk[4] = {0u, 0u, 0u, 0u}, ablk_ep = 0xffffffffu, ablk_idx = 0xffffffffu;  // cached ACTION block
+        uint32_t reach = 0u;    // row x of the reach mask, valid while reach_ok (group-uniform)
+        bool reach_ok = false;
         uint32_t srv_step = 0u;  // SRV: steps served by this launch
         unsigned long long srv_t0 = 0ull, srv_t0b = 0ull, srv_t1 = 0ull;  // CTA 0, thread 0: time stamps of the debug counters
         for (int kk = 0; SRV || kk < io.K; ++kk) {
@@ -532,19 +534,49 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 const int src_lane = sub * L + (inb ? nx : 0);
                 const uint32_t wrow = __shfl_sync(FULL, r.WT, src_lane);
                 const uint32_t frow = __shfl_sync(FULL, r.F, src_lane);
+                bool do_dig = false;  // Agent.dig (environment.py:123-133) on cell (dgx, dgy) this step
+                int dgx = 0, dgy = 0;
                 if (mv) {
                     a.vis = 0;  // agent_pos cleared before the validity test (Q1)
                     if (inb && !((wrow >> ny) & 1u)) {
                         a.ax = nx; a.ay = ny; a.vis = 1;
                         const bool onfire = (frow >> ny) & 1u;
-                        if (a.digging && !onfire) dig(r, x, nx, ny);
+                        if (a.digging && !onfire) { do_dig = true; dgx = nx; dgy = ny; }
                         if (onfire) a.dead = 1;
                     }
                 }
                 if (act && a.alive && c.allow_dig_toggle && action == 4) {
                     a.digging ^= 1;
-                    if (a.digging) dig(r, x, a.ax, a.ay);
+                    if (a.digging) { do_dig = true; dgx = a.ax; dgy = a.ay; }
                 }
+                // The reach mask (cells with a finite path to a finite border point: what the A* searches of get_reward
+                // establish) is kept across steps.  A dug cell simply leaves it when its free 4-neighbours stay connected
+                // through the ring of the 8 cells around it ("simple point"); only otherwise is it flooded again.
+                if (__any_sync(FULL, do_dig && reach_ok)) {
+                    const uint32_t free_now = ~r.I & validmask;
+                    const int base = sub * L;
+                    const uint32_t f0 = __shfl_sync(FULL, free_now, base + dgx);
+                    uint32_t fm = __shfl_sync(FULL, free_now, base + max(dgx - 1, 0));
+                    uint32_t fp = __shfl_sync(FULL, free_now, base + min(dgx + 1, L - 1));
+                    const uint32_t rr = __shfl_sync(FULL, reach, base + dgx);
+                    if (do_dig && reach_ok && ((f0 >> dgy) & 1u) && ((rr >> dgy) & 1u)) {
+                        if (dgx == 0) fm = 0u;
+                        if (dgx + 1 >= W) fp = 0u;
+                        if (x == dgx) reach &= ~(1u << dgy);
+                        const int ym = dgy - 1, yp = dgy + 1;
+                        auto bit = [&](uint32_t row, int y) -> uint32_t { return (y >= 0 && y < H) ? (row >> y) & 1u : 0u; };
+                        // ring of the 8 neighbours, clockwise from N: N NE E SE S SW W NW (N = y - 1, E = x + 1)
+                        const uint32_t ring = bit(f0, ym) | bit(fp, ym) << 1 | bit(fp, dgy) << 2 | bit(fp, yp) << 3 | bit(f0, yp) << 4 |
+                                              bit(fm, yp) << 5 | bit(fm, dgy) << 6 | bit(fm, ym) << 7;
+                        const uint32_t rot1 = ((ring << 1) | (ring >> 7)) & 255u, rot2 = ((ring << 2) | (ring >> 6)) & 255u;
+                        const int n4 = __popc(ring & 0x55u);
+                        int groups = n4 - __popc(ring & rot1 & rot2 & 0x55u);  // a 4-neighbour joined to the previous one through the corner
+                        if (n4 == 4 && groups == 0) groups = 1;
+                        const bool on_seed = dgx == 0 || dgx == H - 1 || dgy == 0 || dgy == H - 1;  // a literal border point
+                        if (on_seed ? n4 > 0 : groups > 1) reach_ok = false;
+                    }
+                }
+                if (do_dig) dig(r, x, dgx, dgy);
             }
             // ---- fire tick: ForestFire.update, forest_fire.py:85-106 (every a_speed steps)
             it -= 1;
@@ -673,13 +705,22 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 // finite border point or connected to one -- where a burning border point does not count for ITSELF.
                 // Burning border points exist off the rim only (W > H maps: the literal [HEIGHT-1, y] column, else
                 // fire_at_border has switched the search off), so the second flood is normally skipped.
-                const uint32_t from_cold = flood(seeds & ~r.B);
-                uint32_t touch = r.B & neighbours(from_cold | seeds);
+                uint32_t touch;
                 if (__any_sync(FULL, check && (seeds & r.B) != 0u)) {  // (`check`: the warp's other env may burn at its rim)
+                    const uint32_t from_cold = flood(seeds & ~r.B);
+                    touch = r.B & neighbours(from_cold | seeds);
                     const uint32_t from_burning = flood(seeds & r.B);
                     // (two burning border points joined only through unburnt cells, with no other burning cell and no
                     //  cold border point in their pocket, would still count as contained here: not reproduced)
                     touch |= r.B & ~seedmask & neighbours(from_burning);
+                } else {
+                    // the usual case: no border point burns, so the search goals are all finite border points and the
+                    // region connected to them is the persistent reach mask (flooded when it is not valid)
+                    if (__any_sync(FULL, check && !reach_ok)) {
+                        reach = flood(seeds);
+                        reach_ok = true;
+                    }
+                    touch = r.B & neighbours(reach);
                 }
                 contained = !group_bits(__ballot_sync(FULL, touch != 0u));
             }
@@ -728,6 +769,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             if (c.auto_reset && act && done) {
                 reset_rows<L, FB, UNI>(r, a, s, c, nullptr, env, x, validmask);
                 a.refresh_wind(s.wind);
+                reach_ok = false;
             }
             __syncwarp();
             if (io.obs != nullptr) {
