@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Turn the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-usage: python profiles/summarize.py r01
+usage: python profiles/summarize.py r02
 Reads (whatever exists):
-  gpurun_out/launches_c2.csv, launches_c4.csv     `ncu --metrics gpu__time_duration.sum ...` launch lists
-  gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 256 steps/launch; WF_C2_KEY names the ncu_traffic key)
-  gpurun_out/prof_c4.ncu-rep, prof_c5.ncu-rep     captures of wf::tile_rollout_kernel (c4 / c5, 16 steps/launch)
-Writes profiles/<round>_*.{csv,txt,json} and profiles/ncu_traffic.json (read by bench.py).
+  gpurun_out/launches_bench.csv (and launches_c2/c4/c5.csv)   `ncu --metrics gpu__time_duration.sum ...` launch lists
+  gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 256 steps per launch)
+  gpurun_out/prof_c4.ncu-rep, prof_c5.ncu-rep     captures of wf::tile_rollout_kernel (c4 / c5, 16 steps per launch)
+Writes profiles/<round>_*.{csv,txt,json} and profiles/ncu_traffic.json (DRAM bytes per STEP, read by bench.py).
 """
 import collections
 import csv
@@ -81,19 +81,19 @@ def main(rnd):
     tpath = os.path.join(PR, "ncu_traffic.json")
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath))
-    for name in ("c2", "c4", "c5"):
+    for name in ("bench", "c2", "c4", "c5"):
         ls = launch_summary(name, rnd)
         if ls:
             summary[f"{name}_launch_list"] = ls
-    for rep, tag, key in (("prof_c2.ncu-rep", "c2_warp_kernel", os.environ.get("WF_C2_KEY", "c2_chunk256")), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4_chunk16"),
-                          ("prof_c5.ncu-rep", "c5_tile_rollout", "c5_chunk16")):
+    for rep, tag, key, steps in (("prof_c2.ncu-rep", "c2_warp_kernel", "c2", 256), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4", 16),
+                                 ("prof_c5.ncu-rep", "c5_tile_rollout", "c5", 16)):
         ks = rep_summary(rep, rnd, tag)
         if ks:
             summary[tag] = ks
-            if key and "dram__bytes_read.sum" in ks[0]:
-                traffic[key] = sum(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]) for k in ks) / len(ks)
-    for stale in ("c4_tick", "c4_obs", "c4_chunk1"):  # kernels of the earlier multi-launch tile pipeline
-        traffic.pop(stale, None)
+            if "dram__bytes_read.sum" in ks[0]:
+                per_launch = sum(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]) for k in ks) / len(ks)
+                traffic[key] = {"dram_bytes_per_step": per_launch / steps,
+                                "source": f"profiles/{rnd}_{tag}_details.txt ({steps}-step launch, ncu --set full)"}
     json.dump(summary, open(os.path.join(PR, f"{rnd}_summary.json"), "w"), indent=1)
     json.dump(traffic, open(tpath, "w"), indent=1)
     print(json.dumps(traffic, indent=1))

@@ -338,6 +338,38 @@ def test_trajectories_do_not_depend_on_sharding():
     assert all(a[k] == b[k] + c[k] for k in a)
 
 
+@pytest.mark.parametrize("policy", ["mlp", "walk"])
+def test_device_policies_do_not_depend_on_sharding(policy):
+    """BASELINE configs[2] shards 65 536 envs over 8 GPUs with the policy evaluated inside the step kernel: every env's
+    trajectory (actions, rewards, dones, observations) must be the same whichever shard -- and whichever GPU, when the
+    box has more than one -- it lands on.  Uneven shards, so that the warp packing (two envs per warp) differs too."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    cfg = dict(width=14, height=14, seed=905, auto_reset=True)
+    n_dev = torch.cuda.device_count()
+    cuts = [0, 21, 42, 64]
+    whole = BatchedForestFire(64, device="cuda:0", **cfg)
+    shards = [BatchedForestFire(cuts[i + 1] - cuts[i], env_id_base=cuts[i], device=f"cuda:{i % n_dev}", **cfg) for i in range(3)]
+    envs = [whole] + shards
+    if policy == "mlp":
+        g = torch.Generator().manual_seed(5)
+        w1, b1 = torch.randn(588, 50, generator=g) * 0.3, torch.randn(50, generator=g) * 0.1
+        w2, b2 = torch.randn(50, 4, generator=g) * 0.5, torch.randn(4, generator=g) * 0.1
+        for e in envs:
+            e.set_policy_mlp(w1, b1, w2, b2, eps=0.1)
+    obs0 = [e.reset() for e in envs]
+    for i, sh in enumerate(shards):
+        assert torch.equal(obs0[0][cuts[i]:cuts[i + 1]].cpu(), obs0[1 + i].cpu())
+    for _ in range(3):  # three launches: the policy's state (episode, step, hidden pre-activations) carries over
+        outs = [e.rollout(70, policy=policy, return_actions=True) for e in envs]
+        for i, sh in enumerate(shards):
+            for j in range(4):  # obs, reward, done, actions
+                assert torch.equal(outs[0][j][:, cuts[i]:cuts[i + 1]].cpu(), outs[1 + i][j].cpu()), (policy, i, j)
+    assert int(outs[0][2].sum()) > 0  # episodes ended and were reset inside the kernel
+    tot = whole.stats()
+    parts = [sh.stats() for sh in shards]
+    assert all(tot[k] == sum(p[k] for p in parts) for k in tot)
+
+
 def _tile_geometry_case(monkeypatch, T, CS, cfg):
     monkeypatch.setenv("WF_TILE_T", str(T))
     monkeypatch.setenv("WF_TILE_CS", str(CS))
