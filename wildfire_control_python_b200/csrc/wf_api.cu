@@ -777,19 +777,10 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
         }
     }
     volatile uint32_t* ctl = ss.ctl;
+    std::memcpy(ss.actions, actions_host, (size_t)s.N * sizeof(int32_t));
     ss.seq += 1u;
-    {   // the request: every action word carries the step's tag, so the message needs no separate doorbell (wf_warp.cu)
-        const uint32_t tag = (ss.seq & 0xffffffu) << 8;
-        const int n_pad = (s.N + 3) / 4 * 4;
-        uint32_t* msg = reinterpret_cast<uint32_t*>(ss.actions);
-        for (int i = 0; i < s.N; ++i) {
-            const int32_t a = actions_host[i];
-            msg[i] = tag | ((a >= 0 && a < 255) ? (uint32_t)a : 255u);  // anything else is "no action" (forest_fire.py:34-39)
-        }
-        for (int i = s.N; i < n_pad; ++i) msg[i] = tag | 255u;
-    }
     std::atomic_thread_fence(std::memory_order_release);
-    ctl[0] = ss.seq;  // (control word: informational unless it says park)
+    ctl[0] = ss.seq;  // ring
     ss.steps += 1;
     const int64_t rps = (int64_t)ss.ctas_per_slice * 4;
     const auto t_start = std::chrono::steady_clock::now();

@@ -17,11 +17,10 @@ struct MlpPolicy {
 // Step-server session (wf_host_session): the warp kernel stays resident and is driven from the host through
 // flags in mapped page-locked memory -- no launch and no stream synchronise per step.
 struct SrvCtl {
-    volatile uint32_t* doorbell;  // mapped host, host -> GPU: control word (0xffffffff: park); the step request itself is the
-                                  // action message: word i of actions_host = (sequence number & 0xffffff) << 8 | action code
+    volatile uint32_t* doorbell;  // mapped host, host -> GPU: sequence number of the step requested (0xffffffff: park)
     volatile uint32_t* parked;    // mapped host, GPU -> host: the launch's generation, once the kernel has decided to exit
     volatile uint32_t* done;      // mapped host, GPU -> host: [slices] flags 16 words apart = sequence number completed
-    const int32_t* actions_host;  // mapped host [N, padded to 4]: tagged action words (code 0..254, 255 = no action)
+    const int32_t* actions_host;  // mapped host [N, padded to 4]: written by wf_step_host before it rings
     int32_t* actions_dev;         // HBM [N, padded to 4]: CTA 0's copy of it, what the warps read (WarpIO::actions)
     uint32_t* go;                 // device: master CTA -> every CTA: index of the step to run (1, 2, ...), 0xffffffff = exit
     uint32_t* count;              // device: [slices] arrival counters

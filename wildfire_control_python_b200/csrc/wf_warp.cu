@@ -354,57 +354,44 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             const int k = SRV ? 0 : kk;  // row of the output arrays
             if (SRV) {
                 if (blockIdx.x == 0) {
-                    // CTA 0 brings the step's actions from the mapped host buffer into HBM (coalesced 16-byte loads, all of a
-                    // thread's loads in flight together; every warp fetching its own action from host memory was 2048 small
-                    // PCIe reads, ~80 us per step) and only then releases the other CTAs.  The message is its own doorbell:
-                    // every word carries the step's 24-bit tag next to the action code, so the CTA simply re-reads the buffer
-                    // until every word shows the tag -- ONE PCIe round trip after the host's stores land, instead of one for
-                    // a doorbell and one for the data.  Thread 0 also watches the control word (park request) and the clock.
-                    const uint32_t want_tag = (srv.seq0 + srv_step + 1u) & 0xffffffu;
-                    const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
-                    const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
-                    int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
-                    const unsigned long long t0 = global_timer_ns();
-                    if (threadIdx.x == 0) srv_t0 = t0;
-                    auto tagged = [&](const int4& v) {
-                        return ((uint32_t)v.x >> 8) == want_tag && ((uint32_t)v.y >> 8) == want_tag && ((uint32_t)v.z >> 8) == want_tag &&
-                               ((uint32_t)v.w >> 8) == want_tag;
-                    };
-                    auto code = [](int w) { const int a8 = w & 255; return a8 == 255 ? -1 : a8; };  // 255 = "no action"
-                    for (int j0 = threadIdx.x; j0 - (int)threadIdx.x < n16; j0 += 8 * blockDim.x) {  // (uniform trip count)
+                    // CTA 0: thread 0 waits for the doorbell, then the whole CTA brings the step's actions from the mapped
+                    // host buffer into HBM with coalesced 16-byte loads (one read over PCIe per 512 bytes; every warp
+                    // fetching its own action from host memory was 2048 small PCIe reads, ~80 us per step), and only
+                    // then are the other CTAs released.
+                    if (threadIdx.x == 0) {
+                        const uint32_t last = srv.seq0 + srv_step;
+                        const unsigned long long t0 = global_timer_ns();
+                        srv_t0 = t0;
+                        uint32_t cmd;
                         for (;;) {
+                            cmd = *srv.doorbell;
+                            if (cmd != last || global_timer_ns() - t0 > srv.idle_ns) break;
+                        }
+                        if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
+                            *srv.parked = srv.generation;
+                            srv_cmd = 0xffffffffu;
+                        } else {
+                            srv_cmd = srv_step + 1u;
+                        }
+                        srv_t0b = global_timer_ns();
+                    }
+                    __syncthreads();
+                    if (srv_cmd != 0xffffffffu) {
+                        const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
+                        const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
+                        int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
+                        // all of a thread's loads are issued before its first store: one PCIe round trip, not one per chunk
+                        for (int j0 = threadIdx.x; j0 < n16; j0 += 8 * blockDim.x) {
                             int4 v[8];
-                            bool ok = true;
 #pragma unroll
                             for (int u = 0; u < 8; ++u)
                                 if (j0 + u * (int)blockDim.x < n16) v[u] = __ldcv(src + j0 + u * blockDim.x);
 #pragma unroll
                             for (int u = 0; u < 8; ++u)
-                                if (j0 + u * (int)blockDim.x < n16) ok = ok && tagged(v[u]);
-                            if (threadIdx.x == 0) {
-                                const uint32_t cmd = *srv.doorbell;
-                                srv_cmd = (cmd == 0xffffffffu || global_timer_ns() - t0 > srv.idle_ns) ? 0xffffffffu : srv_step + 1u;
-                            }
-                            const int all_ok = __syncthreads_and(ok);
-                            if (all_ok) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u)
-                                    if (j0 + u * (int)blockDim.x < n16)
-                                        dst[j0 + u * blockDim.x] = make_int4(code(v[u].x), code(v[u].y), code(v[u].z), code(v[u].w));
-                                if (threadIdx.x == 0) srv_cmd = srv_step + 1u;  // a complete message beats a park request
-                                break;
-                            }
-                            if (srv_cmd == 0xffffffffu) break;  // (written before the barrier above: uniform)
-                            __syncthreads();                    // ... and not rewritten before everyone has read it
+                                if (j0 + u * (int)blockDim.x < n16) dst[j0 + u * blockDim.x] = v[u];
                         }
-                        __syncthreads();
-                        if (srv_cmd == 0xffffffffu) break;
+                        __threadfence();
                     }
-                    if (threadIdx.x == 0) {
-                        if (srv_cmd == 0xffffffffu) *srv.parked = srv.generation;  // parking: idle, or asked to
-                        srv_t0b = global_timer_ns();
-                    }
-                    __threadfence();
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         srv_t1 = global_timer_ns();
