@@ -58,10 +58,10 @@ if __name__ == "__main__":
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
     run("launch", {}, False, N, K)
     if len(sys.argv) > 3 and sys.argv[3] == "quick":
-        for t in (12, 6, 3):
+        for t in (12, 15, 6, 3):
             run(f"session/{t}", {"WF_HOST_THREADS": str(t)}, True, N, K)
-        for sl in (1, 2, 4):
-            run(f"session/12 slices {sl}", {"WF_SESSION_SLICES": str(sl)}, True, N, K)
+        for t in (12, 15, 6, 3):
+            run(f"session/{t} flag+fence", {"WF_HOST_THREADS": str(t), "WF_SESSION_SECTORS": "0"}, True, N, K)
         sys.exit(0)
     run("graph", {"WF_HOST_GRAPH": "1"}, False, N, K)
     run("direct", {"WF_HOST_PACKED": "direct"}, False, N, K)

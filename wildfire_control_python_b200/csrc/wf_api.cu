@@ -25,7 +25,7 @@ void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t 
 bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
                              int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
                              uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
-                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns);
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors);
 int hostpool_default_threads();
 double hostpool_first_flag_seconds(const HostPool* p);
 }  // namespace wf
@@ -120,6 +120,7 @@ struct wf_env {
         unsigned long long* dbg_dev;  // device: the kernel's debug counters (SrvCtl::dbg)
         double t_wait;              // WF_HOST_TIMING: seconds between ringing and the last slice expanded
         int slices, ctas_per_slice;
+        int sectors;                // sectors per record of the self-validating transport (0: completion flags + system fence)
         int64_t launches, steps, relaunch_races;
     } sess;
 };
@@ -717,6 +718,7 @@ static int session_launch(wf_env* e) {
     srv.seq0 = ss.seq;
     srv.generation = ss.generation;
     srv.ctas_per_slice = ss.ctas_per_slice;
+    srv.sectors = ss.sectors;
     const char* idle = getenv("WF_SESSION_IDLE_US");
     srv.dbg = ss.dbg_dev;
     srv.idle_ns = 1000ull * (unsigned long long)((idle && atoll(idle) > 0) ? atoll(idle) : 2000);
@@ -762,7 +764,11 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             std::memset(ss.actions, 0, act_bytes);
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), act_bytes));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.actions_dev), ss.actions, 0));
-            const size_t block_words = (size_t)(kRecordsPerCta * (rec_words + 1) + 31) / 32 * 32;  // one CTA's records, whole lines
+            // WF_SESSION_SECTORS=0: completion flag + system fence instead of self-validating sectors (wf_common.cuh)
+            const char* sv = getenv("WF_SESSION_SECTORS");
+            ss.sectors = (sv && sv[0] == '0') ? 0 : (int)((rec_words + 1 + 6) / 7);
+            const size_t block_words = ss.sectors ? (size_t)kRecordsPerCta * ss.sectors * 8
+                                                  : (size_t)(kRecordsPerCta * (rec_words + 1) + 31) / 32 * 32;  // one CTA's records, whole lines
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)ctas * block_words * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
@@ -787,7 +793,7 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
     for (;;) {
         const bool ok = hostpool_expand_session(e->pool, ss.rec, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw,
                                                 s.N, ss.ctl + 32, ss.seq, rps, reward_host, done_host, e->cfg.default_reward,
-                                                e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000);
+                                                e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000, ss.sectors);
         if (ok) {
             ss.t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             e->a_iter = advance_a_iter(e, 1);  // (after the step: a relaunch below must start from the phase before it)

@@ -30,6 +30,19 @@ constexpr int kObsPacked = 100;
 // (env sub-index 0 in the low half): bits 0-2 reward kind, bit 3 done, bits 4-14 grass-cell count of a burn-out reward.
 constexpr int kObsPackedStatus = 101;
 enum RewardKind : uint32_t { RK_ZERO = 0, RK_DEFAULT = 1, RK_DEATH = 2, RK_CONTAINED = 3, RK_BURNOUT = 4 };
+// Self-validating transport of the session's records (SrvCtl::sectors): a record travels as 32-byte SECTORS of seven
+// payload words + one tag word = sequence number of the step ^ hash of the seven words.  The host accepts a sector when
+// the tag fits what it reads, so it needs no completion flag -- and the GPU no system-scope fence -- and can expand the
+// first records while the last are still on the PCIe link; a torn or stale sector simply does not validate yet.
+constexpr int kSectorPayload = 7;
+__host__ __device__ __forceinline__ uint32_t sector_hash(const uint32_t* w) {
+    uint32_t h = 0x9E3779B9u;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < kSectorPayload; ++i) h = (h + w[i]) * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
 
 // Bytes per observation element of a public obs_dtype (WF_OBS_U8 / WF_OBS_F32 / WF_OBS_BF16).
 __host__ __device__ __forceinline__ int obs_elem_bytes(int dtype) { return dtype == WF_OBS_F32 ? 4 : dtype == WF_OBS_BF16 ? 2 : 1; }

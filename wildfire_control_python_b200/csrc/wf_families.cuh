@@ -26,6 +26,7 @@ struct SrvCtl {
     uint32_t* count;              // device: [slices] arrival counters
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
+    int32_t sectors;              // != 0: records travel as self-validating 32-byte sectors (wf_common.cuh), no flags / fences
     unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)
     unsigned long long* dbg;      // device, 8 counters of CTA 0 (ns, summed over steps; WF_HOST_TIMING prints them):
                                   // 0 doorbell wait + action copy, 1 go -> thread 0's warp has stepped and stored, 2 CTA

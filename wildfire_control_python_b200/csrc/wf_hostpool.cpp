@@ -36,7 +36,15 @@ struct ExpandJob {
     uint8_t* done;
     double default_reward, death_penalty, contained_bonus, cells;
     int64_t timeout_ns;         // session: give up waiting for a flag after this long (the caller then checks the kernel)
+    int64_t sectors;            // session, != 0: each record is `sectors` self-validating 32-byte sectors (7 payload words + tag =
+                                // seq ^ hash), no flags: a record is taken as soon as all its sectors validate
 };
+
+static inline uint32_t sector_hash(const uint32_t* w) {  // == wf_common.cuh
+    uint32_t h = 0x9E3779B9u;
+    for (int i = 0; i < 7; ++i) h = (h + w[i]) * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
 
 static uint64_t g_tab[256];
 static std::once_flag g_tab_once;
@@ -109,7 +117,33 @@ static inline double decode_reward(const ExpandJob& j, uint32_t st) {
     }
 }
 
-static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
+static inline void cpu_pause() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+}
+
+// Sector transport: copy record r's payload into `tmp` once every sector's tag fits its contents.  false: timed out.
+static bool fetch_record(const ExpandJob& j, int64_t r, uint32_t* tmp, const std::chrono::steady_clock::time_point& t0) {
+    const volatile uint32_t* base = j.packed + (r / j.recs_per_block) * j.block_stride + (r % j.recs_per_block) * j.sectors * 8;
+    int spins = 0;
+    for (int64_t sec = 0; sec < j.sectors; ++sec) {
+        uint32_t* out = tmp + 7 * sec;
+        for (;;) {
+            uint32_t w[8];
+            for (int i = 0; i < 8; ++i) w[i] = base[8 * sec + i];
+            if (w[7] == (j.seq ^ sector_hash(w))) {
+                for (int i = 0; i < 7; ++i) out[i] = w[i];
+                break;
+            }
+            cpu_pause();
+            if ((++spins & 255) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(j.timeout_ns)) return false;
+        }
+    }
+    return true;
+}
+
+static bool expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
 #if defined(__x86_64__)
     static const bool bmi2 = __builtin_cpu_supports("bmi2");
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
@@ -117,11 +151,17 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
 #else
     static const bool bmi2 = false;
 #endif
+    const auto t_begin = std::chrono::steady_clock::now();
     for (int64_t r = r0; r < r1; ++r) {
         const int64_t env0 = r * j.envs_per_record;
         const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
         const int64_t bits = nenv * j.env_bits;
         const uint32_t* rec = j.packed + (r / j.recs_per_block) * j.block_stride + (r % j.recs_per_block) * j.rec_stride;
+        uint32_t tmp[7 * 16];  // sector transport: the record's payload, validated (<= 97 words)
+        if (j.sectors) {
+            if (!fetch_record(j, r, tmp, t_begin)) return false;
+            rec = tmp;
+        }
         const uint8_t* in = reinterpret_cast<const uint8_t*>(rec);
         uint8_t* out = j.out + env0 * j.env_bits;
 #if defined(__x86_64__)
@@ -141,6 +181,7 @@ static void expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
             }
         }
     }
+    return true;
 }
 
 class HostPool {
@@ -187,7 +228,7 @@ private:
         const int64_t per = (job_.records + n_ - 1) / n_;
         const int64_t r0 = per * t, r1 = (r0 + per < job_.records) ? r0 + per : job_.records;
         if (r0 >= r1) return;
-        if (job_.flags) {
+        if (job_.flags && !job_.sectors) {
             // session: the GPU raises a slice's flag once all of the slice's records are in host memory; this thread's
             // records may lie in more than one slice
             const auto t0 = std::chrono::steady_clock::now();
@@ -206,7 +247,7 @@ private:
             std::atomic_thread_fence(std::memory_order_acquire);
             if (t == 0) first_flag_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
-        expand_records(job_, r0, r1);
+        if (!expand_records(job_, r0, r1)) failed_.store(1, std::memory_order_release);
     }
     void loop(int t) {
         uint64_t seen = 0;
@@ -259,11 +300,13 @@ void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t 
 bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
                              int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
                              uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
-                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns) {
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors) {
     ExpandJob j{};
     j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
     j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words + 1;
-    j.recs_per_block = 4; j.block_stride = (4 * (rec_words + 1) + 31) / 32 * 32;  // wf_warp.cu: one CTA = 4 warps = 4 records
+    j.recs_per_block = 4;  // wf_warp.cu: one CTA = 4 warps = 4 records
+    j.sectors = sectors;
+    j.block_stride = sectors ? 4 * sectors * 8 : (4 * (rec_words + 1) + 31) / 32 * 32;
     j.flags = flags; j.seq = seq; j.records_per_slice = records_per_slice; j.reward = reward; j.done = done;
     j.default_reward = default_reward; j.death_penalty = death_penalty; j.contained_bonus = contained_bonus; j.cells = cells;
     j.timeout_ns = timeout_ns;

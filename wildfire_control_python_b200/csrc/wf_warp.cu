@@ -275,7 +275,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     // SRV: the CTA's records (one per warp: up to 96 words of observation bits + the status word) are collected here and
     // leave for host memory as ONE 128-byte-aligned block of 16-byte stores -- whole PCIe write transactions instead of
     // the 4-byte-per-lane stores of unaligned 152-byte records (which cost ~25 us per step on the link)
-    __shared__ __align__(16) uint32_t srv_block[SRV ? kWarpsPerBlock * 97 + 31 : 1];
+    __shared__ __align__(16) uint32_t srv_block[SRV ? kWarpsPerBlock * 97 + 31 : 1];  // (+ slack: the sector copy reads 7-word groups)
     for (int v = threadIdx.x; v < 256; v += blockDim.x) {
         uint32_t o = 0u;
 #pragma unroll
@@ -785,8 +785,22 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 unsigned long long srv_t2 = 0ull, srv_t2b = 0ull;
                 if (blockIdx.x == 0 && threadIdx.x == 0) srv_t2 = global_timer_ns();
                 __syncthreads();  // the CTA's records are complete in shared memory
-                {
-                    const int srv_stride = ((EPW * W * H * 3 + 31) >> 5) + 1;
+                const int srv_stride = ((EPW * W * H * 3 + 31) >> 5) + 1;
+                if (srv.sectors) {
+                    // self-validating sectors: output word 8 * sec + slot of the CTA's block = payload word 7 * (sec % nsec) + slot
+                    // of record sec / nsec, slot 7 = step's sequence number ^ hash of the sector's seven payload words
+                    const int nsec = (srv_stride + kSectorPayload - 1) / kSectorPayload;
+                    const uint32_t seq = srv.seq0 + srv_step + 1u;
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * (kWarpsPerBlock * nsec * 8));
+                    for (int j = threadIdx.x; j < kWarpsPerBlock * nsec * 2; j += blockDim.x) {
+                        const int sec = j >> 1, rec = sec / nsec, p0 = (sec - rec * nsec) * kSectorPayload;
+                        const uint32_t* rw = srv_block + rec * srv_stride;
+                        uint32_t w[kSectorPayload];
+#pragma unroll
+                        for (int i = 0; i < kSectorPayload; ++i) w[i] = p0 + i < srv_stride ? rw[p0 + i] : 0u;
+                        dst[j] = (j & 1) ? make_uint4(w[4], w[5], w[6], seq ^ sector_hash(w)) : make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else {
                     const int block_words = (kWarpsPerBlock * srv_stride + 31) & ~31;  // whole 128-byte lines
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * block_words);
                     const uint4* src = reinterpret_cast<const uint4*>(srv_block);
@@ -795,7 +809,15 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 __syncthreads();  // every thread of the CTA has issued its stores to mapped host memory ...
                 if (blockIdx.x == 0 && threadIdx.x == 0) srv_t2b = global_timer_ns();
                 srv_step += 1u;
-                if (threadIdx.x == 0) {
+                if (threadIdx.x == 0 && srv.sectors) {
+                    if (blockIdx.x == 0 && srv.dbg != nullptr) {
+                        srv.dbg[0] += srv_t0b - srv_t0;
+                        srv.dbg[7] += srv_t1 - srv_t0b;
+                        srv.dbg[1] += srv_t2 - srv_t1;
+                        srv.dbg[2] += srv_t2b - srv_t2;
+                        srv.dbg[3] += 1ull;
+                    }
+                } else if (threadIdx.x == 0) {
                     // ... and are ordered before this CTA's arrival at GPU scope.  System-scope fences are expensive (each
                     // one drains the GPU's writes to host memory: ~100 us per step when all 512 CTAs issued one), so only
                     // the LAST CTA of a slice issues one -- it is cumulative over the stores it has observed through the
