@@ -200,13 +200,17 @@ def test_calls_leave_the_current_device_alone():
                                         (dict(width=32, height=32, seed=605, a_speed=2, allow_dig_toggle=True, n_actions=5), 19),
                                         (dict(width=14, height=14, seed=606, fuel=40, extra_ignitions=2), 64)],
                          ids=["14_n601", "10_n7", "20_n530", "17x13_rivers_windrandom", "32_aspeed2_toggle", "14_fuel40"])
-def test_host_session_matches_oracle(monkeypatch, cfg, n_envs):
+@pytest.mark.parametrize("transport", ["flag", "sectors"])
+def test_host_session_matches_oracle(monkeypatch, cfg, n_envs, transport):
     """Every action / reward / done / observation of a session against the oracle, with auto-reset inside the resident
     kernel, and with the session interrupted by other entry points (which park the kernel) and by idle periods (after
     which it parks itself)."""
     import time
     monkeypatch.setenv("WF_HOST_THREADS", "5")
     monkeypatch.setenv("WF_SESSION_IDLE_US", "300")
+    # how the records reach the host: one completion flag behind a system-scope fence (default), or self-validating
+    # 32-byte sectors (seven payload words + sequence number ^ hash) that need neither
+    monkeypatch.setenv("WF_SESSION_SECTORS", "1" if transport == "sectors" else "0")
     gpu, orc = make_pair(n_envs, cfg, auto_reset=True)
     gpu.reset()
     for e in orc:
