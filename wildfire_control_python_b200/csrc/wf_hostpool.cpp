@@ -69,38 +69,55 @@ __attribute__((target("bmi2"))) static void expand_pdep(const uint8_t* in, uint8
 #endif
 
 #if defined(__x86_64__)
-// 4 input bytes -> 32 output bytes per iteration: broadcast, route byte k/8 to lane k, test bit k%8.
-__attribute__((target("avx2"))) static void expand_avx2(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+// 4 input bytes -> 32 output bytes per iteration: broadcast, route byte k/8 to lane k, test bit k%8.  The destination of a
+// record is only 8-byte aligned (W*H*3 bytes per env), and vector stores that straddle cache lines cost about twice as much:
+// 8-byte pieces (one PDEP each) until the destination is aligned, aligned vector stores, 8-byte pieces for the rest.
+__attribute__((target("avx2,bmi2"))) static void expand_avx2(const uint8_t* in, uint8_t* out, int64_t nbytes) {
     const __m256i route = _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3);
     const __m256i bit = _mm256_set1_epi64x((long long)0x8040201008040201ull);
     const __m256i one = _mm256_set1_epi8(1);
     int64_t i = 0;
+    const bool can_align = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;  // (odd-sized grids: plain unaligned stores)
+    for (; can_align && i < nbytes && (reinterpret_cast<uintptr_t>(out + 8 * i) & 31u); ++i) {
+        const uint64_t v = _pdep_u64((uint64_t)in[i], 0x0101010101010101ull);
+        std::memcpy(out + 8 * i, &v, 8);
+    }
     for (; i + 4 <= nbytes; i += 4) {
         uint32_t v;
         std::memcpy(&v, in + i, 4);
         const __m256i b = _mm256_shuffle_epi8(_mm256_set1_epi32((int)v), route);
         const __m256i r = _mm256_and_si256(_mm256_cmpeq_epi8(_mm256_and_si256(b, bit), bit), one);
-        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + 8 * i), r);
+        if (can_align) _mm256_store_si256(reinterpret_cast<__m256i*>(out + 8 * i), r);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + 8 * i), r);
     }
-    for (; i < nbytes; ++i) std::memcpy(out + 8 * i, &g_tab[in[i]], 8);
+    for (; i < nbytes; ++i) {
+        const uint64_t v = _pdep_u64((uint64_t)in[i], 0x0101010101010101ull);
+        std::memcpy(out + 8 * i, &v, 8);
+    }
 }
 #endif
 
 #if defined(__x86_64__)
-// 8 input bytes -> 64 output bytes per iteration: the input IS the byte mask of a masked broadcast of 1.
-__attribute__((target("avx512f,avx512bw"))) static void expand_avx512(const uint8_t* in, uint8_t* out, int64_t nbytes) {
+// 8 input bytes -> 64 output bytes per iteration: the input IS the byte mask of a masked move of 1s.  Same alignment scheme
+// as expand_avx2; no masked stores (a masked 64-byte store of the 3-byte tail cost as much as the 18 full ones together).
+__attribute__((target("avx512f,avx512bw,bmi2"))) static void expand_avx512(const uint8_t* in, uint8_t* out, int64_t nbytes) {
     const __m512i one = _mm512_set1_epi8(1);
     int64_t i = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;  // (odd-sized grids: plain unaligned stores)
+    for (; aligned && i < nbytes && (reinterpret_cast<uintptr_t>(out + 8 * i) & 63u); ++i) {
+        const uint64_t v = _pdep_u64((uint64_t)in[i], 0x0101010101010101ull);
+        std::memcpy(out + 8 * i, &v, 8);
+    }
     for (; i + 8 <= nbytes; i += 8) {
         uint64_t v;
         std::memcpy(&v, in + i, 8);
-        _mm512_storeu_si512(reinterpret_cast<void*>(out + 8 * i), _mm512_maskz_mov_epi8(_cvtu64_mask64(v), one));
+        const __m512i r = _mm512_maskz_mov_epi8(_cvtu64_mask64(v), one);
+        if (aligned) _mm512_store_si512(reinterpret_cast<void*>(out + 8 * i), r);
+        else _mm512_storeu_si512(reinterpret_cast<void*>(out + 8 * i), r);
     }
-    if (i < nbytes) {  // 1..7 input bytes left: one masked store
-        uint64_t v = 0;
-        std::memcpy(&v, in + i, (size_t)(nbytes - i));
-        const __mmask64 live = _cvtu64_mask64((~0ull) >> (64 - 8 * (nbytes - i)));
-        _mm512_mask_storeu_epi8(reinterpret_cast<void*>(out + 8 * i), live, _mm512_maskz_mov_epi8(_cvtu64_mask64(v), one));
+    for (; i < nbytes; ++i) {
+        const uint64_t v = _pdep_u64((uint64_t)in[i], 0x0101010101010101ull);
+        std::memcpy(out + 8 * i, &v, 8);
     }
 }
 #endif
@@ -146,17 +163,19 @@ static bool fetch_record(const ExpandJob& j, int64_t r, uint32_t* tmp, const std
 static bool expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
 #if defined(__x86_64__)
     static const bool bmi2 = __builtin_cpu_supports("bmi2");
-    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
-    static const bool avx512 = __builtin_cpu_supports("avx512bw") && !getenv("WF_HOST_NO_AVX512") && !getenv("WF_HOST_NO_AVX2");
+    static const bool avx2 = bmi2 && __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
+    static const bool avx512 = avx2 && __builtin_cpu_supports("avx512bw") && !getenv("WF_HOST_NO_AVX512");
 #else
     static const bool bmi2 = false;
 #endif
     const auto t_begin = std::chrono::steady_clock::now();
-    for (int64_t r = r0; r < r1; ++r) {
+    int64_t blk = r0 / j.recs_per_block, in_blk = r0 % j.recs_per_block;  // (no division per record)
+    for (int64_t r = r0; r < r1; ++r, ++in_blk) {
+        if (in_blk == j.recs_per_block) { in_blk = 0; ++blk; }
         const int64_t env0 = r * j.envs_per_record;
         const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
         const int64_t bits = nenv * j.env_bits;
-        const uint32_t* rec = j.packed + (r / j.recs_per_block) * j.block_stride + (r % j.recs_per_block) * j.rec_stride;
+        const uint32_t* rec = j.packed + blk * j.block_stride + in_blk * j.rec_stride;
         uint32_t tmp[7 * 16];  // sector transport: the record's payload, validated (<= 97 words)
         if (j.sectors) {
             if (!fetch_record(j, r, tmp, t_begin)) return false;
