@@ -348,11 +348,15 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, with_e2e: bool,
         obs_bytes = N * W * H * 3
         if env.host_threads:  # packed path: one record of ceil(e * W*H*3 / 32) words per e envs (e = 2 if W <= 16 else 1)
             epw = 2 if W <= 16 else 1
-            d2h_obs = ((N + epw - 1) // epw) * ((epw * W * H * 3 + 31) // 32) * 4
+            records, rec_words = (N + epw - 1) // epw, (epw * W * H * 3 + 31) // 32
+            if session:  # + one status word (reward code, done) per record, four records per 128-byte-aligned CTA block
+                d2h = ((records + 3) // 4) * ((4 * (rec_words + 1) + 31) // 32 * 32) * 4
+            else:
+                d2h = records * rec_words * 4 + N * 8 + N
         else:
-            d2h_obs = obs_bytes
+            d2h = obs_bytes + N * 8 + N
         res["e2e"] = {"value": world * N * Ke / te, "unit": "env-steps/s", "h2d_bytes_per_step": N * 4,
-                      "d2h_bytes_per_step": d2h_obs + N * 8 + N, "obs_bytes_delivered_per_step": obs_bytes,
+                      "d2h_bytes_per_step": d2h, "obs_bytes_delivered_per_step": obs_bytes,
                       "steps": K, "repeats": Re, "us_per_step": te * 1e6 / Ke,
                       "host_threads": env.host_threads, "session": session,
                       "api": ("wf_step_host, page-locked host buffers: actions/reward/done zero-copy; observation sent as a bit "
