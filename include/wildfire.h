@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WF_ABI_VERSION 1
+#define WF_ABI_VERSION 2 /* 2: + wf_reset_host, wf_host_session(_active), wf_get/set_a_iter, wf_tile_geometry (additions only) */
 
 enum {
     WF_OK = 0,
@@ -155,8 +155,9 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * bit stream and is expanded into obs_host by a small pool of host threads (WF_HOST_THREADS, default
  * min(12, 3/4 of the cores / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead,
  * WF_HOST_PACKED=direct stores the bit stream straight into mapped host memory instead of one DMA copy;
- * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed; WF_HOST_GRAPH=1 (experimental,
- * a_speed == 1 only) issues kernel + copy as one CUDA graph).
+ * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed; WF_HOST_GRAPH=1
+ * (a_speed == 1 only) issues kernel + copy as one CUDA graph: 40.0-40.6 against 42.1 us per C2 step, tools/e2e_ab.py).
+ * Fastest: wf_host_session below (24.5 us), which also lifts the page-locked requirement.
  * The device alias of each page-locked buffer is looked up once and re-validated every 1024 calls: a caller that
  * unpins or frees a buffer must not hand the same ADDRESS back as a different kind of memory within that window
  * (pass a new address, or destroy the handle). */

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_default_config(lib):
-    assert lib.wf_abi_version() == 1
+    assert lib.wf_abi_version() == 2
     cfg = _lib.WfConfig()
     lib.wf_default_config(C.byref(cfg), 14)
     # Simulation/constants.py:30-47 + utility.py:94-102
