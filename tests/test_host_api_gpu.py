@@ -273,3 +273,21 @@ def test_host_session_is_refused_for_the_tile_family():
     env.reset()
     assert env.host_session(True) is False and env.host_session_state == 0
     env.step_host(np.zeros(4, np.int32))  # the launch-per-step path still serves it
+
+
+@pytest.mark.gpu
+def test_host_session_falls_back_when_the_batch_cannot_be_resident():
+    """The step server is a cooperative launch (every CTA resident).  A batch with more CTAs than the GPU has slots cannot
+    be one: the first step_host turns the session off and the launch-per-step path serves the call -- same results."""
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    N, cfg = 6000, dict(width=10, height=10, seed=621, auto_reset=True)  # 750 CTAs of 8 envs > 592 slots
+    a, b = BatchedForestFire(N, **cfg), BatchedForestFire(N, **cfg)
+    a.reset(); b.reset()
+    assert a.host_session(True)
+    rng = np.random.default_rng(2)
+    for s in range(12):
+        acts = rng.integers(0, 4, N, dtype=np.int32)
+        oa, ra, da, _ = a.step_host(acts)
+        ob, rb, db, _ = b.step_host(acts)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db), s
+    assert a.host_session_state == 0
