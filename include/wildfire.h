@@ -153,7 +153,7 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * be page-locked for full PCIe rate; pageable memory works but is slower.
  * With page-locked buffers, uint8 observations and a grid up to 32x32 the observation crosses PCIe as a
  * bit stream and is expanded into obs_host by a small pool of host threads (WF_HOST_THREADS, default
- * min(12, 3/4 of the cores / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead,
+ * min(12, cores / ranks on the host); WF_HOST_PACKED=0 sends the uint8 array instead,
  * WF_HOST_PACKED=direct stores the bit stream straight into mapped host memory instead of one DMA copy;
  * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed; WF_HOST_GRAPH=1
  * (a_speed == 1 only) issues kernel + copy as one CUDA graph: 40.0-40.6 against 42.1 us per C2 step, tools/e2e_ab.py).
