@@ -54,7 +54,8 @@ WORKLOADS = {
     "c3": dict(n_envs=8192, meta=dict(width=14, height=14), chunk=64, policy=True,
                desc="14x14 Logs/14-sized constants, 8192 envs/GPU, DQN MLP policy 588-50-4 in the loop (eps 0.1), auto-reset"),
     # configs[3]: 256x256, 1024 envs, wind enabled, multi-ignition stress of the stencil
-    "c4": dict(n_envs=1024, meta=dict(width=256, height=256, wind=[0.85, (1, 0)], extra_ignitions=32), chunk=16,
+    # 64 steps per launch: 45.9 / 45.1 / 44.8 / 44.5 us per step with 16 / 32 / 64 / 128 (r02; c5 does not care: 86.4 ... 85.6)
+    "c4": dict(n_envs=1024, meta=dict(width=256, height=256, wind=[0.85, (1, 0)], extra_ignitions=32), chunk=64,
                desc="256x256, wind [0.85,(1,0)], 32 extra ignitions, 1024 envs/GPU, ACTION-stream actions, auto-reset"),
     # configs[4]: 1024x1024 grid, 64 envs per GPU
     "c5": dict(n_envs=64, meta=dict(width=1024, height=1024, extra_ignitions=256), chunk=16,
