@@ -109,6 +109,12 @@ def api_round(rng):
     gpu = BatchedForestFire(N, **cfg)
     twin = None
     orc = [wo.OracleEnv(cfg, env_id=i) for i in range(N)]
+    # step_host through the resident step server on some rounds (warp family; the tile family refuses), with either
+    # transport and a short idle limit, so that it parks itself / is parked by the device-side calls mixed in below
+    os.environ["WF_SESSION_SECTORS"] = str(int(rng.integers(0, 2)))
+    os.environ["WF_SESSION_IDLE_US"] = str(int(rng.choice([50, 300, 2000])))
+    session = bool(rng.random() < 0.6) and gpu.host_session(True)
+    print(f"            session={session} sectors={os.environ['WF_SESSION_SECTORS']} idle_us={os.environ['WF_SESSION_IDLE_US']}", flush=True)
     obs = to_np(gpu.reset())
     for i, e in enumerate(orc):
         assert np.array_equal(obs[i], e.reset()), "reset obs"
@@ -128,8 +134,7 @@ def api_round(rng):
         if op > 0.95 and twin is None:  # checkpoint into a second handle
             st = gpu.get_state()
             twin = BatchedForestFire(N, **cfg)
-            twin.set_state(type=st["type"], burning=st["burning"], fm_inf=st["fm_inf"], fuel=st["fuel"], hits=st["hits"],
-                           scalars=st["scalars"])
+            twin.set_state(**st)
         acts = rng.integers(0, n_act + 1, size=N).astype(np.int32)
         live = [bool(e.planes()["running"]) for e in orc]
         for e in orc:
@@ -148,7 +153,7 @@ def api_round(rng):
             o, r, d, _ = e.step(int(acts[i]))
             assert r_g[i] == r and bool(d_g[i]) == d, (i, k, r_g[i], r, d_g[i], d)
             assert np.array_equal(o_g[i], o), (i, k, "obs")
-        if twin is not None and a_speed == 1:  # (a second handle has its own a_speed_iter: keep to a_speed 1)
+        if twin is not None:  # (the checkpoint carries a_speed_iter)
             o_t, r_t, d_t, _ = twin.step(torch.from_numpy(acts).cuda())
             assert np.array_equal(to_np(o_t), o_g) and np.array_equal(to_np(r_t), r_g), (k, "twin diverged")
         m = np.array([not e.planes()["running"] for e in orc], np.uint8)
