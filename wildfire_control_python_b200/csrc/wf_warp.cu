@@ -272,6 +272,8 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
     __shared__ uint32_t srv_cmd;
+    __shared__ unsigned long long cta_stats[2];  // env-steps and fire ticks of this CTA's envs in this launch
+    if (threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
     // SRV: the CTA's records (one per warp: up to 96 words of observation bits + the status word) are collected here and
     // leave for host memory as ONE 128-byte-aligned block of 16-byte stores -- whole PCIe write transactions instead of
     // the 4-byte-per-lane stores of unaligned 152-byte records (which cost ~25 us per step on the link)
@@ -865,10 +867,16 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             sp[1] = make_int4(a.digging, a.vis, a.running, a.fab);
             sp[2] = make_int4(a.latched, (int)a.episode, (int)a.t, a.wid);
             sp[3] = make_int4(s.wind->wx[a.wid], s.wind->wy[a.wid], a.nburn, 0);
-            if (n_steps_done) atomicAdd(&s.stats[ST_STEPS], (unsigned long long)n_steps_done);
-            if (n_ticks_done) atomicAdd(&s.stats[ST_TICKS], (unsigned long long)n_ticks_done);
         }
     }
+    // Step / tick counters: summed over the CTA in shared memory, one pair of global atomics per CTA (one pair per ENV was
+    // 8192 atomics on two addresses per launch -- microseconds of a one-step launch).
+    if (valid_env && x == 0) {
+        if (n_steps_done) atomicAdd(&cta_stats[0], (unsigned long long)n_steps_done);
+        if (n_ticks_done) atomicAdd(&cta_stats[1], (unsigned long long)n_ticks_done);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && cta_stats[threadIdx.x]) atomicAdd(&s.stats[threadIdx.x == 0 ? ST_STEPS : ST_TICKS], cta_stats[threadIdx.x]);
 }
 
 // The C2 kernel must stay at 128 registers (16 warps per SM: all 2048 warps of a 4096-env batch resident; at 164
