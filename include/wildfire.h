@@ -164,17 +164,20 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
 int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32_t obs_dtype,
                  double* reward_host, uint8_t* done_host);
 /* Step-server session for wf_step_host (grids up to 32x32, uint8 observations).  While a session is on, the step kernel
- * stays RESIDENT on the GPU with every env in registers and is driven through flags in mapped page-locked memory:
- * wf_step_host copies the actions into a mapped buffer and rings a doorbell the kernel polls; the kernel steps, stores
- * the packed observation + reward/done codes straight into mapped host memory and raises one completion flag per
- * slice of the batch; the library's host threads wait on those flags and expand their slice into obs_host (any host
- * memory, pageable or page-locked) while the other slices are still in flight.  No kernel launch, no copy call and no
- * stream synchronise per step.  The caller's buffers may be pageable.
+ * stays RESIDENT on the GPU (a cooperative launch) with every env in registers and is driven through mapped page-locked
+ * memory: wf_step_host copies the actions into a mapped buffer and rings a doorbell that CTA 0 polls; CTA 0 copies the
+ * actions into HBM and releases the other CTAs; every CTA steps its envs and stores its records -- the observation bit
+ * stream plus one status word per record (reward kind, done, burn-out count) -- straight into mapped host memory; the
+ * last CTA to finish issues a system-scope fence and raises the completion flag; the library's host threads then expand
+ * the records into obs_host and decode reward / done (any host memory: the caller's buffers may be pageable).  No kernel
+ * launch, no copy call and no stream synchronise per step: 24.5 instead of 42 us per 4096-env 14x14 step.
  *   wf_host_session(env, 1)  turn it on (the kernel is started by the next wf_step_host);  (env, 0) park it.
  * Any other entry point on the handle (wf_reset, wf_step, wf_get_state, ...) parks the kernel first -- it stores the
  * envs back to HBM and exits -- and the next wf_step_host starts it again, so results never depend on the session.
  * A kernel that sees no doorbell for WF_SESSION_IDLE_US (default 2000) microseconds parks itself: the GPU is not held
  * hostage by a caller that stops stepping (other work on the device is delayed by at most that long).
+ * A batch with more CTAs (8 envs of <= 16 rows, 4 of up to 32 rows, each) than the GPU can hold resident cannot be
+ * served: the first wf_step_host then turns the session off and the launch-per-step path takes over.
  * Returns WF_ERR_INVALID for the tile family.  wf_host_session_active: 0 off, 1 on (kernel parked), 2 kernel resident. */
 int wf_host_session(wf_env* env, int32_t on);
 int wf_host_session_active(const wf_env* env);
