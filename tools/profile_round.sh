@@ -12,5 +12,5 @@ ncu --set full --clock-control none --import-source on -k regex:warp_kernel -s 2
     python bench.py --workload c2 --only-value --steps 256 --warmup 256 --min-region-s 0 > gpurun_out/ncu_c2.log 2>&1; echo "c2 rc=$?"
 for wl in c4 c5; do
   ncu --set full --clock-control none --import-source on -k regex:tile_rollout -s 3 -c 1 -f -o gpurun_out/prof_$wl \
-      python bench.py --workload $wl --only-value --steps 16 --warmup 16 --min-region-s 0 > gpurun_out/ncu_$wl.log 2>&1; echo "$wl rc=$?"
+      python bench.py --workload $wl --chunk 16 --only-value --steps 16 --warmup 16 --min-region-s 0 > gpurun_out/ncu_$wl.log 2>&1; echo "$wl rc=$?"
 done
