@@ -208,6 +208,7 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         if ((tbits & 7) == 0 && (reinterpret_cast<uintptr_t>(o8) & 7u) == 0) {
             uint2* o64 = reinterpret_cast<uint2*>(o8);  // output bytes 8j..8j+7 = stream bits 8j..8j+7
             const uint8_t* stream8 = reinterpret_cast<const uint8_t*>(stream);
+#pragma unroll 4
             for (int j = lane; j < (tbits >> 3); j += 32) o64[j] = tab8[stream8[j]];  // byte of 8 stream bits -> 8 bytes
         } else if ((tbits & 3) == 0 && (reinterpret_cast<uintptr_t>(o8) & 3u) == 0) {
             uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
@@ -565,11 +566,11 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         if (dgx == 0) fm = 0u;
                         if (dgx + 1 >= W) fp = 0u;
                         if (x == dgx) reach &= ~(1u << dgy);
-                        const int ym = dgy - 1, yp = dgy + 1;
-                        auto bit = [&](uint32_t row, int y) -> uint32_t { return (y >= 0 && y < H) ? (row >> y) & 1u : 0u; };
-                        // ring of the 8 neighbours, clockwise from N: N NE E SE S SW W NW (N = y - 1, E = x + 1)
-                        const uint32_t ring = bit(f0, ym) | bit(fp, ym) << 1 | bit(fp, dgy) << 2 | bit(fp, yp) << 3 | bit(f0, yp) << 4 |
-                                              bit(fm, yp) << 5 | bit(fm, dgy) << 6 | bit(fm, ym) << 7;
+                        // ring of the 8 neighbours, clockwise from N: N NE E SE S SW W NW (N = y - 1, E = x + 1).  Bit y - 1 of a
+                        // row is bit y of (row << 1), bit y + 1 is bit y of (row >> 1); rows are zero outside the grid.
+                        auto at = [&](uint32_t v) -> uint32_t { return (v >> dgy) & 1u; };
+                        const uint32_t ring = at(f0 << 1) | at(fp << 1) << 1 | at(fp) << 2 | at(fp >> 1) << 3 | at(f0 >> 1) << 4 |
+                                              at(fm >> 1) << 5 | at(fm) << 6 | at(fm << 1) << 7;
                         const uint32_t rot1 = ((ring << 1) | (ring >> 7)) & 255u, rot2 = ((ring << 2) | (ring >> 6)) & 255u;
                         const int n4 = __popc(ring & 0x55u);
                         int groups = n4 - __popc(ring & rot1 & rot2 & 0x55u);  // a 4-neighbour joined to the previous one through the corner
@@ -643,16 +644,16 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         r.HC[q] = t1 ^ k;
                         k &= t1;
                     }
-                    // ... and compared with kmin, most significant bit first: ge = (count >= kmin)
-                    const uint32_t km = (uint32_t)min(a.kmin, (1 << kHitBits) - 1);
-                    uint32_t gt = 0u, eq = 0xffffffffu;
+                    // ... and compared with kmin: count >= kmin  <=>  count + (2^7 - kmin) carries out of bit 6; the carry
+                    // chain of adding a constant is one majority (a single LOP3) per bit-slice
+                    const uint32_t addc = (uint32_t)(1 << kHitBits) - (uint32_t)min(a.kmin, (1 << kHitBits) - 1);
+                    uint32_t carry = 0u;
 #pragma unroll
-                    for (int q = kHitBits - 1; q >= 0; --q) {
-                        const uint32_t kb = ((km >> q) & 1u) ? 0xffffffffu : 0u;
-                        gt |= eq & r.HC[q] & ~kb;
-                        eq &= ~(r.HC[q] ^ kb);
+                    for (int q = 0; q < kHitBits; ++q) {
+                        const uint32_t cb = 0u - ((addc >> q) & 1u);
+                        carry = (r.HC[q] & cb) | (carry & (r.HC[q] | cb));
                     }
-                    ign = m & (gt | eq);  // only cells heated this tick can cross the threshold
+                    ign = m & carry;  // only cells heated this tick can cross the threshold
                     m = 0u;
                 }
                 uint32_t* hrow = s.hits + ((size_t)(valid_env ? env : 0) * W + x) * H;
