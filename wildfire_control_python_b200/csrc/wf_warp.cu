@@ -169,8 +169,11 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         if (lane + 32 * i < kStreamWords) stream[lane + 32 * i] = 0u;
     __syncwarp();
     if (x < W && sub < n_valid) {
-        auto piece = [&](int p) -> uint32_t {  // cells 8p..8p+7 of this row -> 24 interleaved bits (channels 1 and 2)
-            return (spread3[(frow >> (8 * p)) & 255u] << 1) | (spread3[(freerow >> (8 * p)) & 255u] << 2);
+        auto piece = [&](int p) -> uint32_t {  // cells 8p..8p+7 of this row -> 24 interleaved bits
+            // (the agent_pos mask is one bit of one row; setting that bit under a branch instead of spreading the mask
+            //  measured slower: 2.11 against 2.05 us per C2 step)
+            return spread3[(arow >> (8 * p)) & 255u] | (spread3[(frow >> (8 * p)) & 255u] << 1) |
+                   (spread3[(freerow >> (8 * p)) & 255u] << 2);
         };
         const uint32_t p0 = piece(0), p1 = piece(1);
         uint32_t r0 = p0 | (p1 << 24), r1 = p1 >> 8, r2 = 0u;
@@ -178,12 +181,6 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
             const uint32_t p2 = piece(2), p3 = piece(3);
             r1 |= p2 << 16;
             r2 = (p2 >> 16) | (p3 << 8);
-        }
-        if (arow) {  // channel 0 (agent_pos) is ONE cell of one row: set its bit directly instead of spreading a zero mask
-            const int b = 3 * (__ffs(arow) - 1);
-            if (b < 32) r0 |= 1u << b;
-            else if (b < 64) r1 |= 1u << (b - 32);
-            else r2 |= 1u << (b - 64);
         }
         const int start = sub * nbits + 3 * H * x, w0 = start >> 5, sh = start & 31;
         const uint32_t c0 = r0 << sh, c1 = __funnelshift_l(r0, r1, sh), c2 = __funnelshift_l(r1, r2, sh),
