@@ -185,8 +185,8 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         const int start = sub * nbits + 3 * H * x, w0 = start >> 5, sh = start & 31;
         const uint32_t c0 = r0 << sh, c1 = __funnelshift_l(r0, r1, sh), c2 = __funnelshift_l(r1, r2, sh),
                        c3 = __funnelshift_l(r2, 0u, sh);
-        if (c0) atomicOr(&stream[w0], c0);
-        if (c1) atomicOr(&stream[w0 + 1], c1);
+        atomicOr(&stream[w0], c0);  // (the first two words of a row are hardly ever empty: no test, no branch)
+        atomicOr(&stream[w0 + 1], c1);
         if (c2) atomicOr(&stream[w0 + 2], c2);
         if (c3) atomicOr(&stream[w0 + 3], c3);
     }
