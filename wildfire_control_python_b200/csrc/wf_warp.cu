@@ -187,8 +187,8 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
                        c3 = __funnelshift_l(r2, 0u, sh);
         atomicOr(&stream[w0], c0);  // (the first two words of a row are hardly ever empty: no test, no branch)
         atomicOr(&stream[w0 + 1], c1);
-        if (c2) atomicOr(&stream[w0 + 2], c2);
-        if (c3) atomicOr(&stream[w0 + 3], c3);
+        atomicOr(&stream[w0 + 2], c2);
+        if (L == 32 && c3) atomicOr(&stream[w0 + 3], c3);
     }
     __syncwarp();
     if (n_valid <= 0) return;
