@@ -212,8 +212,14 @@ __device__ __forceinline__ void emit_obs(void* obs_step, int dtype, uint32_t aro
         if ((tbits & 7) == 0 && (reinterpret_cast<uintptr_t>(o8) & 7u) == 0) {
             uint2* o64 = reinterpret_cast<uint2*>(o8);  // output bytes 8j..8j+7 = stream bits 8j..8j+7
             const uint8_t* stream8 = reinterpret_cast<const uint8_t*>(stream);
-#pragma unroll 4
-            for (int j = lane; j < (tbits >> 3); j += 32) o64[j] = tab8[stream8[j]];  // byte of 8 stream bits -> 8 bytes
+            // byte of 8 stream bits -> 8 bytes; fully unrolled under a predicate, so that all the look-ups are in flight together
+            constexpr int kMaxIt = (L == 16) ? 6 : 12;  // (2 x 16 x 16 x 3 or 32 x 32 x 3 bits) / 8 / 32 lanes
+            const int n8 = tbits >> 3;
+#pragma unroll
+            for (int i = 0; i < kMaxIt; ++i) {
+                const int j = lane + 32 * i;
+                if (j < n8) o64[j] = tab8[stream8[j]];
+            }
         } else if ((tbits & 3) == 0 && (reinterpret_cast<uintptr_t>(o8) & 3u) == 0) {
             uint32_t* o32 = reinterpret_cast<uint32_t*>(o8);
             for (int j = lane; j < (tbits >> 2); j += 32) {
