@@ -37,6 +37,7 @@ struct TileState {
     int32_t P_S0, P_S1, P_R;
     int32_t T, CS;  // threads per CTA, CTAs per cluster (one cluster per env)
     bool fused;     // WF_TILE_FUSED=1 (read by wf_create): the fused pass for the shapes that allow it
+    bool overlap;   // WF_TILE_OVERLAP (read by wf_create): see TilePar::overlap
 };
 
 struct TilePar {  // launch constants, precomputed on the host so the kernel re-reads them from the constant bank
@@ -49,6 +50,7 @@ struct TilePar {  // launch constants, precomputed on the host so the kernel re-
     size_t pstride;      // words between consecutive planes (N * RS * HW)
     size_t env_words;    // words between consecutive envs within a plane (RS * HW)
     size_t step_bytes;   // bytes of one step's observation block [N][W][H][3]
+    int32_t overlap;     // two-phase path: finish / next agent phase / barrier Y overlapped with the observation (WF_TILE_OVERLAP)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -90,6 +92,9 @@ struct StepShared {
     int32_t obs_vis, obs_ax, obs_ay;  // agent_pos layer of the observation being emitted
     int32_t obs_ctr;                  // next 128-word observation group of this CTA (dynamic distribution)
     uint32_t stat[ST_N];  // this launch's contribution to the handle's statistics (flushed once, at the end)
+    int32_t obs_agent[2][3];  // overlapped flow: agent_pos layer (visible, x, y) after the action of step k, in slot k & 1
+    int32_t slow;             // overlapped flow: this step's reward needs the whole cluster (seed_cells_touch) before it is known
+    int32_t keep[3];          // ... and the step's totals (burning, grass, ignition on edge) kept meanwhile
 };
 
 int tile_extra_planes() { return 3; }
@@ -133,6 +138,8 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
 __device__ __forceinline__ void cluster_barrier() {  // release/acquire at cluster scope (also orders global memory)
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_cluster(int* local_ptr, uint32_t peer, int v) {  // DSMEM store
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr);
     uint32_t ra;
@@ -334,8 +341,16 @@ __device__ __forceinline__ void apply_dig(const Env& e, const TilePar& t, int wi
 // ForestFire.step part 1: the action (Agent.move :141-155, toggle_digging :136-138) and, on tick
 // steps, Agent.is_dead (:116-120).  Thread 0 of every CTA computes the same thing; only `writer`
 // (cluster rank 0) touches global memory.
-__device__ void agent_phase(const Env& e, const StepCfg& c, const TilePar& t, const TileIO& io, const DevState& s, int k,
-                            int do_tick, int32_t* sc, StepShared& ss, bool writer) {
+__device__ void agent_phase_impl(const Env& e, const StepCfg& c, const TilePar& t, const TileIO& io, const DevState& s, int k,
+                                 int do_tick, int32_t* sc, StepShared& ss, bool writer);
+__device__ __forceinline__ void agent_phase(const Env& e, const StepCfg& c, const TilePar& t, const TileIO& io, const DevState& s,
+                                            int k, int do_tick, int32_t* sc, StepShared& ss, bool writer) {
+    agent_phase_impl(e, c, t, io, s, k, do_tick, sc, ss, writer);
+    // the agent_pos layer of step k's observation (nothing after the action moves the agent; a reset re-reads the scalars)
+    ss.obs_agent[k & 1][0] = sc[WF_S_VISIBLE]; ss.obs_agent[k & 1][1] = sc[WF_S_AX]; ss.obs_agent[k & 1][2] = sc[WF_S_AY];
+}
+__device__ void agent_phase_impl(const Env& e, const StepCfg& c, const TilePar& t, const TileIO& io, const DevState& s, int k,
+                                 int do_tick, int32_t* sc, StepShared& ss, bool writer) {
     ss.act = sc[WF_S_RUNNING];
     ss.dig_word = -1;
     ss.dig_bit = 0u;
@@ -1339,8 +1354,136 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
             return dt;
         };
         int do_tick = tick_of(it);
+        if (tid == 0) { ss.obs_ctr = 0; ss.slow = 0; }
         if (tid == 0 && io.K > 0) agent_phase(e, c, t, io, s, 0, do_tick, sc, ss, writer);
-        for (int k = 0; k < io.K; ++k) {
+        // ---- RUNNING (forest_fire.py:105-106), World.get_reward (environment.py:342-390), done; thread 0 only
+        auto finish_step = [&](int k, int dt, int touches, int n_burning, int n_grass, int edge_ignition) {
+            const int cur = sc[WF_S_RESERVED];
+            if (dt) sc[WF_S_RESERVED] = cur ^ 1;  // the source mask just written becomes current
+            const bool anyB = n_burning > 0;
+            sc[WF_S_N_BURNING] = n_burning;
+            if (dt) {
+                if (edge_ignition) sc[WF_S_FIRE_AT_BORDER] = 1;
+                if (!sc[WF_S_ALIVE] || !anyB) sc[WF_S_RUNNING] = 0;
+            }
+            double rew;
+            const bool check = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && anyB;
+            if (check && !touches) {
+                sc[WF_S_LATCHED] = 1;  // bonus paid once (Q4), tested before the death test
+                rew = c.contained_bonus;
+                ss.stat[ST_CONTAINED] += 1u;
+            } else if (!sc[WF_S_ALIVE]) {
+                rew = c.death_penalty;
+            } else if (!anyB) {
+                rew = __dmul_rn(c.contained_bonus, __ddiv_rn((double)n_grass, (double)(s.W * s.H)));
+            } else {
+                rew = c.default_reward;
+            }
+            sc[WF_S_T] += 1;
+            const bool is_done = !sc[WF_S_RUNNING];
+            ss.stat[ST_STEPS] += 1u;
+            if (dt) ss.stat[ST_TICKS] += 1u;
+            if (is_done) {
+                ss.stat[ST_EPISODES] += 1u;
+                if (sc[WF_S_ALIVE]) ss.stat[ST_BURNOUTS] += 1u;
+            }
+            if (writer) {
+                if (io.reward) io.reward[(size_t)k * s.N + e.env] = rew;
+                if (io.done) io.done[(size_t)k * s.N + e.env] = is_done ? 1 : 0;
+            }
+            ss.reset_now = c.auto_reset && is_done;
+        };
+        // Overlapped flow (two-phase path, TilePar::overlap).  Per step: barrier X -> tick -> CTA barrier -> the partial sums
+        // go to the peers and every thread ARRIVES at cluster barrier Y; warp 0 waits for it, adds the totals up, and thread
+        // 0 does finish + the agent phase of the next step, while the other warps already emit the observation (its agent
+        // layer was fixed by this step's agent phase; they wait for Y afterwards).  The observation is speculative in one
+        // respect: if the episode ends here and auto_reset is on, it is emitted again after the reset.  The rare step whose
+        // reward needs a whole-cluster pass (seed_cells_touch) finishes after the observation instead.
+        for (int k = 0; !FU && t.overlap && k < io.K; ++k) {
+            sync_env<CL>();  // barrier X: agent phase k (and everything thread 0 wrote) is visible; no plane is written before
+            const bool act = ss.act != 0;
+            int digw = ss.dig_word;
+            const int ovis = ss.obs_agent[k & 1][0], oax = ss.obs_agent[k & 1][1], oay = ss.obs_agent[k & 1][2];
+            void* obs_k = io.obs != nullptr ? static_cast<char*>(io.obs) + (size_t)k * step_bytes : nullptr;
+            const int dt = do_tick;
+            do_tick = tick_of(it);  // of step k + 1
+            if (ss.need_flood) {  // rare: the dig may cut the reach plane -> apply it now and re-flood R
+                if (tid == 0 && digw >= e.lo && digw < e.hi) apply_dig(e, t, digw, ss.dig_bit, ss.dig_clear_R);
+                digw = -1;
+                sync_env<CL>();
+                flood<CL>(e, t, red, xch, par, ss);
+            }
+            const int warp = tid >> 5;
+            if (act) {
+                tick_slice<FB, VW>(e, s, c, t, sc, ss, dt != 0, digw, red, qmem);
+                const int cur = sc[WF_S_RESERVED];  // (before thread 0 flips it)
+                __syncthreads();                    // red[] is complete, this CTA's planes are final
+                if (CL) {
+                    if (tid < kRed * e.CS) st_shared_cluster(&xch[par][e.rank][tid & (kRed - 1)], (uint32_t)(tid / kRed), red[tid & (kRed - 1)]);
+                    cluster_arrive();  // barrier Y, first half
+                }
+                if (warp == 0) {
+                    if (CL) cluster_wait();
+                    if (tid < kRed) {
+                        int v = 0;
+                        if (CL) { for (int r = 0; r < e.CS; ++r) v += xch[par][r][tid]; }
+                        else v = red[tid];
+                        ss.tot[tid] = v;
+                        red[tid] = 0;
+                    }
+                    __syncwarp();
+                    if (tid == 0) {
+                        const bool searching = !sc[WF_S_FIRE_AT_BORDER] && !sc[WF_S_LATCHED] && ss.tot[0] > 0 && !(dt && ss.tot[2]);
+                        if (ss.tot[4] && searching && !ss.tot[3]) {
+                            ss.slow = 1;  // rare (W > H maps): a burning cell is a border point itself
+                            ss.reset_now = 0;
+                            ss.keep[0] = ss.tot[0]; ss.keep[1] = ss.tot[1]; ss.keep[2] = ss.tot[2];  // (exchange reuses ss.tot)
+                        } else {
+                            ss.slow = 0;
+                            finish_step(k, dt, ss.tot[3], ss.tot[0], ss.tot[1], ss.tot[2]);
+                            if (!ss.reset_now && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
+                        }
+                    }
+                }
+                if (CL) par ^= 1;
+                if (obs_k != nullptr) emit_obs_slice(e, obs_k, io.obs_dtype, spread3, tab8, qmem, ovis, oax, oay, &ss.obs_ctr);
+                if (CL && warp != 0) cluster_wait();  // barrier Y, second half
+                __syncthreads();  // what thread 0 decided is visible
+                if (ss.slow) {
+                    const int scratch = dt ? ((cur & 1) ? t.P_S1 : t.P_S0) : ((cur & 1) ? t.P_S0 : t.P_S1);  // not the current sources
+                    const int touches = seed_cells_touch<CL>(e, t, scratch, red, xch, par, ss) ? 1 : 0;
+                    if (tid == 0) finish_step(k, dt, touches, ss.keep[0], ss.keep[1], ss.keep[2]);
+                    __syncthreads();
+                }
+            } else {
+                if (tid == 0) {  // frozen env: reward 0, done 1, nothing moves
+                    if (writer) {
+                        if (io.reward) io.reward[(size_t)k * s.N + e.env] = 0.0;
+                        if (io.done) io.done[(size_t)k * s.N + e.env] = 1;
+                    }
+                    ss.reset_now = 0;
+                    ss.slow = 0;
+                    if (k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
+                }
+                if (obs_k != nullptr) emit_obs_slice(e, obs_k, io.obs_dtype, spread3, tab8, qmem, ovis, oax, oay, &ss.obs_ctr);
+                __syncthreads();
+            }
+            const bool late_agent = act && (ss.slow || ss.reset_now);
+            if (ss.reset_now) {
+                reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
+                if (tid == 0) ss.obs_ctr = 0;
+                __syncthreads();
+                if (obs_k != nullptr)  // the new episode's first observation replaces the speculative one
+                    emit_obs_slice(e, obs_k, io.obs_dtype, spread3, tab8, qmem, sc[WF_S_VISIBLE], sc[WF_S_AX], sc[WF_S_AY], &ss.obs_ctr);
+                __syncthreads();
+            }
+            if (tid == 0) {
+                if (late_agent && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
+                ss.obs_ctr = 0;
+                ss.slow = 0;
+            }
+        }
+        for (int k = 0; (FU || !t.overlap) && k < io.K; ++k) {
             WF_TSTAMP(0);
             sync_env<CL>();  // barrier X
             WF_TSTAMP(1);
@@ -1535,6 +1678,7 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     t->P_R = P_FU0 + 2;
     choose_geometry(s, t->T, t->CS);
     t->fused = env_int("WF_TILE_FUSED", 0) != 0;
+    t->overlap = env_int("WF_TILE_OVERLAP", 0) != 0;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = set_smem_attr<5, 1, false>();
     if (e == cudaSuccess) e = set_smem_attr<5, 4, false>();
@@ -1578,6 +1722,7 @@ static TilePar make_par(const TileState* t, const DevState& s, int obs_dtype) {
     p.pstride = (size_t)s.N * s.RS * s.HW;
     p.env_words = (size_t)s.RS * s.HW;
     p.step_bytes = (size_t)s.N * s.W * s.H * 3 * obs_elem_bytes(obs_dtype);
+    p.overlap = t->overlap ? 1 : 0;
     return p;
 }
 
