@@ -159,11 +159,13 @@ def _rollout_against_oracle(gpu, orc, steps, chunk, policy, check_state_every):
     return events
 
 
-@pytest.fixture(params=["two_phase", "fused"])
+@pytest.fixture(params=["overlapped", "phased", "fused"])
 def tile_pass(request, monkeypatch):
-    """Both step structures of the tile kernel: the default two-phase one (tick, then observation) and the opt-in fused
+    """The three step structures of the tile kernel: the default (tick, then observation, with finish / the next agent phase /
+    cluster barrier Y overlapped with the observation), the strictly phased flow (WF_TILE_OVERLAP=0) and the opt-in fused
     pass (WF_TILE_FUSED=1: the tick of step k emits the observation of step k-1 in the same cp.async-staged sweep)."""
     monkeypatch.setenv("WF_TILE_FUSED", "1" if request.param == "fused" else "0")
+    monkeypatch.setenv("WF_TILE_OVERLAP", "0" if request.param == "phased" else "1")
     return request.param
 
 

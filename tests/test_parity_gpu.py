@@ -418,6 +418,17 @@ def test_tile_fused_pass_matches_oracle(monkeypatch, T, CS, cfg):
     _tile_geometry_case(monkeypatch, T, CS, cfg)
 
 
+@pytest.mark.parametrize("T,CS", [(128, 2), (256, 4), (128, 8)])
+@pytest.mark.parametrize("cfg", [dict(width=64, height=64, seed=721, make_rivers=True, wind="random", extra_ignitions=3),
+                                 dict(width=100, height=70, seed=722, wind=[0.85, (1, 0)], extra_ignitions=6, a_speed=2)],
+                         ids=["64_rivers", "100x70_aspeed2"])
+def test_tile_phased_flow_matches_oracle(monkeypatch, T, CS, cfg):
+    """WF_TILE_OVERLAP=0: the strictly phased step (full cluster barrier Y, finish, then the observation) that the default
+    overlapped flow replaced; kept as the A/B reference."""
+    monkeypatch.setenv("WF_TILE_OVERLAP", "0")
+    _tile_geometry_case(monkeypatch, T, CS, cfg)
+
+
 def test_burning_border_point_is_not_its_own_goal():
     """W > H: the reference's literal border points [HEIGHT-1, y] (environment.py:222) form a column INSIDE the
     map, and for 24x13 the fire origin (12, 6) sits on it.  pyastar.astar_path returns an empty path when

@@ -1678,7 +1678,7 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     t->P_R = P_FU0 + 2;
     choose_geometry(s, t->T, t->CS);
     t->fused = env_int("WF_TILE_FUSED", 0) != 0;
-    t->overlap = env_int("WF_TILE_OVERLAP", 0) != 0;
+    t->overlap = env_int("WF_TILE_OVERLAP", 1) != 0;  // default on; 0: the strictly phased flow (A/B, tests)
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = set_smem_attr<5, 1, false>();
     if (e == cudaSuccess) e = set_smem_attr<5, 4, false>();
