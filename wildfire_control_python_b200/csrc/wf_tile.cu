@@ -1399,12 +1399,8 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
         // layer was fixed by this step's agent phase; they wait for Y afterwards).  The observation is speculative in one
         // respect: if the episode ends here and auto_reset is on, it is emitted again after the reset.  The rare step whose
         // reward needs a whole-cluster pass (seed_cells_touch) finishes after the observation instead.
-        if (!FU && t.overlap) sync_env<CL>();  // agent phase 0 is visible; from here on barrier X is split (see below)
         for (int k = 0; !FU && t.overlap && k < io.K; ++k) {
-            // Barrier X of this step -- every CTA's agent phase k has read the planes, so they may be written again -- was
-            // completed at the end of the previous iteration: a warp ARRIVES at it as soon as its own part is done (warp 0 after
-            // the agent phase, the others after barrier Y) and waits for it only once its CTA has finished the observation, so a
-            // CTA that is done does not wait for the slowest CTA's observation before it ticks again.
+            sync_env<CL>();  // barrier X: agent phase k (and everything thread 0 wrote) is visible; no plane is written before
             const bool act = ss.act != 0;
             int digw = ss.dig_word;
             const int ovis = ss.obs_agent[k & 1][0], oax = ss.obs_agent[k & 1][1], oay = ss.obs_agent[k & 1][2];
@@ -1418,17 +1414,16 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                 flood<CL>(e, t, red, xch, par, ss);
             }
             const int warp = tid >> 5;
-            int cur = 0;
             if (act) {
                 tick_slice<FB, VW>(e, s, c, t, sc, ss, dt != 0, digw, red, qmem);
-                cur = sc[WF_S_RESERVED];  // (before thread 0 flips it)
-                __syncthreads();          // red[] is complete, this CTA's planes are final
+                const int cur = sc[WF_S_RESERVED];  // (before thread 0 flips it)
+                __syncthreads();                    // red[] is complete, this CTA's planes are final
                 if (CL) {
                     if (tid < kRed * e.CS) st_shared_cluster(&xch[par][e.rank][tid & (kRed - 1)], (uint32_t)(tid / kRed), red[tid & (kRed - 1)]);
                     cluster_arrive();  // barrier Y, first half
                 }
                 if (warp == 0) {
-                    if (CL) cluster_wait();  // barrier Y, second half: every CTA's tick is done
+                    if (CL) cluster_wait();
                     if (tid < kRed) {
                         int v = 0;
                         if (CL) { for (int r = 0; r < e.CS; ++r) v += xch[par][r][tid]; }
@@ -1449,14 +1444,16 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                             if (!ss.reset_now && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
                         }
                     }
-                    __syncwarp();
-                    if (CL) cluster_arrive();  // barrier X of step k + 1, first half (a late agent phase gets its own barrier below)
                 }
                 if (CL) par ^= 1;
                 if (obs_k != nullptr) emit_obs_slice(e, obs_k, io.obs_dtype, spread3, tab8, qmem, ovis, oax, oay, &ss.obs_ctr);
-                if (CL && warp != 0) {
-                    cluster_wait();    // barrier Y, second half
-                    cluster_arrive();  // barrier X of step k + 1, first half
+                if (CL && warp != 0) cluster_wait();  // barrier Y, second half
+                __syncthreads();  // what thread 0 decided is visible
+                if (ss.slow) {
+                    const int scratch = dt ? ((cur & 1) ? t.P_S1 : t.P_S0) : ((cur & 1) ? t.P_S0 : t.P_S1);  // not the current sources
+                    const int touches = seed_cells_touch<CL>(e, t, scratch, red, xch, par, ss) ? 1 : 0;
+                    if (tid == 0) finish_step(k, dt, touches, ss.keep[0], ss.keep[1], ss.keep[2]);
+                    __syncthreads();
                 }
             } else {
                 if (tid == 0) {  // frozen env: reward 0, done 1, nothing moves
@@ -1468,19 +1465,10 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                     ss.slow = 0;
                     if (k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
                 }
-                __syncthreads();  // (the observation counter was zeroed by thread 0 at the end of the previous iteration)
-                if (CL) cluster_arrive();
                 if (obs_k != nullptr) emit_obs_slice(e, obs_k, io.obs_dtype, spread3, tab8, qmem, ovis, oax, oay, &ss.obs_ctr);
-            }
-            __syncthreads();         // this CTA is done with the observation (its planes may change again); thread 0's decisions are visible
-            if (CL) cluster_wait();  // barrier X of step k + 1, second half: usually complete by now
-            const bool rare = act && (ss.slow || ss.reset_now);
-            if (ss.slow) {
-                const int scratch = dt ? ((cur & 1) ? t.P_S1 : t.P_S0) : ((cur & 1) ? t.P_S0 : t.P_S1);  // not the current sources
-                const int touches = seed_cells_touch<CL>(e, t, scratch, red, xch, par, ss) ? 1 : 0;
-                if (tid == 0) finish_step(k, dt, touches, ss.keep[0], ss.keep[1], ss.keep[2]);
                 __syncthreads();
             }
+            const bool late_agent = act && (ss.slow || ss.reset_now);
             if (ss.reset_now) {
                 reset_env<FB, CL>(e, s, c, t, nullptr, sc, ss, red, xch, par);
                 if (tid == 0) ss.obs_ctr = 0;
@@ -1490,12 +1478,10 @@ __global__ void __launch_bounds__(WF_TILE_MAXT, WF_TILE_MINB) tile_rollout_kerne
                 __syncthreads();
             }
             if (tid == 0) {
-                if (rare && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
+                if (late_agent && k + 1 < io.K) agent_phase(e, c, t, io, s, k + 1, do_tick, sc, ss, writer);
                 ss.obs_ctr = 0;
                 ss.slow = 0;
             }
-            if (rare) sync_env<CL>();  // the late agent phase: its own full barrier X
-            else __syncthreads();      // (thread 0's bookkeeping before anybody starts the next observation)
         }
         for (int k = 0; (FU || !t.overlap) && k < io.K; ++k) {
             WF_TSTAMP(0);
