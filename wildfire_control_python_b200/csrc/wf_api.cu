@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 #include <chrono>
 
 #include "wf_families.cuh"
@@ -591,18 +592,24 @@ int wf_set_policy_mlp(wf_env* e, const float* k1, const float* b1, const float* 
     WF_QUIESCE(e);
     const DevState& s = e->st;
     const int n_in = s.W * s.H * 3, A = e->cfg.n_actions;
-    const size_t n_w1 = (size_t)n_in * hidden, total = n_w1 + hidden + (size_t)hidden * A + A;
-    std::string buf(total * sizeof(float), '\0');
-    float* h = reinterpret_cast<float*>(&buf[0]);
-    std::memcpy(h, k1, n_w1 * sizeof(float));
+    // device layout (MlpPolicy): w1 [n_in][64] permuted for the lanes | base [64] | w2 [2][64][4] | b2 [8]
+    const int L = s.RS, hpl = 64 / L;
+    const size_t n_w1 = (size_t)n_in * 64, total = n_w1 + 64 + 2 * 64 * 4 + 8;
+    std::vector<float> hbuf(total, 0.0f);
+    float* h = hbuf.data();
+    for (int f = 0; f < n_in; ++f)
+        for (int j = 0; j < hidden; ++j) h[(size_t)f * 64 + (j % L) * hpl + j / L] = k1[(size_t)f * hidden + j];
     float* base = h + n_w1;
     for (int j = 0; j < hidden; ++j) {  // the empty map: every cell free (channel 2), no fire, no agent
         double acc = b1[j];
         for (int cell = 0; cell < s.W * s.H; ++cell) acc += k1[(size_t)(cell * 3 + 2) * hidden + j];
         base[j] = (float)acc;
     }
-    std::memcpy(base + hidden, k2, (size_t)hidden * A * sizeof(float));
-    std::memcpy(base + hidden + (size_t)hidden * A, b2, A * sizeof(float));
+    float* w2 = base + 64;
+    for (int j = 0; j < hidden; ++j)
+        for (int b = 0; b < A; ++b) w2[(size_t)(b / 4) * 256 + j * 4 + (b & 3)] = k2[(size_t)j * A + b];
+    float* bias2 = w2 + 512;
+    for (int b = 0; b < 8; ++b) bias2[b] = b < A ? b2[b] : -INFINITY;
     cudaFree(e->mlp_dev);
     e->mlp_dev = nullptr;
     e->mlp = MlpPolicy{};
@@ -610,8 +617,8 @@ int wf_set_policy_mlp(wf_env* e, const float* k1, const float* b1, const float* 
     WF_CUDA(cudaMemcpy(e->mlp_dev, h, total * sizeof(float), cudaMemcpyHostToDevice));
     e->mlp.w1 = e->mlp_dev;
     e->mlp.base = e->mlp_dev + n_w1;
-    e->mlp.w2 = e->mlp.base + hidden;
-    e->mlp.b2 = e->mlp.w2 + (size_t)hidden * A;
+    e->mlp.w2 = e->mlp.base + 64;
+    e->mlp.b2 = e->mlp.w2 + 512;
     e->mlp.hid = hidden;
     e->mlp.n_actions = A;
     e->mlp.eps_u32 = eps >= 1.0 ? 0xffffffffu : (uint32_t)(eps * 4294967296.0);

@@ -4,12 +4,14 @@
 
 namespace wf {
 
-// Q-network of WF_POLICY_MLP, device pointers (owned by the handle).
+// Q-network of WF_POLICY_MLP, device pointers (owned by the handle).  Everything is padded to 64 hidden units and
+// 8 actions (zero weights; -inf bias for the missing actions), so the kernel has no bounds tests.
 struct MlpPolicy {
-    const float* w1;    // [n_in][hid], Keras orientation
-    const float* base;  // [hid]: bias1 + sum over cells of w1[(cell, channel 2)] -- the all-free, no-fire, no-agent map
-    const float* w2;    // [hid][n_actions]
-    const float* b2;    // [n_actions]
+    const float* w1;    // [n_in][64]: hidden unit j = x + L*i of a row sits at x*(64/L) + i (L = lanes per env), i.e. the
+                        // units one lane accumulates are adjacent: one 16- or 8-byte load per changed input bit
+    const float* base;  // [64]: bias1 + sum over cells of w1[(cell, channel 2)] -- the all-free, no-fire, no-agent map
+    const float* w2;    // [2][64] float4: actions 0..3 and 4..7 of every hidden unit
+    const float* b2;    // [8]
     int32_t hid, n_actions;
     uint32_t eps_u32;   // explore iff a 32-bit draw is below this
 };

@@ -289,12 +289,18 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     // leave for host memory as ONE 128-byte-aligned block of 16-byte stores -- whole PCIe write transactions instead of
     // the 4-byte-per-lane stores of unaligned 152-byte records (which cost ~25 us per step on the link)
     __shared__ __align__(16) uint32_t srv_block[SRV ? kWarpsPerBlock * 97 + 31 : 1];  // (+ slack: the sector copy reads 7-word groups)
+    __shared__ float4 mlp_w2[MLP ? 2 * kHidMax : 1];  // second layer (MlpPolicy::w2), read every step
+    __shared__ float mlp_b2[kActMax];
     for (int v = threadIdx.x; v < 256; v += blockDim.x) {
         uint32_t o = 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) o |= ((v >> i) & 1u) << (3 * i);
         spread3[v] = o;
         tab8[v] = make_uint2(((v & 15u) * 0x00204081u) & 0x01010101u, (((v >> 4) & 15u) * 0x00204081u) & 0x01010101u);
+    }
+    if (MLP) {
+        for (int v = threadIdx.x; v < 2 * kHidMax; v += blockDim.x) mlp_w2[v] = reinterpret_cast<const float4*>(io.mlp.w2)[v];
+        if (threadIdx.x < kActMax) mlp_b2[threadIdx.x] = io.mlp.b2[threadIdx.x];
     }
     __syncthreads();
 
@@ -340,7 +346,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     uint32_t pA = 0u, pF = 0u, pFree = validmask;  // the empty map: what `base` stands for
     if (MLP) {
 #pragma unroll
-        for (int i = 0; i < HPL; ++i) hacc[i] = (x + L * i < io.mlp.hid) ? (double)io.mlp.base[x + L * i] : 0.0;
+        for (int i = 0; i < HPL; ++i) hacc[i] = (double)io.mlp.base[x + L * i];
     }
 
     if (io.reset_mode) {
@@ -426,67 +432,82 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 if (SRV) action = valid_env ? __ldcg(&io.actions[env]) : -1;  // HBM copy, rewritten every step (L2, not L1)
                 else action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else if (MLP) {
-                const int hid = io.mlp.hid, A = io.mlp.n_actions;
-                // ---- first layer, incrementally: rows of the observation bits that changed since the last evaluation
+                // ---- first layer, incrementally: the weight rows of the observation bits that changed since the last
+                // evaluation.  Per round the first lane of the env that still has a changed bit announces one of them
+                // (input index and its new value, one shuffle); every lane then adds or subtracts its HPL weights of
+                // that row (one vector load: MlpPolicy::w1 keeps them adjacent).
                 const uint32_t cA = (a.vis && x == a.ax) ? (1u << a.ay) : 0u, cF = r.F, cFree = ~r.I & validmask;
-                const uint32_t dA = cA ^ pA, dF = cF ^ pF, dFree = cFree ^ pFree;
+                uint32_t dA = cA ^ pA, dF = cF ^ pF, dFree = cFree ^ pFree;
                 pA = cA; pF = cF; pFree = cFree;
-                uint32_t rows = group_bits(__ballot_sync(FULL, (dA | dF | dFree) != 0u));
-                while (__any_sync(FULL, rows != 0u)) {
-                    const bool have = rows != 0u;
-                    const int row = have ? __ffs(rows) - 1 : 0;
-                    rows &= rows - 1u;
-                    const int src = sub * L + row;
-                    uint32_t bA = __shfl_sync(FULL, dA, src), bF = __shfl_sync(FULL, dF, src), bR = __shfl_sync(FULL, dFree, src);
-                    const uint32_t nA = __shfl_sync(FULL, cA, src), nF = __shfl_sync(FULL, cF, src), nR = __shfl_sync(FULL, cFree, src);
-                    if (!have) bA = bF = bR = 0u;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        uint32_t m = ch == 0 ? bA : ch == 1 ? bF : bR;
-                        const uint32_t now = ch == 0 ? nA : ch == 1 ? nF : nR;
-                        while (m) {
-                            const int y = __ffs(m) - 1;
-                            m &= m - 1u;
-                            const float* wrow = io.mlp.w1 + (size_t)((row * H + y) * 3 + ch) * hid;
-                            const bool on = (now >> y) & 1u;
-#pragma unroll
-                            for (int i = 0; i < HPL; ++i) {
-                                const int j = x + L * i;
-                                if (j < hid) {
-                                    const double wv = (double)wrow[j];
-                                    hacc[i] = on ? hacc[i] + wv : hacc[i] - wv;
-                                }
-                            }
+                for (;;) {
+                    const uint32_t pending = __ballot_sync(FULL, (dA | dF | dFree) != 0u);
+                    if (pending == 0u) break;
+                    const uint32_t mine = group_bits(pending);
+                    const int owner = mine ? __ffs(mine) - 1 : 0;
+                    uint32_t code = 0u;
+                    if (mine != 0u && x == owner) {
+                        const int ch = dA ? 0 : dF ? 1 : 2;
+                        const uint32_t m = dA ? dA : dF ? dF : dFree;
+                        const uint32_t now = dA ? cA : dF ? cF : cFree;
+                        const uint32_t low = m & (0u - m);
+                        const int y = __ffs(m) - 1;
+                        if (ch == 0) dA ^= low;
+                        else if (ch == 1) dF ^= low;
+                        else dFree ^= low;
+                        code = ((uint32_t)((x * H + y) * 3 + ch) << 1) | ((now & low) ? 1u : 0u);
+                    }
+                    code = __shfl_sync(FULL, code, sub * L + owner);
+                    if (mine) {
+                        const float* wrow = io.mlp.w1 + (size_t)(code >> 1) * kHidMax + x * HPL;
+                        const uint32_t flip = (code & 1u) ? 0u : 0x80000000u;  // bit cleared: subtract the row
+                        float wv[HPL];
+                        if (HPL == 4) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(wrow));
+                            wv[0] = v.x; wv[1] = v.y; wv[HPL > 2 ? 2 : 0] = v.z; wv[HPL > 3 ? 3 : 0] = v.w;
+                        } else {
+                            const float2 v = __ldg(reinterpret_cast<const float2*>(wrow));
+                            wv[0] = v.x; wv[1] = v.y;
                         }
+#pragma unroll
+                        for (int i = 0; i < HPL; ++i) hacc[i] += (double)__uint_as_float(__float_as_uint(wv[i]) ^ flip);
                     }
                 }
-                // ---- sigmoid, second layer, argmax (np.argmax: the first maximum)
+                // ---- sigmoid and second layer: 8 partial Q values per lane (padded units and actions carry zero weights)
                 float q[kActMax];
 #pragma unroll
                 for (int b = 0; b < kActMax; ++b) q[b] = 0.0f;
 #pragma unroll
                 for (int i = 0; i < HPL; ++i) {
                     const int j = x + L * i;
-                    if (j < hid) {
-                        const float sj = 1.0f / (1.0f + __expf(-(float)hacc[i]));
-#pragma unroll
-                        for (int b = 0; b < kActMax; ++b)
-                            if (b < A) q[b] = fmaf(sj, io.mlp.w2[j * A + b], q[b]);
-                    }
+                    const float sj = __fdividef(1.0f, 1.0f + __expf(-(float)hacc[i]));
+                    const float4 wa = mlp_w2[j], wb = mlp_w2[kHidMax + j];
+                    q[0] = fmaf(sj, wa.x, q[0]); q[1] = fmaf(sj, wa.y, q[1]); q[2] = fmaf(sj, wa.z, q[2]); q[3] = fmaf(sj, wa.w, q[3]);
+                    q[4] = fmaf(sj, wb.x, q[4]); q[5] = fmaf(sj, wb.y, q[5]); q[6] = fmaf(sj, wb.z, q[6]); q[7] = fmaf(sj, wb.w, q[7]);
                 }
+                // ---- sum over the env's lanes, transposing on the way: every butterfly step halves the values a lane
+                // carries (it keeps the half its lane bit selects and adds the partner's copy of it), so 8 values cost
+                // 4 + 2 + 1 shuffles and lane x ends with Q of action (x >> (log2 L - 3)) & 7 ...
+                const bool h3 = (x & (L / 2)) != 0, h2 = (x & (L / 4)) != 0, h1 = (x & (L / 8)) != 0;
+                float q4[4], q2[2], qv;
 #pragma unroll
-                for (int b = 0; b < kActMax; ++b) {
-                    if (b < A) {
+                for (int b = 0; b < 4; ++b)
+                    q4[b] = (h3 ? q[b + 4] : q[b]) + __shfl_xor_sync(FULL, h3 ? q[b] : q[b + 4], L / 2, L);
 #pragma unroll
-                        for (int o = L / 2; o > 0; o >>= 1) q[b] += __shfl_xor_sync(FULL, q[b], o, L);
-                        q[b] += io.mlp.b2[b];
-                    }
+                for (int b = 0; b < 2; ++b)
+                    q2[b] = (h2 ? q4[b + 2] : q4[b]) + __shfl_xor_sync(FULL, h2 ? q4[b] : q4[b + 2], L / 4, L);
+                qv = (h1 ? q2[1] : q2[0]) + __shfl_xor_sync(FULL, h1 ? q2[0] : q2[1], L / 8, L);
+#pragma unroll
+                for (int o = L / 16; o > 0; o >>= 1) qv += __shfl_xor_sync(FULL, qv, o, L);
+                int greedy = (h3 ? 4 : 0) | (h2 ? 2 : 0) | (h1 ? 1 : 0);
+                qv += mlp_b2[greedy];  // -inf for actions the network does not have
+                // ... and the argmax (np.argmax: the first maximum) is a butterfly over those three lane bits (the first
+                // partner's action index is known without a shuffle)
+#pragma unroll
+                for (int bit = 0; bit < 3; ++bit) {
+                    const float other = __shfl_xor_sync(FULL, qv, (L / 8) << bit, L);
+                    const int other_a = bit == 0 ? (greedy ^ 1) : __shfl_xor_sync(FULL, greedy, (L / 8) << bit, L);
+                    if (other > qv || (other == qv && other_a < greedy)) { qv = other; greedy = other_a; }
                 }
-                int greedy = 0;
-                float best = q[0];
-#pragma unroll
-                for (int b = 1; b < kActMax; ++b)
-                    if (b < A && q[b] > best) { best = q[b]; greedy = b; }
                 // ---- eps-greedy: EXPLORE stream, one Philox block serves two consecutive steps
                 if ((a.t & 1u) == 0u || ablk_ep != a.episode || ablk_idx != (a.t >> 1)) {
                     philox4x32_10((uint32_t)(c.env_id_base + env), a.episode, a.t >> 1, kStreamExplore, c.key0, c.key1, ablk);
