@@ -178,6 +178,15 @@ int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32
  * hostage by a caller that stops stepping (other work on the device is delayed by at most that long).
  * A batch with more CTAs (8 envs of <= 16 rows, 4 of up to 32 rows, each) than the GPU can hold resident cannot be
  * served: the first wf_step_host then turns the session off and the launch-per-step path takes over.
+ *   wf_host_session(env, 2)  session with a PERSISTENT OBSERVATION ARRAY (the convention of vectorised Gym environments
+ * with copy=False): the caller passes the same obs_host on every wf_step_host and does not write to it between calls; the
+ * kernel then sends, per record, only the list of elements that changed since the previous step (up to 14 per record of
+ * two 14x14 envs: 32 instead of 152 bytes over PCIe) and the host threads patch those elements in place.  A record with
+ * more changes (a reset env, a large fire tick) travels in full and is expanded as in mode 1.  The array is always complete
+ * and equal to what mode 1 delivers after every call: the library compares obs_host with the previous call's pointer and
+ * asks for every record in full whenever it differs, on the first step after the kernel was (re)started and hence after
+ * every other entry point used in between.  What it cannot detect is the caller overwriting the array: then the patched
+ * elements are right and the others stay as the caller left them until their record next travels in full.
  * Returns WF_ERR_INVALID for the tile family.  wf_host_session_active: 0 off, 1 on (kernel parked), 2 kernel resident. */
 int wf_host_session(wf_env* env, int32_t on);
 int wf_host_session_active(const wf_env* env);

@@ -200,7 +200,7 @@ def test_calls_leave_the_current_device_alone():
                                         (dict(width=32, height=32, seed=605, a_speed=2, allow_dig_toggle=True, n_actions=5), 19),
                                         (dict(width=14, height=14, seed=606, fuel=40, extra_ignitions=2), 64)],
                          ids=["14_n601", "10_n7", "20_n530", "17x13_rivers_windrandom", "32_aspeed2_toggle", "14_fuel40"])
-@pytest.mark.parametrize("transport", ["flag", "sectors"])
+@pytest.mark.parametrize("transport", ["flag", "sectors", "persistent"])
 def test_host_session_matches_oracle(monkeypatch, cfg, n_envs, transport):
     """Every action / reward / done / observation of a session against the oracle, with auto-reset inside the resident
     kernel, and with the session interrupted by other entry points (which park the kernel) and by idle periods (after
@@ -215,7 +215,9 @@ def test_host_session_matches_oracle(monkeypatch, cfg, n_envs, transport):
     gpu.reset()
     for e in orc:
         e.reset()
-    assert gpu.host_session(True) and gpu.host_session_state == 1
+    # "persistent": wf_host_session mode 2 -- step_host hands out the same array every call, only the elements that
+    # changed travel (change-list records; records with more than 14 changes, e.g. reset envs, travel in full)
+    assert gpu.host_session(True, persistent_obs=transport == "persistent") and gpu.host_session_state == 1
     for s in range(150):
         acts = np.array([e.random_action() for e in orc], np.int32)
         obs, rew, done, _ = gpu.step_host(acts)
@@ -264,6 +266,37 @@ def test_host_session_pageable_buffers_and_plain_path_agree():
         assert L.wf_step_host(a._h, acts.ctypes.data, obs.ctypes.data, 0, rew.ctypes.data, done.ctypes.data) == 0
         o2, r2, d2, _ = b.step_host(acts)
         assert np.array_equal(obs, o2) and np.array_equal(rew, r2) and np.array_equal(done.astype(bool), d2), s
+
+
+@pytest.mark.gpu
+def test_host_session_persistent_obs_follows_the_callers_array():
+    """Mode 2 patches the caller's array in place; a different array than the previous call's (here: two arrays in turn,
+    then one array for a while, then a fresh one) gets every record in full, so each array handed in is complete."""
+    from wildfire_control_python_b200 import _lib
+    from wildfire_control_python_b200.batched import BatchedForestFire
+    N, cfg = 333, dict(width=14, height=14, seed=612, auto_reset=True)
+    a, b = BatchedForestFire(N, **cfg), BatchedForestFire(N, **cfg)
+    a.reset(); b.reset()
+    L = _lib.lib()
+    assert L.wf_host_session(a._h, 2) == 0
+    bufs = [np.full((N, 14, 14, 3), 7, np.uint8) for _ in range(3)]
+    rew = np.zeros(N); done = np.zeros(N, np.uint8)
+    rng = np.random.default_rng(2)
+    for s in range(120):
+        obs = bufs[s & 1] if s < 40 else bufs[0] if s < 100 else bufs[2]
+        if s == 100:
+            bufs[2][:] = 9  # never seen by the library: must come back complete
+        acts = rng.integers(0, 4, N, dtype=np.int32)
+        assert L.wf_step_host(a._h, acts.ctypes.data, obs.ctypes.data, 0, rew.ctypes.data, done.ctypes.data) == 0
+        o2, r2, d2, _ = b.step_host(acts)
+        assert np.array_equal(obs, o2) and np.array_equal(rew, r2) and np.array_equal(done.astype(bool), d2), s
+    assert L.wf_host_session(a._h, 1) == 0  # back to full records, same array: nothing stale
+    for s in range(10):
+        acts = rng.integers(0, 4, N, dtype=np.int32)
+        assert L.wf_step_host(a._h, acts.ctypes.data, bufs[2].ctypes.data, 0, rew.ctypes.data, done.ctypes.data) == 0
+        o2, r2, d2, _ = b.step_host(acts)
+        assert np.array_equal(bufs[2], o2) and np.array_equal(rew, r2), s
+    assert L.wf_host_session(a._h, 3) == _lib.WF_ERR_INVALID
 
 
 @pytest.mark.gpu

@@ -22,11 +22,11 @@ import numpy as np
 sys.path.insert(0, %r)
 import torch
 from wildfire_control_python_b200 import BatchedForestFire
-N, K, session = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3] == "1"
+N, K, session = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3] != "0"
 env = BatchedForestFire(N, width=14, height=14, auto_reset=True, seed=0)
 env.reset()
 if session:
-    assert env.host_session(True)
+    assert env.host_session(True, persistent_obs=sys.argv[3] == "2")
 acts = np.random.default_rng(0).integers(0, 4, size=(256, N), dtype=np.int32)
 for k in range(50):
     env.step_host(acts[k])
@@ -43,13 +43,15 @@ env.close()
 
 def run(name, env_extra, session, N, K):
     env = dict(os.environ, WF_HOST_TIMING="1", **env_extra)
-    r = subprocess.run([sys.executable, "-c", WORKER, str(N), str(K), "1" if session else "0"], env=env, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, "-c", WORKER, str(N), str(K), str(int(session))], env=env, capture_output=True, text=True)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if not line:
         print(f"{name:22s} FAILED: {r.stderr[-400:]}", flush=True)
         return
     d = json.loads(line[-1])
     extra = " | ".join(l for l in r.stderr.splitlines() if l.startswith("wf_"))
+    if os.environ.get("E2E_AB_FULL"):
+        print(r.stderr, flush=True)
     print(f"{name:22s} best {d['best']:6.1f}  median {d['median']:6.1f} us/step   threads {d['threads']:2d}  {extra}", flush=True)
 
 
@@ -62,6 +64,11 @@ if __name__ == "__main__":
             run(f"session/{t}", {"WF_HOST_THREADS": str(t)}, True, N, K)
         for t in (12, 15, 6, 3):
             run(f"session/{t} flag+fence", {"WF_HOST_THREADS": str(t), "WF_SESSION_SECTORS": "0"}, True, N, K)
+        sys.exit(0)
+    if len(sys.argv) > 3 and sys.argv[3] == "persistent":
+        for t in (12, 6, 4, 3, 2, 1):
+            run(f"session/{t}", {"WF_HOST_THREADS": str(t)}, 1, N, K)
+            run(f"persistent/{t}", {"WF_HOST_THREADS": str(t)}, 2, N, K)
         sys.exit(0)
     run("graph", {"WF_HOST_GRAPH": "1"}, False, N, K)
     run("direct", {"WF_HOST_PACKED": "direct"}, False, N, K)

@@ -232,12 +232,16 @@ class BatchedForestFire:
             _lib.check(rc)
         return hb["np_obs"], hb["np_reward"], hb["np_done"], {}
 
-    def host_session(self, on: bool = True) -> bool:
+    def host_session(self, on: bool = True, persistent_obs: bool = False) -> bool:
         """Turn the step-server session of ``step_host`` on / off (``wf_host_session``, include/wildfire.h): the step
         kernel stays resident and is driven through mapped host memory -- no launch, copy call or synchronise per
-        step.  Returns whether a session is on afterwards (False for grids larger than 32x32: not supported there)."""
+        step.  Returns whether a session is on afterwards (False for grids larger than 32x32: not supported there).
+
+        ``persistent_obs=True``: ``step_host`` returns the same observation array every call anyway (like a vectorised
+        Gym environment with ``copy=False``); with this flag the caller promises not to WRITE to it between steps, and
+        only the elements that changed cross PCIe and are patched in place (mode 2 of ``wf_host_session``)."""
         L = _lib.lib()
-        rc = L.wf_host_session(self._h, 1 if on else 0)
+        rc = L.wf_host_session(self._h, (2 if persistent_obs else 1) if on else 0)
         if rc == _lib.WF_ERR_INVALID and on:
             return False
         _lib.check(rc)

@@ -26,7 +26,8 @@ void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t 
 bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
                              int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
                              uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
-                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors);
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors,
+                             const uint32_t* full_area, int64_t full_stride);
 int hostpool_default_threads();
 double hostpool_first_flag_seconds(const HostPool* p);
 }  // namespace wf
@@ -122,6 +123,12 @@ struct wf_env {
         double t_wait;              // WF_HOST_TIMING: seconds between ringing and the last slice expanded
         int slices, ctas_per_slice;
         int sectors;                // sectors per record of the self-validating transport (0: completion flags + system fence)
+        bool persistent_obs;        // wf_host_session mode 2: change-list records, the caller's array is patched in place
+        uint32_t* full;             // mapped host [records][full_stride]: whole bit streams of the records flagged "full"
+        uint32_t* full_dev;
+        int full_stride;
+        const void* frame_ptr;      // the caller's observation array as of the last step served (nullptr: not in step with it)
+        int64_t full_frames;        // steps that asked for every record in full
         int64_t launches, steps, relaunch_races;
     } sess;
 };
@@ -424,6 +431,7 @@ void wf_destroy(wf_env* e) {
     if (e->sess.ctl) cudaFreeHost(e->sess.ctl);
     if (e->sess.actions) cudaFreeHost(e->sess.actions);
     if (e->sess.rec) cudaFreeHost(e->sess.rec);
+    if (e->sess.full) cudaFreeHost(e->sess.full);
     cudaFree(e->sess.sync_dev);
     cudaFree(e->sess.actions_hbm);
     if (e->sess.steps && getenv("WF_HOST_TIMING")) {
@@ -725,7 +733,11 @@ static int session_launch(wf_env* e) {
     srv.seq0 = ss.seq;
     srv.generation = ss.generation;
     srv.ctas_per_slice = ss.ctas_per_slice;
-    srv.sectors = ss.sectors;
+    srv.sectors = ss.persistent_obs ? 0 : ss.sectors;
+    srv.delta = ss.persistent_obs ? 1 : 0;
+    srv.full_area = ss.full_dev;
+    srv.full_stride = ss.full_stride;
+    ss.frame_ptr = nullptr;  // a launch's first step sends every record in full
     const char* idle = getenv("WF_SESSION_IDLE_US");
     srv.dbg = ss.dbg_dev;
     srv.idle_ns = 1000ull * (unsigned long long)((idle && atoll(idle) > 0) ? atoll(idle) : 2000);
@@ -766,7 +778,7 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));
             std::memset(ss.ctl, 0, (32 + 16 * kSessMaxSlices) * sizeof(uint32_t));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.ctl_dev), ss.ctl, 0));
-            const size_t act_bytes = (size_t)((s.N + 3) / 4) * 4 * sizeof(int32_t);
+            const size_t act_bytes = (size_t)((s.N + 3) / 4 + 1) * 4 * sizeof(int32_t);  // (+ one chunk: the full-frame request)
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.actions), act_bytes, cudaHostAllocMapped));
             std::memset(ss.actions, 0, act_bytes);
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), act_bytes));
@@ -780,6 +792,9 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
                                                   : (size_t)(kRecordsPerCta * (rec_words + 1) + 31) / 32 * 32;  // one CTA's records, whole lines
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.rec), (size_t)ctas * block_words * sizeof(uint32_t), cudaHostAllocMapped));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.rec_dev), ss.rec, 0));
+            ss.full_stride = (int)((rec_words + 3) / 4 * 4);
+            WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.full), (size_t)records * ss.full_stride * sizeof(uint32_t), cudaHostAllocMapped));
+            WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.full_dev), ss.full, 0));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.sync_dev), (16 + kSessMaxSlices) * sizeof(uint32_t)));
             WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.dbg_dev), 8 * sizeof(unsigned long long)));
             WF_CUDA(cudaMemset(ss.dbg_dev, 0, 8 * sizeof(unsigned long long)));
@@ -793,17 +808,26 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
     }
     volatile uint32_t* ctl = ss.ctl;
     std::memcpy(ss.actions, actions_host, (size_t)s.N * sizeof(int32_t));
+    uint64_t db_flags = 0;
+    if (ss.persistent_obs) {  // another array than last step's (or none yet): ask for every record in full
+        const bool want_full = ss.frame_ptr != obs_host;
+        db_flags = want_full ? 1u : 0u;
+        ss.full_frames += want_full ? 1 : 0;
+        ss.frame_ptr = nullptr;  // (until this step has been delivered)
+    }
     ss.seq += 1u;
     std::atomic_thread_fence(std::memory_order_release);
-    ctl[0] = ss.seq;  // ring
+    *reinterpret_cast<volatile uint64_t*>(ss.ctl) = (uint64_t)ss.seq | (db_flags << 32);  // ring (one store: number and flags)
     ss.steps += 1;
     const int64_t rps = (int64_t)ss.ctas_per_slice * 4;
     const auto t_start = std::chrono::steady_clock::now();
     for (;;) {
         const bool ok = hostpool_expand_session(e->pool, ss.rec, static_cast<uint8_t*>(obs_host), records, rec_words, env_bits, epw,
                                                 s.N, ss.ctl + 32, ss.seq, rps, reward_host, done_host, e->cfg.default_reward,
-                                                e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000, ss.sectors);
+                                                e->cfg.death_penalty, e->cfg.contained_bonus, (double)(s.W * s.H), 200000,
+                                                ss.persistent_obs ? 0 : ss.sectors, ss.persistent_obs ? ss.full : nullptr, ss.full_stride);
         if (ok) {
+            if (ss.persistent_obs) ss.frame_ptr = obs_host;
             ss.t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             e->a_iter = advance_a_iter(e, 1);  // (after the step: a relaunch below must start from the phase before it)
             return WF_OK;
@@ -837,6 +861,11 @@ int wf_host_session(wf_env* e, int32_t on) {
         int coop = 0;
         WF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
         if (!coop) return fail(WF_ERR_INVALID, "wf_host_session: the device has no cooperative launch");
+        if (on != 1 && on != 2) return fail(WF_ERR_INVALID, "wf_host_session: on must be 0, 1 or 2");
+        if (e->sess.persistent_obs != (on == 2)) {  // another record format: the kernel is started again
+            WF_QUIESCE(e);
+            e->sess.persistent_obs = on == 2;
+        }
         e->sess.wanted = true;
         return WF_OK;
     }

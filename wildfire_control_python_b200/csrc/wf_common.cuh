@@ -44,6 +44,12 @@ __host__ __device__ __forceinline__ uint32_t sector_hash(const uint32_t* w) {
     return h ^ (h >> 15);
 }
 
+// Change-list records of a step-server session with a persistent observation array (wf_host_session mode 2): per warp
+// kDeltaWords words = the status word + kDeltaEntries 16-bit entries (element index within the warp's envs << 1 | new value;
+// 0xffff: unused).  kDeltaFullBit of the status word: the warp's complete bit stream is in SrvCtl::full_area instead.
+constexpr int kDeltaWords = 8, kDeltaEntries = 14;
+constexpr uint32_t kDeltaFullBit = 0x8000u;
+
 // Bytes per observation element of a public obs_dtype (WF_OBS_U8 / WF_OBS_F32 / WF_OBS_BF16).
 __host__ __device__ __forceinline__ int obs_elem_bytes(int dtype) { return dtype == WF_OBS_F32 ? 4 : dtype == WF_OBS_BF16 ? 2 : 1; }
 constexpr uint16_t kBf16One = 0x3F80u;  // 1.0 in bfloat16

@@ -29,6 +29,12 @@ struct SrvCtl {
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
     int32_t sectors;              // != 0: records travel as self-validating 32-byte sectors (wf_common.cuh), no flags / fences
+    int32_t delta;                // != 0: change-list records (kDeltaWords words per warp, WarpIO::obs = [CTAs][4][kDeltaWords]);
+                                  // a warp whose envs changed in more than kDeltaEntries elements -- or when the host asks for
+                                  // it (actions_host[N padded to 4] != 0), or on the launch's first step -- sends its whole bit
+                                  // stream to full_area instead and sets kDeltaFullBit in the status word
+    uint32_t* full_area;          // mapped host [records][full_stride] words
+    int32_t full_stride;          // words between two records of full_area (a multiple of 4)
     unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)
     unsigned long long* dbg;      // device, 8 counters of CTA 0 (ns, summed over steps; WF_HOST_TIMING prints them):
                                   // 0 doorbell wait + action copy, 1 go -> thread 0's warp has stepped and stored, 2 CTA

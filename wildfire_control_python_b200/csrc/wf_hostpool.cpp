@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -36,6 +37,9 @@ struct ExpandJob {
     uint8_t* done;
     double default_reward, death_penalty, contained_bonus, cells;
     int64_t timeout_ns;         // session: give up waiting for a flag after this long (the caller then checks the kernel)
+    const uint32_t* full_area;  // session with a persistent observation array (wf_host_session mode 2), != nullptr: `packed` holds
+    int64_t full_stride;        // change-list records (8 words per record, blocks of 4); a record whose status word has bit 15
+                                // set is complete in full_area[record * full_stride] instead
     int64_t sectors;            // session, != 0: each record is `sectors` self-validating 32-byte sectors (7 payload words + tag =
                                 // seq ^ hash), no flags: a record is taken as soon as all its sectors validate
 };
@@ -160,37 +164,86 @@ static bool fetch_record(const ExpandJob& j, int64_t r, uint32_t* tmp, const std
     return true;
 }
 
-static bool expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
+// Change-list records: patch the elements that changed; records flagged "full" are expanded from the full area.
+static void expand_one(const ExpandJob& j, const uint32_t* rec, int64_t env0, int64_t nenv);
+static void apply_delta_records(const ExpandJob& j, int64_t r0, int64_t r1) {
+    constexpr int kWords = 8, kEntries = 14;
+#if defined(__x86_64__)
+    // The GPU has just written these lines: none is in a cache of this core, and a range of a few KB is over before the
+    // hardware prefetcher has caught on.  Ask for all of them at once.
+    {
+        const char* p0 = reinterpret_cast<const char*>(j.packed + (r0 >> 2) * (4 * kWords));
+        const char* p1 = reinterpret_cast<const char*>(j.packed + ((r1 + 3) >> 2) * (4 * kWords));
+        for (const char* p = p0; p < p1; p += 64) _mm_prefetch(p, _MM_HINT_T0);
+    }
+#endif
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint32_t* rec = j.packed + (r >> 2) * (4 * kWords) + (r & 3) * kWords;
+        const int64_t env0 = r * j.envs_per_record;
+        const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
+        const uint32_t st = rec[0];
+        if (st & 0x8000u) {
+            expand_one(j, j.full_area + r * j.full_stride, env0, nenv);
+        } else {
+            // all 14 entries, unused ones (0xffff) into a dummy byte: a loop that stops at the first unused entry
+            // mispredicts its exit once per record (55 instead of ~20 cycles per record)
+            uint8_t* out = j.out + env0 * j.env_bits;
+            const uint16_t* e = reinterpret_cast<const uint16_t*>(rec) + 2;
+            uint8_t dummy;
+#pragma GCC unroll 14
+            for (int k = 0; k < kEntries; ++k) {
+                const uint32_t v = e[k];
+                uint8_t* dst = v == 0xffffu ? &dummy : out + (v >> 1);
+                *dst = (uint8_t)(v & 1u);
+            }
+            (void)dummy;
+        }
+        for (int64_t k = 0; k < nenv; ++k) {
+            const uint32_t sk = (st >> (16 * k)) & 0x7fffu;
+            if (j.reward) j.reward[env0 + k] = decode_reward(j, sk);
+            if (j.done) j.done[env0 + k] = (uint8_t)((sk >> 3) & 1u);
+        }
+    }
+}
+
+// The observation bits of one record -> the bytes of its envs.
+static void expand_one(const ExpandJob& j, const uint32_t* rec, int64_t env0, int64_t nenv) {
 #if defined(__x86_64__)
     static const bool bmi2 = __builtin_cpu_supports("bmi2");
     static const bool avx2 = bmi2 && __builtin_cpu_supports("avx2") && !getenv("WF_HOST_NO_AVX2");
     static const bool avx512 = avx2 && __builtin_cpu_supports("avx512bw") && !getenv("WF_HOST_NO_AVX512");
-#else
-    static const bool bmi2 = false;
 #endif
+    const int64_t bits = nenv * j.env_bits;
+    const uint8_t* in = reinterpret_cast<const uint8_t*>(rec);
+    uint8_t* out = j.out + env0 * j.env_bits;
+#if defined(__x86_64__)
+    if (avx512) expand_avx512(in, out, bits >> 3);
+    else if (avx2) expand_avx2(in, out, bits >> 3);
+    else if (bmi2) expand_pdep(in, out, bits >> 3);
+    else
+#endif
+        expand_table(in, out, bits >> 3);
+    for (int64_t b = bits & ~(int64_t)7; b < bits; ++b) out[b] = (in[b >> 3] >> (b & 7)) & 1;  // ragged tail
+}
+
+static bool expand_records(const ExpandJob& j, int64_t r0, int64_t r1) {
+    if (j.full_area) {
+        apply_delta_records(j, r0, r1);
+        return true;
+    }
     const auto t_begin = std::chrono::steady_clock::now();
     int64_t blk = r0 / j.recs_per_block, in_blk = r0 % j.recs_per_block;  // (no division per record)
     for (int64_t r = r0; r < r1; ++r, ++in_blk) {
         if (in_blk == j.recs_per_block) { in_blk = 0; ++blk; }
         const int64_t env0 = r * j.envs_per_record;
         const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
-        const int64_t bits = nenv * j.env_bits;
         const uint32_t* rec = j.packed + blk * j.block_stride + in_blk * j.rec_stride;
         uint32_t tmp[7 * 16];  // sector transport: the record's payload, validated (<= 97 words)
         if (j.sectors) {
             if (!fetch_record(j, r, tmp, t_begin)) return false;
             rec = tmp;
         }
-        const uint8_t* in = reinterpret_cast<const uint8_t*>(rec);
-        uint8_t* out = j.out + env0 * j.env_bits;
-#if defined(__x86_64__)
-        if (avx512) expand_avx512(in, out, bits >> 3);
-        else if (avx2) expand_avx2(in, out, bits >> 3);
-        else if (bmi2) expand_pdep(in, out, bits >> 3);
-        else
-#endif
-            expand_table(in, out, bits >> 3);
-        for (int64_t b = bits & ~(int64_t)7; b < bits; ++b) out[b] = (in[b >> 3] >> (b & 7)) & 1;  // ragged tail
+        expand_one(j, rec, env0, nenv);
         if (j.rec_stride > j.rec_words) {  // session records: reward / done of the record's envs
             const uint32_t st = rec[j.rec_words];
             for (int64_t k = 0; k < nenv; ++k) {
@@ -217,12 +270,19 @@ public:
         }
         cv_.notify_all();
         for (auto& th : workers_) th.join();
+        if (jobs_timed_ && getenv("WF_HOST_TIMING")) {  // per thread: when its flag was seen (from the job's start) and its own work
+            fprintf(stderr, "wf_hostpool: %lld session jobs; thread: flag seen after / work (us):", (long long)jobs_timed_);
+            for (int t = 0; t < n_; ++t) fprintf(stderr, " %d: %.2f / %.2f;", t, 1e6 * t_flag_[t] / jobs_timed_, 1e6 * t_work_[t] / jobs_timed_);
+            fprintf(stderr, "\n");
+        }
     }
     int threads() const { return n_; }
     double first_flag_seconds() const { return first_flag_s_; }  // session jobs: thread 0's accumulated wait for its flag(s)
     // Returns false if a session slice timed out waiting for its completion flag (nothing of that slice was expanded).
     bool run(const ExpandJob& job) {
         job_ = job;
+        job_t0_ = std::chrono::steady_clock::now();
+        if (job.flags) jobs_timed_ += 1;
         failed_.store(0, std::memory_order_relaxed);
         pending_.store(n_ - 1, std::memory_order_relaxed);
         {
@@ -266,7 +326,12 @@ private:
             std::atomic_thread_fence(std::memory_order_acquire);
             if (t == 0) first_flag_s_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
+        const auto t_seen = std::chrono::steady_clock::now();
         if (!expand_records(job_, r0, r1)) failed_.store(1, std::memory_order_release);
+        if (job_.flags && t < 64) {
+            t_flag_[t] += std::chrono::duration<double>(t_seen - job_t0_).count();
+            t_work_[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_seen).count();
+        }
     }
     void loop(int t) {
         uint64_t seen = 0;
@@ -300,6 +365,9 @@ private:
     std::condition_variable cv_;
     bool stop_ = false;
     double first_flag_s_ = 0.0;
+    std::chrono::steady_clock::time_point job_t0_{};
+    double t_flag_[64] = {0}, t_work_[64] = {0};
+    int64_t jobs_timed_ = 0;
 };
 
 // C-level hooks used by wf_api.cu
@@ -319,7 +387,8 @@ void hostpool_expand(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t 
 bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, int64_t records, int64_t rec_words,
                              int64_t env_bits, int64_t envs_per_record, int64_t n_envs, const volatile uint32_t* flags,
                              uint32_t seq, int64_t records_per_slice, double* reward, uint8_t* done, double default_reward,
-                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors) {
+                             double death_penalty, double contained_bonus, double cells, int64_t timeout_ns, int64_t sectors,
+                             const uint32_t* full_area, int64_t full_stride) {
     ExpandJob j{};
     j.packed = packed; j.out = out; j.records = records; j.rec_words = rec_words; j.env_bits = env_bits;
     j.envs_per_record = envs_per_record; j.n_envs = n_envs; j.rec_stride = rec_words + 1;
@@ -329,6 +398,7 @@ bool hostpool_expand_session(HostPool* p, const uint32_t* packed, uint8_t* out, 
     j.flags = flags; j.seq = seq; j.records_per_slice = records_per_slice; j.reward = reward; j.done = done;
     j.default_reward = default_reward; j.death_penalty = death_penalty; j.contained_bonus = contained_bonus; j.cells = cells;
     j.timeout_ns = timeout_ns;
+    j.full_area = full_area; j.full_stride = full_stride;
     return p->run(j);
 }
 double hostpool_first_flag_seconds(const HostPool* p) { return p ? p->first_flag_seconds() : 0.0; }

@@ -279,10 +279,10 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     constexpr int EPW = 32 / L;  // envs per warp
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t GMASK = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
-    __shared__ uint32_t stream_all[kWarpsPerBlock][kStreamWords];
+    __shared__ __align__(16) uint32_t stream_all[kWarpsPerBlock][kStreamWords];
     __shared__ uint32_t spread3[256];  // bit i of the index -> bit 3i
     __shared__ uint2 tab8[256];        // bit i of the index -> byte i
-    __shared__ uint32_t srv_cmd;
+    __shared__ uint32_t srv_cmd, srv_flags;
     __shared__ unsigned long long cta_stats[2];  // env-steps and fire ticks of this CTA's envs in this launch
     if (threadIdx.x < 2) cta_stats[threadIdx.x] = 0ull;
     // SRV: the CTA's records (one per warp: up to 96 words of observation bits + the status word) are collected here and
@@ -368,6 +368,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
         uint32_t reach = 0u;    // row x of the reach mask, valid while reach_ok (group-uniform)
         bool reach_ok = false;
         uint32_t srv_step = 0u;  // SRV: steps served by this launch
+        int srv_want_full = 0;   // SRV, change-list records: the host asks for every record in full this step
         unsigned long long srv_t0 = 0ull, srv_t0b = 0ull, srv_t1 = 0ull;  // CTA 0, thread 0: time stamps of the debug counters
         for (int kk = 0; SRV || kk < io.K; ++kk) {
             const int k = SRV ? 0 : kk;  // row of the output arrays
@@ -381,11 +382,14 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         const uint32_t last = srv.seq0 + srv_step;
                         const unsigned long long t0 = global_timer_ns();
                         srv_t0 = t0;
-                        uint32_t cmd;
-                        for (;;) {
-                            cmd = *srv.doorbell;
+                        uint32_t cmd, flags;
+                        for (;;) {  // the doorbell is one 64-bit word: sequence number | flags << 32 (bit 0: every record in full)
+                            const unsigned long long db = *reinterpret_cast<const volatile unsigned long long*>(srv.doorbell);
+                            cmd = (uint32_t)db;
+                            flags = (uint32_t)(db >> 32);
                             if (cmd != last || global_timer_ns() - t0 > srv.idle_ns) break;
                         }
+                        srv_flags = flags;
                         if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
                             *srv.parked = srv.generation;
                             srv_cmd = 0xffffffffu;
@@ -414,6 +418,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         srv_t1 = global_timer_ns();
+                        if (srv.delta) srv.actions_dev[((s.N + 3) >> 2) << 2] = (int32_t)(srv_flags & 1u);  // the host's full-frame request
                         st_release_gpu(srv.go, srv_cmd);
                     }
                 } else {
@@ -429,7 +434,10 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             const bool act = valid_env && a.running;  // finished envs are frozen (reward 0, done 1)
             int action;
             if (io.actions != nullptr) {
-                if (SRV) action = valid_env ? __ldcg(&io.actions[env]) : -1;  // HBM copy, rewritten every step (L2, not L1)
+                if (SRV) {
+                    action = valid_env ? __ldcg(&io.actions[env]) : -1;  // HBM copy, rewritten every step (L2, not L1)
+                    if (srv.delta) srv_want_full = __ldcg(&io.actions[((s.N + 3) >> 2) << 2]);  // (needed after the step: the load is hidden)
+                }
                 else action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else if (MLP) {
                 // ---- first layer, incrementally: the weight rows of the observation bits that changed since the last
@@ -806,7 +814,55 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 reach_ok = false;
             }
             __syncwarp();
-            if (io.obs != nullptr) {
+            if (SRV && srv.delta) {
+                // ---- persistent observation array: send what changed since the last step this warp sent
+                const uint32_t cA = (a.vis && x == a.ax) ? (1u << a.ay) : 0u, cF = r.F, cFree = ~r.I & validmask;
+                uint32_t dA = cA ^ pA, dF = cF ^ pF, dFree = cFree ^ pFree;
+                pA = cA; pF = cF; pFree = cFree;
+                const bool want_full = srv_step == 0u || srv_want_full != 0;
+                uint32_t* const cw = srv_block + warp * kDeltaWords;
+                if (lane < kDeltaWords) cw[lane] = 0xffffffffu;
+                __syncwarp();
+                int total = want_full ? kDeltaEntries + 1 : 0;
+                while (total <= kDeltaEntries) {
+                    const bool has = (dA | dF | dFree) != 0u;
+                    const uint32_t pend = __ballot_sync(FULL, has);
+                    if (pend == 0u) break;
+                    if (has) {
+                        const int ch = dA ? 0 : dF ? 1 : 2;
+                        const uint32_t m = dA ? dA : dF ? dF : dFree;
+                        const uint32_t now = dA ? cA : dF ? cF : cFree;
+                        const uint32_t low = m & (0u - m);
+                        const int y = __ffs(m) - 1;
+                        if (ch == 0) dA ^= low;
+                        else if (ch == 1) dF ^= low;
+                        else dFree ^= low;
+                        const int slot = total + __popc(pend & ((1u << lane) - 1u));
+                        const uint32_t elem = (uint32_t)(sub * (W * H * 3) + (x * H + y) * 3 + ch);
+                        if (slot < kDeltaEntries)
+                            reinterpret_cast<uint16_t*>(cw)[2 + slot] = (uint16_t)((elem << 1) | ((now & low) ? 1u : 0u));
+                    }
+                    total += __popc(pend);
+                }
+                const bool full = total > kDeltaEntries;  // warp-uniform
+                {
+                    const uint32_t status16 = rkind | (done ? 8u : 0u) | (rcnt << 4);
+                    uint32_t st = __shfl_sync(FULL, status16, 0);
+                    if (EPW == 2) st |= __shfl_sync(FULL, status16, L & 31) << 16;
+                    __syncwarp();
+                    if (lane == 0) cw[0] = st | (full ? kDeltaFullBit : 0u);
+                }
+                if (full && n_valid > 0) {  // the whole stream, as aligned 16-byte stores straight into the host's full area
+                    // (emit_obs leaves the stream in stream_warp; the copy it makes into the warp's slot of the CTA's block
+                    //  -- behind the change-list records -- is not used)
+                    emit_obs<L, true>(srv_block + kWarpsPerBlock * kDeltaWords + warp * (((EPW * W * H * 3 + 31) >> 5) + 1), kObsPackedStatus,
+                                      cA, cF, cFree, stream_warp, spread3, tab8, lane, sub, x, W, H, env0, n_valid, 0u);
+                    __syncwarp();
+                    const int n4 = (((EPW * W * H * 3 + 31) >> 5) + 3) >> 2;
+                    uint4* dst = reinterpret_cast<uint4*>(srv.full_area + (size_t)(env0 / EPW) * srv.full_stride);
+                    if (lane < n4) dst[lane] = reinterpret_cast<const uint4*>(stream_warp)[lane];
+                }
+            } else if (io.obs != nullptr) {
                 const size_t step_bytes =
                     io.obs_dtype == kObsPacked ? (size_t)((s.N + EPW - 1) / EPW) * ((EPW * W * H * 3 + 31) >> 5) * 4
                                                : (size_t)s.N * W * H * 3 * obs_elem_bytes(io.obs_dtype);
@@ -834,6 +890,9 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         for (int i = 0; i < kSectorPayload; ++i) w[i] = p0 + i < srv_stride ? rw[p0 + i] : 0u;
                         dst[j] = (j & 1) ? make_uint4(w[4], w[5], w[6], seq ^ sector_hash(w)) : make_uint4(w[0], w[1], w[2], w[3]);
                     }
+                } else if (srv.delta) {
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * (kWarpsPerBlock * kDeltaWords));
+                    if (threadIdx.x < kWarpsPerBlock * kDeltaWords / 4) dst[threadIdx.x] = reinterpret_cast<const uint4*>(srv_block)[threadIdx.x];
                 } else {
                     const int block_words = (kWarpsPerBlock * srv_stride + 31) & ~31;  // whole 128-byte lines
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * block_words);
