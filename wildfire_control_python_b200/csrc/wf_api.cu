@@ -9,6 +9,9 @@
 #include <new>
 #include <string>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <chrono>
 
 #include "wf_families.cuh"
@@ -807,7 +810,6 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
         }
     }
     volatile uint32_t* ctl = ss.ctl;
-    std::memcpy(ss.actions, actions_host, (size_t)s.N * sizeof(int32_t));
     uint64_t db_flags = 0;
     if (ss.persistent_obs) {  // another array than last step's (or none yet): ask for every record in full
         const bool want_full = ss.frame_ptr != obs_host;
@@ -816,8 +818,33 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
         ss.frame_ptr = nullptr;  // (until this step has been delivered)
     }
     ss.seq += 1u;
+    *reinterpret_cast<volatile uint64_t*>(ss.ctl) = (uint64_t)ss.seq | (db_flags << 32);  // (the doorbell word: 0xffffffff parks)
+    {
+        // The ring: every action tagged with the step's sequence number (wf_warp.cu: CTA 0 polls this buffer).
+        const uint32_t tag = ((ss.seq & kSrvTagMask) << 8) | (uint32_t)(db_flags << 30);
+        const int64_t npad = (int64_t)(s.N + 3) / 4 * 4;
+        // (the GPU validates every word's tag: it may read while this loop is writing.  It reads these lines all the time,
+        //  so ordinary stores would have to win each line back from the I/O agent first -- 4 us per step; streaming stores
+        //  go past the caches)
+        int32_t* dst = ss.actions;
+        int64_t i = 0;
+#if defined(__x86_64__)
+        for (; i + 4 <= s.N; i += 4) {
+            __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(actions_host + i));
+            const __m128i big = _mm_or_si128(_mm_cmpgt_epi32(a, _mm_set1_epi32(254)), _mm_cmplt_epi32(a, _mm_setzero_si128()));
+            a = _mm_or_si128(_mm_andnot_si128(big, a), _mm_and_si128(big, _mm_set1_epi32(255)));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_or_si128(a, _mm_set1_epi32((int)tag)));
+        }
+#endif
+        for (; i < npad; ++i) {
+            const uint32_t a = i < s.N ? (uint32_t)actions_host[i] : 255u;
+            dst[i] = (int32_t)((a < 255u ? a : 255u) | tag);
+        }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
+    }
     std::atomic_thread_fence(std::memory_order_release);
-    *reinterpret_cast<volatile uint64_t*>(ss.ctl) = (uint64_t)ss.seq | (db_flags << 32);  // ring (one store: number and flags)
     ss.steps += 1;
     const int64_t rps = (int64_t)ss.ctas_per_slice * 4;
     const auto t_start = std::chrono::steady_clock::now();

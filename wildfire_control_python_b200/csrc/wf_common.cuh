@@ -44,6 +44,9 @@ __host__ __device__ __forceinline__ uint32_t sector_hash(const uint32_t* w) {
     return h ^ (h >> 15);
 }
 
+// Step-server session: the actions in the mapped host buffer are tagged with their step's sequence number (bits 8-29).
+constexpr uint32_t kSrvTagMask = 0x3fffffu;
+
 // Change-list records of a step-server session with a persistent observation array (wf_host_session mode 2): per warp
 // kDeltaWords words = the status word + kDeltaEntries 16-bit entries (element index within the warp's envs << 1 | new value;
 // 0xffff: unused).  kDeltaFullBit of the status word: the warp's complete bit stream is in SrvCtl::full_area instead.

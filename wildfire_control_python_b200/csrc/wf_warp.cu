@@ -374,51 +374,67 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             const int k = SRV ? 0 : kk;  // row of the output arrays
             if (SRV) {
                 if (blockIdx.x == 0) {
-                    // CTA 0: thread 0 waits for the doorbell, then the whole CTA brings the step's actions from the mapped
-                    // host buffer into HBM with coalesced 16-byte loads (one read over PCIe per 512 bytes; every warp
-                    // fetching its own action from host memory was 2048 small PCIe reads, ~80 us per step), and only
-                    // then are the other CTAs released.
+                    // CTA 0 waits for the step's actions and brings them into HBM; only then are the other CTAs released.
+                    // The mapped host buffer holds TAGGED actions: bits 0-7 the action (255: none), bits 8-29 the step's
+                    // sequence number, bit 30 "every record in full".  The whole CTA polls the buffer itself with batched
+                    // 16-byte loads until every word carries this step's tag, so the actions arrive with the poll that
+                    // notices them: one PCIe round trip instead of one for a doorbell plus one for the actions (and 2048
+                    // warps each fetching its own action from host memory was ~80 us per step).  Thread 0 also reads the
+                    // doorbell word -- the host writes 0xffffffff there to park the kernel -- and keeps the idle clock.
+                    const uint32_t want_tag = (srv.seq0 + srv_step + 1u) & kSrvTagMask;
+                    const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
+                    const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
+                    int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
+                    unsigned long long t0 = 0ull;
                     if (threadIdx.x == 0) {
-                        const uint32_t last = srv.seq0 + srv_step;
-                        const unsigned long long t0 = global_timer_ns();
+                        t0 = global_timer_ns();
                         srv_t0 = t0;
-                        uint32_t cmd, flags;
-                        for (;;) {  // the doorbell is one 64-bit word: sequence number | flags << 32 (bit 0: every record in full)
-                            const unsigned long long db = *reinterpret_cast<const volatile unsigned long long*>(srv.doorbell);
-                            cmd = (uint32_t)db;
-                            flags = (uint32_t)(db >> 32);
-                            if (cmd != last || global_timer_ns() - t0 > srv.idle_ns) break;
-                        }
-                        srv_flags = flags;
-                        if (cmd == last || cmd == 0xffffffffu) {  // nobody rang, or the host asks the kernel to park
-                            *srv.parked = srv.generation;
-                            srv_cmd = 0xffffffffu;
-                        } else {
-                            srv_cmd = srv_step + 1u;
-                        }
-                        srv_t0b = global_timer_ns();
+                        srv_cmd = srv_step + 1u;
                     }
-                    __syncthreads();
-                    if (srv_cmd != 0xffffffffu) {
-                        const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
-                        const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
-                        int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
-                        // all of a thread's loads are issued before its first store: one PCIe round trip, not one per chunk
-                        for (int j0 = threadIdx.x; j0 < n16; j0 += 8 * blockDim.x) {
+                    auto tag_ok = [&](int w) { return (((uint32_t)w >> 8) & kSrvTagMask) == want_tag; };
+                    auto strip = [](int w) { return (w & 255) == 255 ? -1 : (w & 255); };
+                    bool parked = false;
+                    for (int base = 0; base < n16 && !parked; base += 8 * (int)blockDim.x) {
+                        for (;;) {
                             int4 v[8];
+                            bool ok = true;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (j0 + u * (int)blockDim.x < n16) v[u] = __ldcv(src + j0 + u * blockDim.x);
+                            for (int u = 0; u < 8; ++u) {
+                                const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
+                                if (j < n16) v[u] = __ldcv(src + j);
+                            }
+                            uint32_t cmd = 0u;
+                            if (base == 0 && threadIdx.x == 0) cmd = *srv.doorbell;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (j0 + u * (int)blockDim.x < n16) dst[j0 + u * blockDim.x] = v[u];
+                            for (int u = 0; u < 8; ++u) {
+                                const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
+                                if (j < n16) ok = ok && tag_ok(v[u].x) && tag_ok(v[u].y) && tag_ok(v[u].z) && tag_ok(v[u].w);
+                            }
+                            if (__syncthreads_and(ok)) {
+                                if (base == 0 && threadIdx.x == 0) srv_flags = ((uint32_t)v[0].x >> 30) & 1u;
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
+                                    if (j < n16) dst[j] = make_int4(strip(v[u].x), strip(v[u].y), strip(v[u].z), strip(v[u].w));
+                                }
+                                break;
+                            }
+                            if (base == 0) {  // not (all) there yet: asked to park, or idle for too long?
+                                if (threadIdx.x == 0 && (cmd == 0xffffffffu || global_timer_ns() - t0 > srv.idle_ns)) {
+                                    *srv.parked = srv.generation;
+                                    srv_cmd = 0xffffffffu;
+                                }
+                                __syncthreads();
+                                if (srv_cmd == 0xffffffffu) { parked = true; break; }
+                            }
                         }
-                        __threadfence();
                     }
+                    if (threadIdx.x == 0) srv_t0b = global_timer_ns();
+                    if (!parked) __threadfence();
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         srv_t1 = global_timer_ns();
-                        if (srv.delta) srv.actions_dev[((s.N + 3) >> 2) << 2] = (int32_t)(srv_flags & 1u);  // the host's full-frame request
+                        if (srv.delta && !parked) srv.actions_dev[((s.N + 3) >> 2) << 2] = (int32_t)(srv_flags & 1u);  // the host's full-frame request
                         st_release_gpu(srv.go, srv_cmd);
                     }
                 } else {
