@@ -113,8 +113,10 @@ def api_round(rng):
     # transport and a short idle limit, so that it parks itself / is parked by the device-side calls mixed in below
     os.environ["WF_SESSION_SECTORS"] = str(int(rng.integers(0, 2)))
     os.environ["WF_SESSION_IDLE_US"] = str(int(rng.choice([50, 300, 2000])))
-    session = bool(rng.random() < 0.6) and gpu.host_session(True)
-    print(f"            session={session} sectors={os.environ['WF_SESSION_SECTORS']} idle_us={os.environ['WF_SESSION_IDLE_US']}", flush=True)
+    persistent = bool(rng.random() < 0.5)  # wf_host_session mode 2: change-list records, the array is patched in place
+    session = bool(rng.random() < 0.7) and gpu.host_session(True, persistent_obs=persistent)
+    print(f"            session={session} persistent_obs={persistent} sectors={os.environ['WF_SESSION_SECTORS']} "
+          f"idle_us={os.environ['WF_SESSION_IDLE_US']}", flush=True)
     obs = to_np(gpu.reset())
     for i, e in enumerate(orc):
         assert np.array_equal(obs[i], e.reset()), "reset obs"
