@@ -157,7 +157,7 @@ int wf_set_policy_mlp(wf_env* env, const float* kernel1_host, const float* bias1
  * WF_HOST_PACKED=direct stores the bit stream straight into mapped host memory instead of one DMA copy;
  * WF_HOST_TIMING=1 prints the launch / sync / expand split when the handle is destroyed; WF_HOST_GRAPH=1
  * (a_speed == 1 only) issues kernel + copy as one CUDA graph: 40.0-40.6 against 42.1 us per C2 step, tools/e2e_ab.py).
- * Fastest: wf_host_session below (24.5 us), which also lifts the page-locked requirement.
+ * Fastest: wf_host_session below (23 us; 19 us with a persistent observation array), which also lifts the page-locked requirement.
  * The device alias of each page-locked buffer is looked up once and re-validated every 1024 calls: a caller that
  * unpins or frees a buffer must not hand the same ADDRESS back as a different kind of memory within that window
  * (pass a new address, or destroy the handle). */
@@ -165,12 +165,12 @@ int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32
                  double* reward_host, uint8_t* done_host);
 /* Step-server session for wf_step_host (grids up to 32x32, uint8 observations).  While a session is on, the step kernel
  * stays RESIDENT on the GPU (a cooperative launch) with every env in registers and is driven through mapped page-locked
- * memory: wf_step_host copies the actions into a mapped buffer and rings a doorbell that CTA 0 polls; CTA 0 copies the
- * actions into HBM and releases the other CTAs; every CTA steps its envs and stores its records -- the observation bit
+ * memory: wf_step_host writes the actions, tagged with the step's sequence number, into a mapped buffer that CTA 0 polls;
+ * CTA 0 copies them into HBM and releases the other CTAs; every CTA steps its envs and stores its records -- the observation bit
  * stream plus one status word per record (reward kind, done, burn-out count) -- straight into mapped host memory; the
  * last CTA to finish issues a system-scope fence and raises the completion flag; the library's host threads then expand
  * the records into obs_host and decode reward / done (any host memory: the caller's buffers may be pageable).  No kernel
- * launch, no copy call and no stream synchronise per step: 24.5 instead of 42 us per 4096-env 14x14 step.
+ * launch, no copy call and no stream synchronise per step: 23 instead of 42 us per 4096-env 14x14 step.
  *   wf_host_session(env, 1)  turn it on (the kernel is started by the next wf_step_host);  (env, 0) park it.
  * Any other entry point on the handle (wf_reset, wf_step, wf_get_state, ...) parks the kernel first -- it stores the
  * envs back to HBM and exits -- and the next wf_step_host starts it again, so results never depend on the session.
