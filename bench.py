@@ -379,8 +379,8 @@ def measure(D: Dist, name: str, K: int, Wm: int, chunk_arg: int, with_e2e: bool,
             res["e2e"]["persistent_obs"] = {
                 "value": world * N * Kp / tp, "unit": "env-steps/s", "us_per_step": tp * 1e6 / Kp, "repeats": Rp,
                 "d2h_bytes_per_step": ctas * 128,
-                "note": "wf_host_session(env, 2): change-list records (32 B per two envs) + the full record (160 B) of every "
-                        "pair of envs with more than 14 changed elements (about 4 % of them per step: resets, large fire ticks); "
+                "note": "wf_host_session(env, 2): one 128-byte change-list block per 8 envs + the full record (160 B) of every "
+                        "pair of envs with more than 13 changed elements (about 4 % of them per step: resets, large fire ticks); "
                         "the array is complete and equal to the headline's after every call (tests/test_host_api_gpu.py)"}
     res["stats"] = env.stats()
     env.close()

@@ -47,10 +47,12 @@ __host__ __device__ __forceinline__ uint32_t sector_hash(const uint32_t* w) {
 // Step-server session: the actions in the mapped host buffer are tagged with their step's sequence number (bits 8-29).
 constexpr uint32_t kSrvTagMask = 0x3fffffu;
 
-// Change-list records of a step-server session with a persistent observation array (wf_host_session mode 2): per warp
-// kDeltaWords words = the status word + kDeltaEntries 16-bit entries (element index within the warp's envs << 1 | new value;
-// 0xffff: unused).  kDeltaFullBit of the status word: the warp's complete bit stream is in SrvCtl::full_area instead.
-constexpr int kDeltaWords = 8, kDeltaEntries = 14;
+// Change-list blocks of a step-server session with a persistent observation array (wf_host_session mode 2): one block of
+// kDeltaBlockWords words per CTA (= 4 records): word 0 = number of entries | mask of the records sent in full << 8, words
+// 1-4 = the records' status words, then up to 4 * kDeltaEntries 16-bit entries (element index within the CTA's envs << 1 |
+// new value).  A record (warp) with more than kDeltaEntries changed elements has its complete bit stream in
+// SrvCtl::full_area instead (its bit of the mask; also kDeltaFullBit of its status word).
+constexpr int kDeltaBlockWords = 32, kDeltaEntries = 13, kDeltaFirstEntry = 10 /* 16-bit units */;
 constexpr uint32_t kDeltaFullBit = 0x8000u;
 
 // Bytes per observation element of a public obs_dtype (WF_OBS_U8 / WF_OBS_F32 / WF_OBS_BF16).

@@ -29,10 +29,9 @@ struct SrvCtl {
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
     int32_t sectors;              // != 0: records travel as self-validating 32-byte sectors (wf_common.cuh), no flags / fences
-    int32_t delta;                // != 0: change-list records (kDeltaWords words per warp, WarpIO::obs = [CTAs][4][kDeltaWords]);
-                                  // a warp whose envs changed in more than kDeltaEntries elements -- or when the host asks for
-                                  // it (actions_host[N padded to 4] != 0), or on the launch's first step -- sends its whole bit
-                                  // stream to full_area instead and sets kDeltaFullBit in the status word
+    int32_t delta;                // != 0: change-list blocks (wf_common.cuh; WarpIO::obs = [CTAs][kDeltaBlockWords]); a warp whose
+                                  // envs changed in more than kDeltaEntries elements -- or when the host asks for it (bit 30 of
+                                  // the action tags), or on the launch's first step -- sends its whole bit stream to full_area
     uint32_t* full_area;          // mapped host [records][full_stride] words
     int32_t full_stride;          // words between two records of full_area (a multiple of 4)
     unsigned long long idle_ns;   // no doorbell for this long: the kernel parks itself (the GPU is not held hostage)

@@ -38,8 +38,8 @@ struct ExpandJob {
     double default_reward, death_penalty, contained_bonus, cells;
     int64_t timeout_ns;         // session: give up waiting for a flag after this long (the caller then checks the kernel)
     const uint32_t* full_area;  // session with a persistent observation array (wf_host_session mode 2), != nullptr: `packed` holds
-    int64_t full_stride;        // change-list records (8 words per record, blocks of 4); a record whose status word has bit 15
-                                // set is complete in full_area[record * full_stride] instead
+    int64_t full_stride;        // change-list blocks (32 words per 4 records, wf_common.cuh); a record flagged in its block's header
+                                // is complete in full_area[record * full_stride] instead
     int64_t sectors;            // session, != 0: each record is `sectors` self-validating 32-byte sectors (7 payload words + tag =
                                 // seq ^ hash), no flags: a record is taken as soon as all its sectors validate
 };
@@ -164,44 +164,46 @@ static bool fetch_record(const ExpandJob& j, int64_t r, uint32_t* tmp, const std
     return true;
 }
 
-// Change-list records: patch the elements that changed; records flagged "full" are expanded from the full area.
+// Change-list blocks (wf_common.cuh): per CTA block the status words of its 4 records, the records sent in full (expanded
+// from the full area) and ONE list of the elements that changed in the others.
 static void expand_one(const ExpandJob& j, const uint32_t* rec, int64_t env0, int64_t nenv);
 static void apply_delta_records(const ExpandJob& j, int64_t r0, int64_t r1) {
-    constexpr int kWords = 8, kEntries = 14;
+    constexpr int kBlockWords = 32, kFirstEntry = 10;
+    const int64_t b0 = (r0 + 3) >> 2, b1 = (r1 + 3) >> 2;  // whole blocks; consecutive record ranges give consecutive block ranges
 #if defined(__x86_64__)
     // The GPU has just written these lines: none is in a cache of this core, and a range of a few KB is over before the
-    // hardware prefetcher has caught on.  Ask for all of them at once.
-    {
-        const char* p0 = reinterpret_cast<const char*>(j.packed + (r0 >> 2) * (4 * kWords));
-        const char* p1 = reinterpret_cast<const char*>(j.packed + ((r1 + 3) >> 2) * (4 * kWords));
-        for (const char* p = p0; p < p1; p += 64) _mm_prefetch(p, _MM_HINT_T0);
+    // hardware prefetcher has caught on.  Ask for the first ones at once, the rest a little ahead.
+    for (int64_t b = b0; b < b1 && b < b0 + 16; ++b) {
+        _mm_prefetch(reinterpret_cast<const char*>(j.packed + b * kBlockWords), _MM_HINT_T0);
+        _mm_prefetch(reinterpret_cast<const char*>(j.packed + b * kBlockWords) + 64, _MM_HINT_T0);
     }
 #endif
-    for (int64_t r = r0; r < r1; ++r) {
-        const uint32_t* rec = j.packed + (r >> 2) * (4 * kWords) + (r & 3) * kWords;
-        const int64_t env0 = r * j.envs_per_record;
-        const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
-        const uint32_t st = rec[0];
-        if (st & 0x8000u) {
-            expand_one(j, j.full_area + r * j.full_stride, env0, nenv);
-        } else {
-            // all 14 entries, unused ones (0xffff) into a dummy byte: a loop that stops at the first unused entry
-            // mispredicts its exit once per record (55 instead of ~20 cycles per record)
-            uint8_t* out = j.out + env0 * j.env_bits;
-            const uint16_t* e = reinterpret_cast<const uint16_t*>(rec) + 2;
-            uint8_t dummy;
-#pragma GCC unroll 14
-            for (int k = 0; k < kEntries; ++k) {
-                const uint32_t v = e[k];
-                uint8_t* dst = v == 0xffffu ? &dummy : out + (v >> 1);
-                *dst = (uint8_t)(v & 1u);
-            }
-            (void)dummy;
+    const int64_t rec_elems = j.envs_per_record * j.env_bits;
+    for (int64_t b = b0; b < b1; ++b) {
+        const uint32_t* blk = j.packed + b * kBlockWords;
+#if defined(__x86_64__)
+        if (b + 16 < b1) {
+            _mm_prefetch(reinterpret_cast<const char*>(blk + 16 * kBlockWords), _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char*>(blk + 16 * kBlockWords) + 64, _MM_HINT_T0);
         }
-        for (int64_t k = 0; k < nenv; ++k) {
-            const uint32_t sk = (st >> (16 * k)) & 0x7fffu;
-            if (j.reward) j.reward[env0 + k] = decode_reward(j, sk);
-            if (j.done) j.done[env0 + k] = (uint8_t)((sk >> 3) & 1u);
+#endif
+        const uint32_t hdr = blk[0];
+        const int count = (int)(hdr & 0xffu);
+        uint8_t* out = j.out + 4 * b * rec_elems;
+        const uint16_t* e = reinterpret_cast<const uint16_t*>(blk) + kFirstEntry;
+        for (int k = 0; k < count; ++k) out[e[k] >> 1] = (uint8_t)(e[k] & 1u);
+        for (int w = 0; w < 4; ++w) {
+            const int64_t r = 4 * b + w;
+            if (r >= j.records) break;
+            const int64_t env0 = r * j.envs_per_record;
+            const int64_t nenv = (j.n_envs - env0 < j.envs_per_record) ? (j.n_envs - env0) : j.envs_per_record;
+            const uint32_t st = blk[1 + w];
+            if ((hdr >> (8 + w)) & 1u) expand_one(j, j.full_area + r * j.full_stride, env0, nenv);
+            for (int64_t k = 0; k < nenv; ++k) {
+                const uint32_t sk = (st >> (16 * k)) & 0x7fffu;
+                if (j.reward) j.reward[env0 + k] = decode_reward(j, sk);
+                if (j.done) j.done[env0 + k] = (uint8_t)((sk >> 3) & 1u);
+            }
         }
     }
 }

@@ -288,7 +288,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
     // SRV: the CTA's records (one per warp: up to 96 words of observation bits + the status word) are collected here and
     // leave for host memory as ONE 128-byte-aligned block of 16-byte stores -- whole PCIe write transactions instead of
     // the 4-byte-per-lane stores of unaligned 152-byte records (which cost ~25 us per step on the link)
-    __shared__ __align__(16) uint32_t srv_block[SRV ? kWarpsPerBlock * 97 + 31 : 1];  // (+ slack: the sector copy reads 7-word groups)
+    __shared__ __align__(16) uint32_t srv_block[SRV ? kWarpsPerBlock * 97 + 31 + 96 : 1];  // (+ slack: the sector copy reads 7-word groups)
     __shared__ float4 mlp_w2[MLP ? 2 * kHidMax : 1];  // second layer (MlpPolicy::w2), read every step
     __shared__ float mlp_b2[kActMax];
     for (int v = threadIdx.x; v < 256; v += blockDim.x) {
@@ -836,9 +836,8 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                 uint32_t dA = cA ^ pA, dF = cF ^ pF, dFree = cFree ^ pFree;
                 pA = cA; pF = cF; pFree = cFree;
                 const bool want_full = srv_step == 0u || srv_want_full != 0;
-                uint32_t* const cw = srv_block + warp * kDeltaWords;
-                if (lane < kDeltaWords) cw[lane] = 0xffffffffu;
-                __syncwarp();
+                // this warp's list: status word, count, then its entries (16-bit units from index 4); the CTA merges the four
+                uint32_t* const cw = srv_block + kDeltaBlockWords + warp * 12;
                 int total = want_full ? kDeltaEntries + 1 : 0;
                 while (total <= kDeltaEntries) {
                     const bool has = (dA | dF | dFree) != 0u;
@@ -856,7 +855,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         const int slot = total + __popc(pend & ((1u << lane) - 1u));
                         const uint32_t elem = (uint32_t)(sub * (W * H * 3) + (x * H + y) * 3 + ch);
                         if (slot < kDeltaEntries)
-                            reinterpret_cast<uint16_t*>(cw)[2 + slot] = (uint16_t)((elem << 1) | ((now & low) ? 1u : 0u));
+                            reinterpret_cast<uint16_t*>(cw)[4 + slot] = (uint16_t)((elem << 1) | ((now & low) ? 1u : 0u));
                     }
                     total += __popc(pend);
                 }
@@ -865,13 +864,15 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                     const uint32_t status16 = rkind | (done ? 8u : 0u) | (rcnt << 4);
                     uint32_t st = __shfl_sync(FULL, status16, 0);
                     if (EPW == 2) st |= __shfl_sync(FULL, status16, L & 31) << 16;
-                    __syncwarp();
-                    if (lane == 0) cw[0] = st | (full ? kDeltaFullBit : 0u);
+                    if (lane == 0) {
+                        cw[0] = st | (full ? kDeltaFullBit : 0u);
+                        cw[1] = (full || n_valid <= 0) ? 0u : (uint32_t)total;
+                    }
                 }
                 if (full && n_valid > 0) {  // the whole stream, as aligned 16-byte stores straight into the host's full area
                     // (emit_obs leaves the stream in stream_warp; the copy it makes into the warp's slot of the CTA's block
                     //  -- behind the change-list records -- is not used)
-                    emit_obs<L, true>(srv_block + kWarpsPerBlock * kDeltaWords + warp * (((EPW * W * H * 3 + 31) >> 5) + 1), kObsPackedStatus,
+                    emit_obs<L, true>(srv_block + kDeltaBlockWords + 48 + warp * (((EPW * W * H * 3 + 31) >> 5) + 1), kObsPackedStatus,
                                       cA, cF, cFree, stream_warp, spread3, tab8, lane, sub, x, W, H, env0, n_valid, 0u);
                     __syncwarp();
                     const int n4 = (((EPW * W * H * 3 + 31) >> 5) + 3) >> 2;
@@ -907,8 +908,27 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                         dst[j] = (j & 1) ? make_uint4(w[4], w[5], w[6], seq ^ sector_hash(w)) : make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 } else if (srv.delta) {
-                    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * (kWarpsPerBlock * kDeltaWords));
-                    if (threadIdx.x < kWarpsPerBlock * kDeltaWords / 4) dst[threadIdx.x] = reinterpret_cast<const uint4*>(srv_block)[threadIdx.x];
+                    // merge the four warps' lists into the CTA's block: header, status words, entries back to back
+                    const uint32_t* pw = srv_block + kDeltaBlockWords;
+                    const int t = threadIdx.x;
+                    const int c0 = (int)pw[1], c1 = c0 + (int)pw[13], c2 = c1 + (int)pw[25], c3 = c2 + (int)pw[37];
+                    if (t == 0) {
+                        const uint32_t fullmask = ((pw[0] >> 15) & 1u) | (((pw[12] >> 15) & 1u) << 1) | (((pw[24] >> 15) & 1u) << 2) |
+                                                  (((pw[36] >> 15) & 1u) << 3);
+                        srv_block[0] = (uint32_t)c3 | (fullmask << 8);
+                    } else if (t < 5) {
+                        srv_block[t] = pw[(t - 1) * 12];
+                    }
+                    if (t < kWarpsPerBlock * kDeltaEntries) {
+                        const int w = (t >= c0) + (t >= c1) + (t >= c2);
+                        const int first = w == 0 ? 0 : w == 1 ? c0 : w == 2 ? c1 : c2;
+                        uint32_t e = 0xffffu;
+                        if (t < c3) e = (uint32_t)reinterpret_cast<const uint16_t*>(pw + w * 12)[4 + t - first] + (uint32_t)(w * EPW * W * H * 3) * 2u;
+                        reinterpret_cast<uint16_t*>(srv_block)[kDeltaFirstEntry + t] = (uint16_t)e;
+                    }
+                    __syncthreads();
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * kDeltaBlockWords);
+                    if (t < kDeltaBlockWords / 4) dst[t] = reinterpret_cast<const uint4*>(srv_block)[t];
                 } else {
                     const int block_words = (kWarpsPerBlock * srv_stride + 31) & ~31;  // whole 128-byte lines
                     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint32_t*>(io.obs) + (size_t)blockIdx.x * block_words);
