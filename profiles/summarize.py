@@ -6,6 +6,7 @@ Reads (whatever exists):
   gpurun_out/launches_bench.csv (and launches_c2/c4/c5.csv)   `ncu --metrics gpu__time_duration.sum ...` launch lists
   gpurun_out/prof_c2.ncu-rep                      `ncu --set full` capture of wf::warp_kernel (c2, 256 steps per launch)
   gpurun_out/prof_c4.ncu-rep, prof_c5.ncu-rep     captures of wf::tile_rollout_kernel (c4 / c5, 16 steps per launch)
+  gpurun_out/prof_c3.ncu-rep                      capture of wf::warp_kernel<..., MLP> (c3, 64 steps per launch; tools/profile_c3.sh)
 Writes profiles/<round>_*.{csv,txt,json} and profiles/ncu_traffic.json (DRAM bytes per STEP, read by bench.py).
 """
 import collections
@@ -86,7 +87,8 @@ def main(rnd):
         if ls:
             summary[f"{name}_launch_list"] = ls
     for rep, tag, key, steps in (("prof_c2.ncu-rep", "c2_warp_kernel", "c2", 256), ("prof_c4.ncu-rep", "c4_tile_rollout", "c4", 16),
-                                 ("prof_c5.ncu-rep", "c5_tile_rollout", "c5", 16)):
+                                 ("prof_c5.ncu-rep", "c5_tile_rollout", "c5", 16),
+                                 ("prof_c3.ncu-rep", "c3_warp_kernel_mlp", "c3", 64)):  # in-kernel Q-network (tools/profile_c3.sh)
         ks = rep_summary(rep, rnd, tag)
         if ks:
             summary[tag] = ks

@@ -11,7 +11,7 @@ from wildfire_control_python_b200 import BatchedForestFire  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 wl = WORKLOADS[name]
-N, K = wl["n_envs"], (int(sys.argv[2]) if len(sys.argv) > 2 else wl["chunk"])
+N, K = int(os.environ.get("AB_N", wl["n_envs"])), (int(sys.argv[2]) if len(sys.argv) > 2 else wl["chunk"])
 W, H = wl["meta"]["width"], wl["meta"]["height"]
 env = BatchedForestFire(N, auto_reset=True, seed=0, **wl["meta"])
 env.reset()

@@ -14,3 +14,4 @@ for wl in c4 c5; do
   ncu --set full --clock-control none --import-source on -k regex:tile_rollout -s 3 -c 1 -f -o gpurun_out/prof_$wl \
       python bench.py --workload $wl --chunk 16 --only-value --steps 16 --warmup 16 --min-region-s 0 > gpurun_out/ncu_$wl.log 2>&1; echo "$wl rc=$?"
 done
+tools/profile_c3.sh

@@ -25,6 +25,7 @@
 // The A* containment search (pyastar/astar.cpp) is the persistent reach plane R (cells with a finite
 // 4-connected path to a finite border point), re-flooded by the cluster only when a dig may disconnect
 // it; burning cells that are border points themselves (W > H maps) get a scratch flood (seed_cells_touch).
+#include <cstdio>
 #include <cstdlib>
 
 #include "wf_families.cuh"
@@ -1655,7 +1656,10 @@ static void choose_geometry(const DevState& s, int& T, int& CS) {
     while (p > 128 && p > nunits) p /= 2;
     T = (int)(p < 512 ? p : 512);
     CS = (int)(p / T);
-    if (p == 2048) { T = 256; CS = 8; }
+    // Few large envs (C5: 64 of 1024x1024): 16 CTAs of 128 threads per env rather than 8 of 256 -- 84.2-84.7 against 88.1-91.1 us
+    // per C5 step in three alternating runs on one box (r02).  16 is a non-portable cluster size: tile_create falls back to
+    // 256 x 8 if the device cannot hold such a cluster.
+    if (p == 2048) { T = 128; CS = 16; }
     const int t_env = env_int("WF_TILE_T", 0), cs_env = env_int("WF_TILE_CS", 0);
     if (t_env == 128 || t_env == 256 || t_env == 512) T = t_env;
     if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8 || cs_env == 16) CS = cs_env;
@@ -1695,6 +1699,25 @@ cudaError_t tile_create(TileState** out, const DevState& s, const StepCfg&) {
     if (e != cudaSuccess) {
         delete t;
         return e;
+    }
+    if (t->CS == 16 && env_int("WF_TILE_CS", 0) != 16) {  // chosen, not forced: only if such clusters can be resident
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16);
+        cfg.blockDim = dim3(t->T);
+        cfg.dynamicSmemBytes = (size_t)t->T * 4 * 28;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, tile_rollout_kernel<5, 4, true, false>, &cfg) != cudaSuccess || nc < 1) {
+            cudaGetLastError();
+            t->T = 256;
+            t->CS = 8;
+        }
     }
     *out = t;
     return cudaSuccess;
@@ -1747,6 +1770,13 @@ static cudaError_t launch(const TileState* t, const DevState& s, const StepCfg& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (env_int("WF_TILE_DEBUG", 0)) {  // how many clusters of this shape the GPU holds at once (waves = grid / that)
+        static bool said = false;
+        int nc = 0;
+        if (!said && cudaOccupancyMaxActiveClusters(&nc, tile_rollout_kernel<FB, VW, true, FU>, &cfg) == cudaSuccess)
+            fprintf(stderr, "wf_tile: %d clusters of %d x %d threads in the grid, %d resident at once\n", s.N, t->CS, t->T, nc);
+        said = true;
+    }
     return cudaLaunchKernelEx(&cfg, tile_rollout_kernel<FB, VW, true, FU>, s, c, p, io);
 }
 
