@@ -781,10 +781,11 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.ctl), (32 + 16 * kSessMaxSlices) * sizeof(uint32_t), cudaHostAllocMapped));
             std::memset(ss.ctl, 0, (32 + 16 * kSessMaxSlices) * sizeof(uint32_t));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.ctl_dev), ss.ctl, 0));
-            const size_t act_bytes = (size_t)((s.N + 3) / 4 + 1) * 4 * sizeof(int32_t);  // (+ one chunk: the full-frame request)
+            const size_t act_bytes = (size_t)srv_action_chunks(s.N) * 16;  // packed and tagged (wf_common.cuh)
             WF_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ss.actions), act_bytes, cudaHostAllocMapped));
             std::memset(ss.actions, 0, act_bytes);
-            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), act_bytes));
+            // the kernel's unpacked copy: 24 actions per chunk (+ one word: the full-frame request)
+            WF_CUDA(cudaMalloc(reinterpret_cast<void**>(&ss.actions_hbm), ((size_t)srv_action_chunks(s.N) * 24 + 4) * sizeof(int32_t)));
             WF_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ss.actions_dev), ss.actions, 0));
             // WF_SESSION_SECTORS=1: self-validating sectors (wf_common.cuh) instead of the completion flag + system fence.
             // Measured, not faster (C2: 27.4 against 26.4 us per step with 12 host threads, 54.7 against 42.3 with 3: the
@@ -820,25 +821,34 @@ static int session_step(wf_env* e, const int32_t* actions_host, void* obs_host, 
     ss.seq += 1u;
     *reinterpret_cast<volatile uint64_t*>(ss.ctl) = (uint64_t)ss.seq | (db_flags << 32);  // (the doorbell word: 0xffffffff parks)
     {
-        // The ring: every action tagged with the step's sequence number (wf_warp.cu: CTA 0 polls this buffer).
-        const uint32_t tag = ((ss.seq & kSrvTagMask) << 8) | (uint32_t)(db_flags << 30);
-        const int64_t npad = (int64_t)(s.N + 3) / 4 * 4;
-        // (the GPU validates every word's tag: it may read while this loop is writing.  It reads these lines all the time,
-        //  so ordinary stores would have to win each line back from the I/O agent first -- 4 us per step; streaming stores
-        //  go past the caches)
+        // The ring: the actions, six per word, every word tagged with the step's sequence number (wf_common.cuh; CTA 0 of the
+        // kernel polls this buffer and validates every word, so it may read while this loop is writing).  The GPU reads these
+        // lines all the time: ordinary stores would have to win each line back from the I/O agent first (4 us per step when
+        // the buffer was 16 KB); streaming stores go past the caches.
+        const uint32_t tag = ((ss.seq & kSrvTagMask) << 24) | (uint32_t)(db_flags << 31);
+        const int64_t n_words = (int64_t)srv_action_chunks(s.N) * 4;
         int32_t* dst = ss.actions;
         int64_t i = 0;
+        auto nib = [](int32_t a) -> uint32_t { return (uint32_t)a < 15u ? (uint32_t)a : 15u; };
+        for (int64_t w = 0; w < n_words; w += 4) {
+            uint32_t word[4];
+            if (i + 24 <= s.N) {  // a whole chunk: no bounds tests
+                const int32_t* a = actions_host + i;
+                for (int q = 0; q < 4; ++q, a += 6)
+                    word[q] = tag | nib(a[0]) | (nib(a[1]) << 4) | (nib(a[2]) << 8) | (nib(a[3]) << 12) | (nib(a[4]) << 16) | (nib(a[5]) << 20);
+                i += 24;
+            } else {
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t v = tag;
+                    for (int k = 0; k < 6; ++k, ++i) v |= (i < s.N ? nib(actions_host[i]) : 15u) << (4 * k);
+                    word[q] = v;
+                }
+            }
 #if defined(__x86_64__)
-        for (; i + 4 <= s.N; i += 4) {
-            __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(actions_host + i));
-            const __m128i big = _mm_or_si128(_mm_cmpgt_epi32(a, _mm_set1_epi32(254)), _mm_cmplt_epi32(a, _mm_setzero_si128()));
-            a = _mm_or_si128(_mm_andnot_si128(big, a), _mm_and_si128(big, _mm_set1_epi32(255)));
-            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_or_si128(a, _mm_set1_epi32((int)tag)));
-        }
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + w), _mm_set_epi32((int)word[3], (int)word[2], (int)word[1], (int)word[0]));
+#else
+            for (int q = 0; q < 4; ++q) dst[w + q] = (int32_t)word[q];
 #endif
-        for (; i < npad; ++i) {
-            const uint32_t a = i < s.N ? (uint32_t)actions_host[i] : 255u;
-            dst[i] = (int32_t)((a < 255u ? a : 255u) | tag);
         }
 #if defined(__x86_64__)
         _mm_sfence();

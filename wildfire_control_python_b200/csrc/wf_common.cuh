@@ -44,8 +44,11 @@ __host__ __device__ __forceinline__ uint32_t sector_hash(const uint32_t* w) {
     return h ^ (h >> 15);
 }
 
-// Step-server session: the actions in the mapped host buffer are tagged with their step's sequence number (bits 8-29).
-constexpr uint32_t kSrvTagMask = 0x3fffffu;
+// Step-server session: the mapped host buffer holds the step's actions PACKED AND TAGGED, six per 32-bit word: bits 4k..4k+3
+// action k of the word (15: none), bits 24-30 the step's sequence number mod 128, bit 31 "every record in full".  CTA 0 polls
+// the buffer itself, so it is kept small: 2.7 KB per poll for 4096 envs.  srv_action_chunks: 16-byte chunks of the buffer.
+constexpr uint32_t kSrvTagMask = 0x7fu;
+__host__ __device__ __forceinline__ int srv_action_chunks(int n_envs) { return ((n_envs + 5) / 6 + 3) / 4; }
 
 // Change-list blocks of a step-server session with a persistent observation array (wf_host_session mode 2): one block of
 // kDeltaBlockWords words per CTA (= 4 records): word 0 = number of entries | mask of the records sent in full << 8, words

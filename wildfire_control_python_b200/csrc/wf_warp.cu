@@ -375,47 +375,57 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             if (SRV) {
                 if (blockIdx.x == 0) {
                     // CTA 0 waits for the step's actions and brings them into HBM; only then are the other CTAs released.
-                    // The mapped host buffer holds TAGGED actions: bits 0-7 the action (255: none), bits 8-29 the step's
-                    // sequence number, bit 30 "every record in full".  The whole CTA polls the buffer itself with batched
-                    // 16-byte loads until every word carries this step's tag, so the actions arrive with the poll that
-                    // notices them: one PCIe round trip instead of one for a doorbell plus one for the actions (and 2048
-                    // warps each fetching its own action from host memory was ~80 us per step).  Thread 0 also reads the
-                    // doorbell word -- the host writes 0xffffffff there to park the kernel -- and keeps the idle clock.
+                    // The mapped host buffer holds the actions packed and TAGGED (wf_common.cuh: six 4-bit actions + the
+                    // step's sequence number in every word).  The whole CTA polls the buffer itself with batched 16-byte
+                    // loads until every word carries this step's tag, so the actions arrive with the poll that notices
+                    // them: one PCIe round trip instead of one for a doorbell plus one for the actions (and 2048 warps each
+                    // fetching its own action from host memory was ~80 us per step).  Thread 0 also reads the doorbell
+                    // word -- the host writes 0xffffffff there to park the kernel -- and keeps the idle clock.
                     const uint32_t want_tag = (srv.seq0 + srv_step + 1u) & kSrvTagMask;
-                    const int n16 = (s.N + 3) >> 2;  // both buffers are padded to whole 16-byte chunks
+                    const int n16 = srv_action_chunks(s.N);
                     const int4* src = reinterpret_cast<const int4*>(srv.actions_host);
-                    int4* dst = reinterpret_cast<int4*>(srv.actions_dev);
+                    int4* dst = reinterpret_cast<int4*>(srv.actions_dev);  // [24 * n16] unpacked actions
                     unsigned long long t0 = 0ull;
                     if (threadIdx.x == 0) {
                         t0 = global_timer_ns();
                         srv_t0 = t0;
                         srv_cmd = srv_step + 1u;
                     }
-                    auto tag_ok = [&](int w) { return (((uint32_t)w >> 8) & kSrvTagMask) == want_tag; };
-                    auto strip = [](int w) { return (w & 255) == 255 ? -1 : (w & 255); };
+                    auto tag_ok = [&](int w) { return (((uint32_t)w >> 24) & kSrvTagMask) == want_tag; };
+                    auto unpack = [](int w, int k) { const int a = (w >> (4 * k)) & 15; return a == 15 ? -1 : a; };
+                    constexpr int kBatch = 4;  // chunks a thread polls at once (4 x 128 threads x 24 = 12 288 envs per pass)
                     bool parked = false;
-                    for (int base = 0; base < n16 && !parked; base += 8 * (int)blockDim.x) {
+                    for (int base = 0; base < n16 && !parked; base += kBatch * (int)blockDim.x) {
                         for (;;) {
-                            int4 v[8];
+                            int4 v[kBatch];
                             bool ok = true;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
+                            for (int u = 0; u < kBatch; ++u) {
                                 const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
                                 if (j < n16) v[u] = __ldcv(src + j);
                             }
                             uint32_t cmd = 0u;
                             if (base == 0 && threadIdx.x == 0) cmd = *srv.doorbell;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
+                            for (int u = 0; u < kBatch; ++u) {
                                 const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
                                 if (j < n16) ok = ok && tag_ok(v[u].x) && tag_ok(v[u].y) && tag_ok(v[u].z) && tag_ok(v[u].w);
                             }
                             if (__syncthreads_and(ok)) {
-                                if (base == 0 && threadIdx.x == 0) srv_flags = ((uint32_t)v[0].x >> 30) & 1u;
+                                if (base == 0 && threadIdx.x == 0) srv_flags = (uint32_t)v[0].x >> 31;
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
+                                for (int u = 0; u < kBatch; ++u) {
                                     const int j = base + (int)threadIdx.x + u * (int)blockDim.x;
-                                    if (j < n16) dst[j] = make_int4(strip(v[u].x), strip(v[u].y), strip(v[u].z), strip(v[u].w));
+                                    if (j < n16) {
+                                        const int w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                                        for (int q = 0; q < 6; ++q) {  // 24 actions = 6 stores of 16 bytes
+                                            int o[4];
+#pragma unroll
+                                            for (int i = 0; i < 4; ++i) o[i] = unpack(w[(4 * q + i) / 6], (4 * q + i) % 6);
+                                            dst[6 * j + q] = make_int4(o[0], o[1], o[2], o[3]);
+                                        }
+                                    }
                                 }
                                 break;
                             }
@@ -434,7 +444,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         srv_t1 = global_timer_ns();
-                        if (srv.delta && !parked) srv.actions_dev[((s.N + 3) >> 2) << 2] = (int32_t)(srv_flags & 1u);  // the host's full-frame request
+                        if (srv.delta && !parked) srv.actions_dev[24 * srv_action_chunks(s.N)] = (int32_t)(srv_flags & 1u);  // the host's full-frame request
                         st_release_gpu(srv.go, srv_cmd);
                     }
                 } else {
@@ -452,7 +462,7 @@ __device__ __forceinline__ void warp_body(const DevState& s, const StepCfg& c, c
             if (io.actions != nullptr) {
                 if (SRV) {
                     action = valid_env ? __ldcg(&io.actions[env]) : -1;  // HBM copy, rewritten every step (L2, not L1)
-                    if (srv.delta) srv_want_full = __ldcg(&io.actions[((s.N + 3) >> 2) << 2]);  // (needed after the step: the load is hidden)
+                    if (srv.delta) srv_want_full = __ldcg(&io.actions[24 * srv_action_chunks(s.N)]);  // (needed after the step: the load is hidden)
                 }
                 else action = valid_env ? io.actions[(size_t)k * s.N + env] : -1;
             } else if (MLP) {
