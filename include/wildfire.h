@@ -165,7 +165,8 @@ int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32
                  double* reward_host, uint8_t* done_host);
 /* Step-server session for wf_step_host (grids up to 32x32, uint8 observations).  While a session is on, the step kernel
  * stays RESIDENT on the GPU (a cooperative launch) with every env in registers and is driven through mapped page-locked
- * memory: wf_step_host writes the actions, tagged with the step's sequence number, into a mapped buffer that CTA 0 polls;
+ * memory: wf_step_host writes the actions, packed six per word and tagged with the step's sequence number, into a mapped
+ * buffer that CTA 0 polls;
  * CTA 0 copies them into HBM and releases the other CTAs; every CTA steps its envs and stores its records -- the observation bit
  * stream plus one status word per record (reward kind, done, burn-out count) -- straight into mapped host memory; the
  * last CTA to finish issues a system-scope fence and raises the completion flag; the library's host threads then expand
