@@ -19,18 +19,19 @@ struct MlpPolicy {
 // Step-server session (wf_host_session): the warp kernel stays resident and is driven from the host through
 // flags in mapped page-locked memory -- no launch and no stream synchronise per step.
 struct SrvCtl {
-    volatile uint32_t* doorbell;  // mapped host, host -> GPU: sequence number of the step requested (0xffffffff: park)
+    volatile uint32_t* doorbell;  // mapped host, host -> GPU: sequence number of the last step requested; 0xffffffff: park (the
+                                  // request itself is the tagged action buffer)
     volatile uint32_t* parked;    // mapped host, GPU -> host: the launch's generation, once the kernel has decided to exit
     volatile uint32_t* done;      // mapped host, GPU -> host: [slices] flags 16 words apart = sequence number completed
-    const int32_t* actions_host;  // mapped host [N, padded to 4]: written by wf_step_host before it rings
-    int32_t* actions_dev;         // HBM [N, padded to 4]: CTA 0's copy of it, what the warps read (WarpIO::actions)
+    const int32_t* actions_host;  // mapped host [srv_action_chunks(N) * 4] words: the step's actions, packed and tagged (wf_common.cuh)
+    int32_t* actions_dev;         // HBM [24 * srv_action_chunks(N) + 4]: CTA 0's unpacked copy, what the warps read (WarpIO::actions)
     uint32_t* go;                 // device: master CTA -> every CTA: index of the step to run (1, 2, ...), 0xffffffff = exit
     uint32_t* count;              // device: [slices] arrival counters
     uint32_t seq0, generation;    // sequence number already processed when the kernel starts; id of this launch
     int32_t ctas_per_slice;
     int32_t sectors;              // != 0: records travel as self-validating 32-byte sectors (wf_common.cuh), no flags / fences
     int32_t delta;                // != 0: change-list blocks (wf_common.cuh; WarpIO::obs = [CTAs][kDeltaBlockWords]); a warp whose
-                                  // envs changed in more than kDeltaEntries elements -- or when the host asks for it (bit 30 of
+                                  // envs changed in more than kDeltaEntries elements -- or when the host asks for it (bit 31 of
                                   // the action tags), or on the launch's first step -- sends its whole bit stream to full_area
     uint32_t* full_area;          // mapped host [records][full_stride] words
     int32_t full_stride;          // words between two records of full_area (a multiple of 4)
