@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WF_ABI_VERSION 2 /* 2: + wf_reset_host, wf_host_session(_active), wf_get/set_a_iter, wf_tile_geometry (additions only) */
+#define WF_ABI_VERSION 2 /* 2: + wf_reset_host, wf_host_session(_active), wf_get/set_a_iter, wf_tile_geometry, wf_apply_change_blocks (additions only) */
 
 enum {
     WF_OK = 0,
@@ -202,6 +202,16 @@ int wf_host_threads(const wf_env* env);
  * record = element k of the group's [e][W][H][3] block -- into uint8 obs_host[n_envs][W][H][3]. */
 int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t n_envs, int32_t width,
                          int32_t height, int32_t threads);
+/* The host half of wf_host_session mode 2 on its own (no GPU needed): apply one step's change-list blocks to obs_host.
+ * blocks_host: one block of 32 words per 4 records (a record = e consecutive envs as in wf_expand_packed_obs): word 0 =
+ * number of entries | mask of the records sent in full << 8; words 1-4 = the records' status words (16 bits per env:
+ * bits 0-2 reward kind -- 0 zero, 1 default, 2 death, 3 containment, 4 burn-out = contained_bonus * (count / (W * H)) --
+ * bit 3 done, bits 4-14 the burn-out's grass count); then 16-bit entries (element index within the block's envs << 1 |
+ * new value).  A record flagged in the mask is taken whole from full_area_host[record * full_stride] (packed as for
+ * wf_expand_packed_obs).  reward_host / done_host [n_envs] may be NULL. */
+int wf_apply_change_blocks(const uint32_t* blocks_host, const uint32_t* full_area_host, int32_t full_stride, uint8_t* obs_host,
+                           double* reward_host, uint8_t* done_host, int32_t n_envs, int32_t width, int32_t height,
+                           double default_reward, double death_penalty, double contained_bonus, int32_t threads);
 
 /* ---- state access (parity injection, checkpointing) --------------------------------
  * Canonical planes, device pointers, any may be NULL:

@@ -107,6 +107,9 @@ def lib():
     L.wf_host_threads.restype = C.c_int
     L.wf_expand_packed_obs.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.wf_expand_packed_obs.restype = C.c_int
+    L.wf_apply_change_blocks.argtypes = [vp, vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                         C.c_double, C.c_int32]
+    L.wf_apply_change_blocks.restype = C.c_int
     L.wf_state_bytes_per_env.argtypes = [vp]
     L.wf_state_bytes_per_env.restype = C.c_int64
     for name in ("wf_create", "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state",
@@ -125,5 +128,5 @@ EXPORTED_SYMBOLS = [
     "wf_default_config", "wf_create", "wf_destroy", "wf_last_error", "wf_abi_version", "wf_kernel_family",
     "wf_reset", "wf_step", "wf_rollout", "wf_rollout_policy", "wf_set_policy_mlp", "wf_step_host", "wf_get_state", "wf_set_state", "wf_set_fire_to",
     "wf_get_obs", "wf_get_wind_table", "wf_stats", "wf_stats_reset", "wf_philox_kat", "wf_launch_count",
-    "wf_state_bytes_per_env", "wf_host_threads", "wf_expand_packed_obs", "wf_get_a_iter", "wf_set_a_iter", "wf_reset_host", "wf_tile_geometry", "wf_host_session", "wf_host_session_active",
+    "wf_state_bytes_per_env", "wf_host_threads", "wf_expand_packed_obs", "wf_apply_change_blocks", "wf_get_a_iter", "wf_set_a_iter", "wf_reset_host", "wf_tile_geometry", "wf_host_session", "wf_host_session_active",
 ]

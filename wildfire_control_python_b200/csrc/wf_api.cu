@@ -488,6 +488,23 @@ int wf_expand_packed_obs(const uint32_t* packed_host, uint8_t* obs_host, int32_t
     hostpool_destroy(p);
     return WF_OK;
 }
+int wf_apply_change_blocks(const uint32_t* blocks_host, const uint32_t* full_area_host, int32_t full_stride, uint8_t* obs_host,
+                           double* reward_host, uint8_t* done_host, int32_t n_envs, int32_t width, int32_t height,
+                           double default_reward, double death_penalty, double contained_bonus, int32_t threads) {
+    if (!blocks_host || !full_area_host || !obs_host || n_envs < 1 || width < 1 || height < 1 || width > 32 || height > 32 ||
+        threads < 1 || full_stride < 1)
+        return fail(WF_ERR_INVALID, "wf_apply_change_blocks: bad argument");
+    const int epw = width <= 16 ? 2 : 1;
+    const int64_t env_bits = (int64_t)width * height * 3, records = (n_envs + epw - 1) / epw, rec_words = (epw * env_bits + 31) / 32;
+    if (full_stride < rec_words) return fail(WF_ERR_INVALID, "wf_apply_change_blocks: full_stride is smaller than a record");
+    alignas(64) static const volatile uint32_t flag[16] = {1u};  // "the step is complete"
+    HostPool* p = hostpool_create(threads);
+    const bool ok = hostpool_expand_session(p, blocks_host, obs_host, records, rec_words, env_bits, epw, n_envs, flag, 1u, records,
+                                            reward_host, done_host, default_reward, death_penalty, contained_bonus,
+                                            (double)(width * height), 1000000000, 0, full_area_host, full_stride);
+    hostpool_destroy(p);
+    return ok ? WF_OK : fail(WF_ERR_STATE, "wf_apply_change_blocks: timed out");
+}
 int64_t wf_state_bytes_per_env(const wf_env* e) {
     if (!e) return 0;
     const DevState& s = e->st;
