@@ -442,11 +442,13 @@ void wf_destroy(wf_env* e) {
         if (e->sess.dbg_dev) cudaMemcpy(d, e->sess.dbg_dev, sizeof(d), cudaMemcpyDeviceToHost);
         const double n = d[3] ? (double)d[3] : 1.0;
         fprintf(stderr, "wf_host_session: %lld steps in %lld launches of the step server (%lld park/ring races); host ring->expanded "
-                        "%.2f us (first flag after %.2f us); CTA 0 per step: doorbell wait %.2f us, action copy %.2f us, step %.2f us, CTA barrier "
-                        "%.2f us, block store + arrive %.2f us; system fence + flag of a slice's last CTA %.2f us\n",
+                        "%.2f us (first flag after %.2f us); CTA 0 per step: wait for the tagged actions (idle time included) %.2f us, fence + release "
+                        "%.2f us, step %.2f us, CTA barrier %.2f us, block store + arrive %.2f us; system fence + flag of a slice's last CTA "
+                        "%.2f us; steps that asked for every record in full (mode 2): %lld\n",
                 (long long)e->sess.steps, (long long)e->sess.launches, (long long)e->sess.relaunch_races,
                 1e6 * e->sess.t_wait / (double)e->sess.steps, 1e6 * hostpool_first_flag_seconds(e->pool) / (double)e->sess.steps,
-                d[0] / n / 1e3, d[7] / n / 1e3, d[1] / n / 1e3, d[2] / n / 1e3, d[4] / n / 1e3, d[6] ? d[5] / (double)d[6] / 1e3 : 0.0);
+                d[0] / n / 1e3, d[7] / n / 1e3, d[1] / n / 1e3, d[2] / n / 1e3, d[4] / n / 1e3, d[6] ? d[5] / (double)d[6] / 1e3 : 0.0,
+                (long long)e->sess.full_frames);
     }
     cudaFree(e->sess.dbg_dev);
     if (e->tstate) tile_destroy(e->tstate);
