@@ -175,7 +175,7 @@ int wf_step_host(wf_env* env, const int32_t* actions_host, void* obs_host, int32
  *   wf_host_session(env, 1)  turn it on (the kernel is started by the next wf_step_host);  (env, 0) park it.
  * Any other entry point on the handle (wf_reset, wf_step, wf_get_state, ...) parks the kernel first -- it stores the
  * envs back to HBM and exits -- and the next wf_step_host starts it again, so results never depend on the session.
- * A kernel that sees no doorbell for WF_SESSION_IDLE_US (default 2000) microseconds parks itself: the GPU is not held
+ * A kernel that sees no step request for WF_SESSION_IDLE_US (default 2000) microseconds parks itself: the GPU is not held
  * hostage by a caller that stops stepping (other work on the device is delayed by at most that long).
  * A batch with more CTAs (8 envs of <= 16 rows, 4 of up to 32 rows, each) than the GPU can hold resident cannot be
  * served: the first wf_step_host then turns the session off and the launch-per-step path takes over.
